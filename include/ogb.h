@@ -1,0 +1,220 @@
+/*
+ * ogb.h -- C ABI of the B200 overlap-graph builder (libogb.so).
+ *
+ * The reference (abiswas-odu/metagenomics) has no plugin / FFI interface; its boundary for the
+ * overlap-graph build is the C++ class API used at one call site (MetaGenomics/main.cpp:33,45-47):
+ *
+ *     Dataset *dataSet = new Dataset(pairedEndFileNames, singleEndFileNames, minimumOverlapLength);
+ *     HashTable *hashTable = new HashTable();
+ *     hashTable->insertDataset(dataSet, minimumOverlapLength);
+ *     overlapGraph = new OverlapGraph(hashTable);
+ *
+ * metagenomics_b200/host/ re-implements those classes (same names, signatures and post-conditions)
+ * on top of the entry points below; INTEGRATION.md shows the binding. Every entry point cites the
+ * reference interface it replaces (file:line relative to MetaGenomics/).
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success or a non-zero
+ * OGB_E_* code (text via ogb_last_error(), thread local); nothing calls exit(); read IDs are
+ * 1-based like the reference's (Dataset.cpp:335-341); all device work is CUDA for sm_100a -- there
+ * is no CPU fallback: device entry points fail with OGB_E_CUDA when no GPU is usable.
+ */
+#ifndef OGB_H_
+#define OGB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OGB_VERSION 100
+
+enum {
+	OGB_OK = 0,
+	OGB_E_ARG = 1,      /* bad argument */
+	OGB_E_CUDA = 2,     /* CUDA runtime / no device */
+	OGB_E_NCCL = 3,     /* NCCL */
+	OGB_E_STATE = 4,    /* call order (e.g. build before upload) */
+	OGB_E_CAPACITY = 5, /* output buffer too small / internal capacity exceeded */
+	OGB_E_IO = 6,       /* file could not be read */
+	OGB_E_NOMEM = 7
+};
+
+typedef struct ogb_dataset ogb_dataset; /* host: filtered, canonical, sorted, unique reads */
+typedef struct ogb_context ogb_context; /* device: one GPU (one rank) */
+
+/* One directed overlap edge, the flat form of the reference's Edge record (Edge.h:17-44):
+ * source / destination read IDs, overlapOrientation 0..3 and overlapOffset (UINT16 at creation,
+ * OverlapGraph.cpp:407,410). */
+typedef struct ogb_edge {
+	uint32_t src;
+	uint32_t dst;
+	uint16_t offset;
+	uint8_t orient;
+	uint8_t reserved;
+} ogb_edge; /* 12 bytes */
+
+/* Counters and device timings of the last build (CUDA events on the context's stream). */
+typedef struct ogb_stats {
+	uint64_t n_reads;          /* unique reads resident on the device */
+	uint64_t table_buckets;    /* index size in buckets */
+	uint64_t table_bytes;
+	uint64_t n_contained;      /* reads with superReadID != 0 */
+	uint64_t contain_probes;   /* P_c  windows scanned by the containment pass (0 if skipped) */
+	uint64_t contain_hits;     /* C_c  verified containment hits */
+	uint64_t overlap_probes;   /* P_e  windows scanned by the overlap pass (this rank) */
+	uint64_t probe_sectors;    /* index buckets (32 B sectors) actually loaded by the overlap pass */
+	uint64_t candidates;       /* fingerprint matches sent to verification */
+	uint64_t edges_pre;        /* E_pre  directed edges before reduction (global) */
+	uint64_t edges_pre_local;  /* emitted by this rank */
+	uint64_t pivot_entries;    /* T  adjacency entries scanned by active pivots (this rank) */
+	uint64_t active_pivots;
+	uint64_t edges_final;      /* E_final directed edges after reduction (global) */
+	uint64_t nodes_final;      /* numberOfNodes (reads with >= 1 surviving edge) */
+	uint64_t max_degree;       /* largest pre-reduction out-degree (this rank) */
+	uint64_t overflow_reads;   /* reads that took the large-degree slow path */
+	uint32_t kernel_launches;  /* kernels of this library launched by the last hash_build+build_graph */
+	uint32_t reserved;
+	float ms_pack;             /* K0 */
+	float ms_hash_build;       /* K1 */
+	float ms_contain;          /* K2 (+ allreduce) */
+	float ms_overlap;          /* K3 (+K4: per-node sort fused) */
+	float ms_exchange_pre;     /* C1 allgatherv of pre-reduction edges (0 on one GPU) */
+	float ms_mark;             /* K5 */
+	float ms_reduce;           /* K6 (+C2/C3) */
+	float ms_total;            /* hash_build + mark_contained + build_graph, device time */
+} ogb_stats;
+
+int ogb_version(void);
+const char *ogb_last_error(void);
+
+/* ----------------------------------------------------------------------------------------------
+ * Host side: the Dataset stage that defines read IDs (adjacent to the hot path).
+ * -------------------------------------------------------------------------------------------- */
+
+/* Dataset::Dataset() (Dataset.cpp:24-33). */
+int ogb_dataset_create(ogb_dataset **out);
+void ogb_dataset_destroy(ogb_dataset *ds);
+
+/* Dataset::readDataset (Dataset.cpp:110-193) for in-memory reads: n ASCII reads, read i =
+ * bases[offsets[i] .. offsets[i+1]). Case is folded like :155-156. Reads are only collected here;
+ * filtering happens in ogb_dataset_finalize because it needs minOverlap. */
+int ogb_dataset_add_reads(ogb_dataset *ds, const char *bases, const uint64_t *offsets, uint64_t n);
+
+/* Dataset::readDataset (Dataset.cpp:110-193) for a FASTA ('>') or FASTQ ('@') file; multi-line
+ * FASTA records are joined (:145). */
+int ogb_dataset_add_file(ogb_dataset *ds, const char *path);
+
+/* The rest of Dataset::Dataset(pe, se, minOverlap) (Dataset.cpp:39-65): keep reads with
+ * length > minOverlap made of ACGT only and with no base count >= (UINT64)(len*.8)
+ * (:158, testRead :398-413); store the lexicographically smaller of read / reverse complement
+ * (:161-164); sort lexicographically, shorter prefix first (sortReads :197-202); merge equal reads
+ * counting frequency and assign ID = rank+1 (removeDupicateReads :316-345). */
+int ogb_dataset_finalize(ogb_dataset *ds, uint32_t min_overlap);
+
+uint64_t ogb_dataset_n_reads(const ogb_dataset *ds);   /* Dataset::getNumberOfReads (:352): good reads */
+uint64_t ogb_dataset_n_unique(const ogb_dataset *ds);  /* Dataset::getNumberOfUniqueReads (:361) */
+uint64_t ogb_dataset_shortest(const ogb_dataset *ds);  /* Dataset::shortestReadLength (Dataset.h:36) */
+uint64_t ogb_dataset_longest(const ogb_dataset *ds);   /* Dataset::longestReadLength  (Dataset.h:37) */
+uint32_t ogb_dataset_min_overlap(const ogb_dataset *ds);
+
+/* Packed form handed to the device: read id (1-based) occupies words
+ * [word_offsets[id-1], word_offsets[id-1] + ceil(len/32)) of `words`; base k of the read sits in
+ * bits 63-2*(k%32) .. 62-2*(k%32) of word k/32 (A=0 C=1 G=2 T=3, unused low bits zero). */
+const uint64_t *ogb_dataset_words(const ogb_dataset *ds, uint64_t *n_words);
+const uint64_t *ogb_dataset_word_offsets(const ogb_dataset *ds); /* n_unique + 1 entries */
+const uint16_t *ogb_dataset_lengths(const ogb_dataset *ds);      /* n_unique entries (Read::getReadLength) */
+const uint32_t *ogb_dataset_frequencies(const ogb_dataset *ds);  /* n_unique entries (Read::getFrequency) */
+
+/* Read::getStringForward / getStringReverse (Read.h:58-59) of Dataset::getReadFromID(id)
+ * (Dataset.cpp:482-492). strand 0 = forward, 1 = reverse complement. out holds >= len bytes. */
+int ogb_dataset_get_read(const ogb_dataset *ds, uint64_t id, int strand, char *out, uint32_t cap, uint32_t *len);
+
+/* Dataset::getReadFromString (Dataset.cpp:421-455): binary search of min(read, rc); *id = 0 if
+ * the string is not in the dataset (the reference exits there). */
+int ogb_dataset_find_read(const ogb_dataset *ds, const char *bases, uint32_t len, uint64_t *id);
+
+/* ----------------------------------------------------------------------------------------------
+ * Device side.
+ * -------------------------------------------------------------------------------------------- */
+
+/* One context per process and GPU. Single-GPU: rank 0 of 1. */
+int ogb_context_create(ogb_context **out, int device);
+
+/* Multi-GPU (one process per GPU): `nccl_uid` is the 128-byte ncclUniqueId made by
+ * ogb_nccl_unique_id on rank 0 and distributed by the caller (torch.distributed store, MPI, ...). */
+int ogb_nccl_unique_id(void *out128);
+int ogb_context_create_dist(ogb_context **out, int device, int rank, int n_ranks, const void *nccl_uid);
+void ogb_context_destroy(ogb_context *ctx);
+int ogb_context_rank(const ogb_context *ctx, int *rank, int *n_ranks);
+
+/* Read storage (Read::setRead + Read::reverseComplement, Read.cpp:75-82,115-127): copies the n
+ * sorted unique reads to the device and runs K0, which 2-bit packs forward strands (ASCII variant)
+ * and writes the reverse complements. IDs = index + 1. Replaces any previous upload. */
+int ogb_reads_upload(ogb_context *ctx, const char *bases, const uint64_t *offsets, uint64_t n);
+int ogb_reads_upload_packed(ogb_context *ctx, const uint64_t *words, const uint64_t *word_offsets,
+                            const uint16_t *lengths, uint64_t n);
+int ogb_reads_upload_dataset(ogb_context *ctx, const ogb_dataset *ds);
+
+/* HashTable::insertDataset(Dataset*, minOverlapLength) (HashTable.cpp:50-80): hashStringLength =
+ * minOverlap-1 (:54); 4 keys per read -- prefix/suffix of forward and of reverse complement
+ * (hashRead :88-104) -- inserted by K1 into an open-addressing table of 32-byte buckets. */
+int ogb_hash_build(ogb_context *ctx, uint32_t min_overlap);
+
+/* HashTable::getListOfReads(string) (HashTable.cpp:202-221) for n_keys keys of hashStringLength
+ * bases each (keys concatenated, ASCII). Returns for key k the entries (id | orientation<<62,
+ * HashTable.cpp:165) in out[out_offsets[k] .. out_offsets[k+1]), ascending id then orientation
+ * (the reference's insertion order). out_offsets has n_keys+1 entries. */
+int ogb_hash_lookup(ogb_context *ctx, const char *keys, uint64_t n_keys, uint64_t *out, uint64_t out_cap,
+                    uint64_t *out_offsets);
+uint64_t ogb_hash_string_length(const ogb_context *ctx); /* HashTable::getHashStringLength (HashTable.h:34) */
+uint64_t ogb_hash_table_size(const ogb_context *ctx);    /* HashTable::getHashTableSize (HashTable.h:33): slots */
+
+/* OverlapGraph::markContainedReads (OverlapGraph.cpp:225-290) with checkOverlapForContainedRead
+ * (:302-340): K2. No-op when all reads have one length (:228). */
+int ogb_mark_contained(ogb_context *ctx);
+/* Read::superReadID (Read.h:50) for ids 0..n (entry 0 unused, = 0). */
+int ogb_super_read_ids(ogb_context *ctx, uint64_t *out, uint64_t cap);
+
+/* OverlapGraph::buildOverlapGraphFromHashTable (OverlapGraph.cpp:107-210, up to `delete hashTable`)
+ * minus markContainedReads/readMatePairsFromFile: insertAllEdgesOfRead + checkOverlap (K3, :354-383,
+ * :529-565), per-node sort by offset (:563), markTransitiveEdges (K5, :574-615),
+ * removeTransitiveEdges (K6, :623-661) and, on several ranks, the edge exchanges. The result stays
+ * on the device until ogb_graph_edges. keep_pre != 0 keeps the pre-reduction edge list readable. */
+int ogb_build_graph(ogb_context *ctx, int keep_pre);
+
+/* Number of directed edges in the graph: which = 0 post-reduction (OverlapGraph::getNumberOfEdges,
+ * OverlapGraph.h:76), 1 pre-reduction (needs keep_pre). */
+int ogb_graph_edge_count(ogb_context *ctx, int which, uint64_t *n);
+/* Copies the edges, sorted by (src, offset, dst, orient), to host memory. */
+int ogb_graph_edges(ogb_context *ctx, int which, ogb_edge *out, uint64_t cap);
+
+int ogb_get_stats(ogb_context *ctx, ogb_stats *out);
+
+/* Pinned host memory for upload/download staging (released by ogb_free_host). */
+int ogb_alloc_host(void **out, size_t bytes);
+void ogb_free_host(void *p);
+
+/* ----------------------------------------------------------------------------------------------
+ * Synthetic read generator used by bench.py and the tests (seeded, host only). Not part of the
+ * reference; SURVEY.md 8(d) defines the five configurations.
+ * -------------------------------------------------------------------------------------------- */
+
+/* Uniform i.i.d. ACGT genome of `len` bases. */
+int ogb_synth_genome(uint64_t seed, uint64_t len, char *out);
+
+/* Samples n_reads error-free reads from the concatenated genomes (genome g =
+ * genomes[g_offsets[g] .. g_offsets[g+1]), picked with probability weights[g]*len). Read length is
+ * uniform in [len_min, len_max]; strand flipped with p = 0.5. paired != 0: reads come in pairs
+ * (2i, 2i+1), mate 2 = reverse complement of the far end of a fragment ~ N(insert_mean, insert_sd)
+ * clipped to >= 2*len. Output: bases (concatenated) + offsets (n_reads + 1). */
+int ogb_synth_reads(uint64_t seed, const char *genomes, const uint64_t *g_offsets, const double *weights,
+                    uint32_t n_genomes, uint64_t n_reads, uint32_t len_min, uint32_t len_max, int paired,
+                    double insert_mean, double insert_sd, char *out_bases, uint64_t out_cap,
+                    uint64_t *out_offsets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OGB_H_ */

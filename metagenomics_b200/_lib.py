@@ -1,0 +1,103 @@
+"""ctypes binding of libogb.so (include/ogb.h). There is no fallback: a missing library raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libogb.so")
+
+OGB_OK, OGB_E_ARG, OGB_E_CUDA, OGB_E_NCCL, OGB_E_STATE, OGB_E_CAPACITY, OGB_E_IO, OGB_E_NOMEM = range(8)
+
+
+class OgbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libogb error {code}: {msg}")
+        self.code = code
+
+
+class Edge(C.Structure):
+    """ogb_edge (include/ogb.h) = flat form of the reference Edge record (Edge.h:17-44)."""
+    _fields_ = [("src", C.c_uint32), ("dst", C.c_uint32), ("offset", C.c_uint16), ("orient", C.c_uint8),
+                ("reserved", C.c_uint8)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "n_reads", "table_buckets", "table_bytes", "n_contained", "contain_probes", "contain_hits",
+        "overlap_probes", "probe_sectors", "candidates", "edges_pre", "edges_pre_local", "pivot_entries",
+        "active_pivots", "edges_final", "nodes_final", "max_degree", "overflow_reads")] + [
+        ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)] + [(n, C.c_float) for n in (
+            "ms_pack", "ms_hash_build", "ms_contain", "ms_overlap", "ms_exchange_pre", "ms_mark", "ms_reduce",
+            "ms_total")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+# every symbol include/ogb.h declares: name -> (restype, argtypes)
+_u64p = C.POINTER(C.c_uint64)
+_vp = C.c_void_p
+PROTOTYPES = {
+    "ogb_version": (C.c_int, []),
+    "ogb_last_error": (C.c_char_p, []),
+    "ogb_dataset_create": (C.c_int, [C.POINTER(_vp)]),
+    "ogb_dataset_destroy": (None, [_vp]),
+    "ogb_dataset_add_reads": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
+    "ogb_dataset_add_file": (C.c_int, [_vp, C.c_char_p]),
+    "ogb_dataset_finalize": (C.c_int, [_vp, C.c_uint32]),
+    "ogb_dataset_n_reads": (C.c_uint64, [_vp]),
+    "ogb_dataset_n_unique": (C.c_uint64, [_vp]),
+    "ogb_dataset_shortest": (C.c_uint64, [_vp]),
+    "ogb_dataset_longest": (C.c_uint64, [_vp]),
+    "ogb_dataset_min_overlap": (C.c_uint32, [_vp]),
+    "ogb_dataset_words": (_vp, [_vp, _u64p]),
+    "ogb_dataset_word_offsets": (_vp, [_vp]),
+    "ogb_dataset_lengths": (_vp, [_vp]),
+    "ogb_dataset_frequencies": (_vp, [_vp]),
+    "ogb_dataset_get_read": (C.c_int, [_vp, C.c_uint64, C.c_int, _vp, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "ogb_dataset_find_read": (C.c_int, [_vp, C.c_char_p, C.c_uint32, _u64p]),
+    "ogb_context_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "ogb_nccl_unique_id": (C.c_int, [_vp]),
+    "ogb_context_create_dist": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _vp]),
+    "ogb_context_destroy": (None, [_vp]),
+    "ogb_context_rank": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ogb_reads_upload": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
+    "ogb_reads_upload_packed": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64]),
+    "ogb_reads_upload_dataset": (C.c_int, [_vp, _vp]),
+    "ogb_hash_build": (C.c_int, [_vp, C.c_uint32]),
+    "ogb_hash_lookup": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp]),
+    "ogb_hash_string_length": (C.c_uint64, [_vp]),
+    "ogb_hash_table_size": (C.c_uint64, [_vp]),
+    "ogb_mark_contained": (C.c_int, [_vp]),
+    "ogb_super_read_ids": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "ogb_build_graph": (C.c_int, [_vp, C.c_int]),
+    "ogb_graph_edge_count": (C.c_int, [_vp, C.c_int, _u64p]),
+    "ogb_graph_edges": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
+    "ogb_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "ogb_alloc_host": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
+    "ogb_free_host": (None, [_vp]),
+    "ogb_synth_genome": (C.c_int, [C.c_uint64, C.c_uint64, _vp]),
+    "ogb_synth_reads": (C.c_int, [C.c_uint64, _vp, _vp, _vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int,
+                                  C.c_double, C.c_double, _vp, C.c_uint64, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads libogb.so (built in-tree by __graft_entry__.build() / csrc/Makefile)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OgbError(-1, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in PROTOTYPES.items():
+            f = getattr(l, name)  # AttributeError if the library does not export a declared symbol
+            f.restype, f.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != OGB_OK:
+        raise OgbError(rc, lib().ogb_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,749 @@
+// ogb_device.cu -- device half of libogb.so: context, HBM pools, kernel orchestration and the
+// extern "C" entry points declared in include/ogb.h. One context = one GPU = one rank.
+//
+// Orchestration of one build (reference call sites in brackets):
+//   ogb_reads_upload*   H2D + K0                         [Read::setRead, Read.cpp:75-82]
+//   ogb_hash_build      K1                               [HashTable::insertDataset, HashTable.cpp:50-80]
+//   ogb_mark_contained  K2 (+ allreduce-max)             [OverlapGraph::markContainedReads, OverlapGraph.cpp:225-290]
+//   ogb_build_graph     K3 (+big) -> C1 -> K5 -> C2 -> K6 -> C3   [buildOverlapGraphFromHashTable, OverlapGraph.cpp:107-210]
+// All buffers are grow-only pools owned by the context, so a repeated build allocates nothing.
+
+#include "ogb_internal.h"
+#include "ogb_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+#define CUDA_TRY(x)                                                                                      \
+	do {                                                                                                 \
+		cudaError_t e_ = (x);                                                                            \
+		if (e_ != cudaSuccess) {                                                                         \
+			ogb_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #x); \
+			return OGB_E_CUDA;                                                                           \
+		}                                                                                                \
+	} while (0)
+#define OGB_TRY(x) do { int r_ = (x); if (r_ != OGB_OK) return r_; } while (0)
+
+// ---- NCCL through dlopen: no link-time dependency, and inside a torch process the already loaded
+// libnccl.so.2 (torch's bundled one) is reused instead of a second copy.
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { NCCL_UINT8 = 1, NCCL_UINT32 = 3, NCCL_UINT64 = 5 };   // ncclDataType_t values (nccl.h)
+enum { NCCL_MAX = 2 };                                         // ncclRedOp_t
+struct NcclApi {
+	void *lib = nullptr;
+	int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	int (*CommDestroy)(ncclComm_t) = nullptr;
+	int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load()
+{
+	if (g_nccl.lib) return OGB_OK;
+	void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!lib) { ogb_set_error("cannot load libnccl.so.2: %s", dlerror()); return OGB_E_NCCL; }
+#define SYM(field, name) *(void **)(&g_nccl.field) = dlsym(lib, name); if (!g_nccl.field) { ogb_set_error("libnccl: missing %s", name); return OGB_E_NCCL; }
+	SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+	SYM(AllGather, "ncclAllGather") SYM(AllReduce, "ncclAllReduce") SYM(Broadcast, "ncclBroadcast")
+	SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+	g_nccl.lib = lib;
+	return OGB_OK;
+}
+#define NCCL_TRY(x)                                                                                   \
+	do {                                                                                              \
+		int r_ = (x);                                                                                 \
+		if (r_ != 0) { ogb_set_error("NCCL error %s at %s:%d", g_nccl.GetErrorString(r_), __FILE__, __LINE__); return OGB_E_NCCL; } \
+	} while (0)
+
+template <class T> struct Pool {
+	T *p = nullptr;
+	size_t cap = 0;   // elements
+	int ensure(size_t need)
+	{
+		if (need <= cap) return OGB_OK;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		cudaError_t e = cudaMalloc((void **)&p, need * sizeof(T));
+		if (e != cudaSuccess) { ogb_set_error("cudaMalloc of %zu bytes failed: %s", need * sizeof(T), cudaGetErrorString(e)); return OGB_E_NOMEM; }
+		cap = need;
+		return OGB_OK;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+enum { EV_BEGIN = 0, EV_PACK0, EV_PACK1, EV_HASH0, EV_HASH1, EV_CONT0, EV_CONT1, EV_OVL0, EV_OVL1, EV_XPRE1, EV_MARK1, EV_RED1, EV_COUNT };
+
+struct ogb_context {
+	int device = 0, rank = 0, nranks = 1, sm_count = 148;
+	cudaStream_t stream = nullptr;
+	ncclComm_t comm = nullptr;
+	cudaEvent_t ev[EV_COUNT] = {};
+	// packed reads
+	Pool<u64> words, meta;
+	Pool<char> stage_bytes;          // upload staging (ASCII bases / tight words)
+	Pool<u64> stage_offs;
+	Pool<unsigned short> stage_lens;
+	u32 n = 0, uniform_len = 0, uniform_pw = 0, min_len = 0, max_len = 0;
+	bool have_reads = false;
+	// index
+	Pool<u64> slots;
+	u32 nb = 0, h = 0;
+	bool have_table = false;
+	// containment
+	Pool<u64> sup;
+	Pool<u32> contained;
+	bool contain_done = false, any_contained = false;
+	// graph
+	Pool<u64> nodes, edges, pos, sums;
+	Pool<unsigned char> eflag, keep, scratch_state;
+	Pool<u32> cnt, overflow, scratch_keys;
+	Pool<ogb_edge> fin, pre;
+	u64 n_final = 0, n_pre = 0;
+	bool have_graph = false, have_pre = false;
+	u64 *d_ctr = nullptr, *h_ctr = nullptr;
+	ogb_stats st = {};
+	u32 launches = 0;
+
+	ReadStore rs() const { ReadStore r; r.words = words.p; r.meta = uniform_len ? nullptr : meta.p; r.n = n; r.uniform_len = uniform_len; r.uniform_pw = uniform_pw; return r; }
+	Table tb() const { Table t; t.slots = slots.p; t.nb = nb; t.h = h; return t; }
+	void shard(u32 &lo, u32 &hi) const
+	{
+		u64 per = ((u64)n + nranks - 1) / nranks;
+		lo = (u32)std::min<u64>(n, per * rank);
+		hi = (u32)std::min<u64>(n, per * (rank + 1));
+	}
+};
+
+static int ctr_zero(ogb_context *c) { CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, CTR_COUNT * sizeof(u64), c->stream)); return OGB_OK; }
+static int ctr_fetch(ogb_context *c)
+{
+	CUDA_TRY(cudaMemcpyAsync(c->h_ctr, c->d_ctr, CTR_COUNT * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return OGB_OK;
+}
+static int grid_for(ogb_context *c, const void *kernel, int block)
+{
+	int per_sm = 1;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+	return c->sm_count * per_sm;
+}
+static float ev_ms(ogb_context *c, int a, int b) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) { cudaGetLastError(); return 0; } return ms; }
+
+static int context_create_common(ogb_context **out, int device)
+{
+	if (!out) { ogb_set_error("ogb_context_create: out is NULL"); return OGB_E_ARG; }
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) {
+		ogb_set_error("no usable CUDA device (%s); libogb has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+		cudaGetLastError();
+		return OGB_E_CUDA;
+	}
+	if (device < 0 || device >= count) { ogb_set_error("device %d out of range (%d devices)", device, count); return OGB_E_ARG; }
+	CUDA_TRY(cudaSetDevice(device));
+	ogb_context *c = new ogb_context();
+	c->device = device;
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+	c->sm_count = prop.multiProcessorCount;
+	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	for (int i = 0; i < EV_COUNT; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
+	CUDA_TRY(cudaMalloc((void **)&c->d_ctr, CTR_COUNT * sizeof(u64)));
+	CUDA_TRY(cudaMallocHost((void **)&c->h_ctr, CTR_COUNT * sizeof(u64)));
+	CUDA_TRY(cudaMemset(c->d_ctr, 0, CTR_COUNT * sizeof(u64)));
+	*out = c;
+	return OGB_OK;
+}
+
+extern "C" int ogb_context_create(ogb_context **out, int device) { return context_create_common(out, device); }
+
+extern "C" int ogb_nccl_unique_id(void *out128)
+{
+	if (!out128) { ogb_set_error("ogb_nccl_unique_id: NULL output"); return OGB_E_ARG; }
+	OGB_TRY(nccl_load());
+	ncclUniqueId id;
+	NCCL_TRY(g_nccl.GetUniqueId(&id));
+	memcpy(out128, &id, sizeof id);
+	return OGB_OK;
+}
+
+extern "C" int ogb_context_create_dist(ogb_context **out, int device, int rank, int n_ranks, const void *nccl_uid)
+{
+	if (n_ranks < 1 || rank < 0 || rank >= n_ranks) { ogb_set_error("ogb_context_create_dist: bad rank %d of %d", rank, n_ranks); return OGB_E_ARG; }
+	OGB_TRY(context_create_common(out, device));
+	ogb_context *c = *out;
+	c->rank = rank; c->nranks = n_ranks;
+	if (n_ranks > 1) {
+		if (!nccl_uid) { ogb_set_error("ogb_context_create_dist: NULL nccl id"); return OGB_E_ARG; }
+		OGB_TRY(nccl_load());
+		ncclUniqueId id;
+		memcpy(&id, nccl_uid, sizeof id);
+		NCCL_TRY(g_nccl.CommInitRank(&c->comm, n_ranks, id, rank));
+	}
+	return OGB_OK;
+}
+
+extern "C" void ogb_context_destroy(ogb_context *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	if (c->comm) g_nccl.CommDestroy(c->comm);
+	c->words.release(); c->meta.release(); c->stage_bytes.release(); c->stage_offs.release(); c->stage_lens.release();
+	c->slots.release(); c->sup.release(); c->contained.release(); c->nodes.release(); c->edges.release(); c->pos.release();
+	c->sums.release(); c->eflag.release(); c->keep.release(); c->scratch_state.release(); c->cnt.release(); c->overflow.release();
+	c->scratch_keys.release(); c->fin.release(); c->pre.release();
+	if (c->d_ctr) cudaFree(c->d_ctr);
+	if (c->h_ctr) cudaFreeHost(c->h_ctr);
+	for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" int ogb_context_rank(const ogb_context *c, int *rank, int *n_ranks)
+{
+	if (!c) { ogb_set_error("NULL context"); return OGB_E_ARG; }
+	if (rank) *rank = c->rank;
+	if (n_ranks) *n_ranks = c->nranks;
+	return OGB_OK;
+}
+
+extern "C" int ogb_alloc_host(void **out, size_t bytes)
+{
+	if (!out) { ogb_set_error("ogb_alloc_host: NULL output"); return OGB_E_ARG; }
+	cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+	if (e != cudaSuccess) { ogb_set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return OGB_E_CUDA; }
+	return OGB_OK;
+}
+extern "C" void ogb_free_host(void *p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------------
+// Read upload + K0
+// ------------------------------------------------------------------------------------------------
+
+// Decides the device layout from the lengths: uniform stride or per-read meta.
+static int layout_reads(ogb_context *c, const std::vector<u32> &lens, u64 &total_words, std::vector<u64> &meta_host)
+{
+	u32 n = (u32)lens.size();
+	u32 mn = 0xFFFFFFFFu, mx = 0;
+	for (u32 i = 0; i < n; i++) { mn = std::min(mn, lens[i]); mx = std::max(mx, lens[i]); }
+	c->n = n; c->min_len = n ? mn : 0; c->max_len = mx;
+	if (n && mn == mx) {
+		c->uniform_len = mx;
+		c->uniform_pw = ((mx + 63) >> 6) << 1;
+		total_words = (u64)n * 2 * c->uniform_pw;
+		meta_host.clear();
+	} else {
+		c->uniform_len = 0; c->uniform_pw = 0;
+		meta_host.resize(n);
+		u64 off = 0;
+		for (u32 i = 0; i < n; i++) {
+			if (off >= (1ull << 47)) { ogb_set_error("read store too large"); return OGB_E_CAPACITY; }
+			meta_host[i] = (off << 16) | lens[i];
+			off += 2 * (u64)(((lens[i] + 63) >> 6) << 1);
+		}
+		total_words = off;
+	}
+	return OGB_OK;
+}
+
+static int upload_common(ogb_context *c, u64 total_words, const std::vector<u64> &meta_host)
+{
+	OGB_TRY(c->words.ensure(total_words + 8));          // +8: extract32 may touch one word past a strand
+	CUDA_TRY(cudaMemsetAsync(c->words.p + total_words, 0, 8 * sizeof(u64), c->stream));
+	if (!meta_host.empty()) {
+		OGB_TRY(c->meta.ensure(meta_host.size()));
+		CUDA_TRY(cudaMemcpyAsync(c->meta.p, meta_host.data(), meta_host.size() * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+	}
+	c->have_reads = true; c->have_table = false; c->contain_done = false; c->any_contained = false; c->have_graph = false; c->have_pre = false;
+	return OGB_OK;
+}
+
+extern "C" int ogb_reads_upload(ogb_context *c, const char *bases, const uint64_t *offsets, uint64_t n)
+{
+	if (!c || (n && (!bases || !offsets))) { ogb_set_error("ogb_reads_upload: NULL argument"); return OGB_E_ARG; }
+	if (n >= (1ull << 30)) { ogb_set_error("ogb_reads_upload: at most 2^30-1 reads per context"); return OGB_E_CAPACITY; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	std::vector<u32> lens(n);
+	for (u64 i = 0; i < n; i++) {
+		u64 L = offsets[i + 1] - offsets[i];
+		if (L < 2 || L > 65535) { ogb_set_error("ogb_reads_upload: read %llu has length %llu (allowed 2..65535)", (unsigned long long)(i + 1), (unsigned long long)L); return OGB_E_ARG; }
+		lens[i] = (u32)L;
+	}
+	u64 total_words = 0;
+	std::vector<u64> meta_host;
+	OGB_TRY(layout_reads(c, lens, total_words, meta_host));
+	OGB_TRY(upload_common(c, total_words, meta_host));
+	if (n == 0) return OGB_OK;
+	u64 nbytes = offsets[n] - offsets[0];
+	OGB_TRY(c->stage_bytes.ensure(nbytes));
+	OGB_TRY(c->stage_offs.ensure(n + 1));
+	std::vector<u64> rel(n + 1);
+	for (u64 i = 0; i <= n; i++) rel[i] = offsets[i] - offsets[0];
+	CUDA_TRY(cudaEventRecord(c->ev[EV_PACK0], c->stream));
+	CUDA_TRY(cudaMemcpyAsync(c->stage_bytes.p, bases + offsets[0], nbytes, cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(c->stage_offs.p, rel.data(), (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+	u32 max_pw = ((c->max_len + 63) >> 6) << 1;
+	u64 threads = (u64)n * max_pw;
+	k_pack_ascii<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->stage_bytes.p, c->stage_offs.p, c->words.p,
+	                                                                      c->uniform_len ? nullptr : c->meta.p, (u32)n, c->uniform_len, c->uniform_pw, max_pw);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaEventRecord(c->ev[EV_PACK1], c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->st.ms_pack = ev_ms(c, EV_PACK0, EV_PACK1);
+	c->st.n_reads = n;
+	return OGB_OK;
+}
+
+extern "C" int ogb_reads_upload_packed(ogb_context *c, const uint64_t *words, const uint64_t *word_offsets, const uint16_t *lengths, uint64_t n)
+{
+	if (!c || (n && (!words || !word_offsets || !lengths))) { ogb_set_error("ogb_reads_upload_packed: NULL argument"); return OGB_E_ARG; }
+	if (n >= (1ull << 30)) { ogb_set_error("ogb_reads_upload_packed: at most 2^30-1 reads per context"); return OGB_E_CAPACITY; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	std::vector<u32> lens(n);
+	for (u64 i = 0; i < n; i++) {
+		if (lengths[i] < 2) { ogb_set_error("ogb_reads_upload_packed: read %llu shorter than 2", (unsigned long long)(i + 1)); return OGB_E_ARG; }
+		lens[i] = lengths[i];
+	}
+	u64 total_words = 0;
+	std::vector<u64> meta_host;
+	OGB_TRY(layout_reads(c, lens, total_words, meta_host));
+	OGB_TRY(upload_common(c, total_words, meta_host));
+	if (n == 0) return OGB_OK;
+	u64 in_words = word_offsets[n] - word_offsets[0];
+	OGB_TRY(c->stage_bytes.ensure(in_words * sizeof(u64)));
+	OGB_TRY(c->stage_offs.ensure(n + 1));
+	OGB_TRY(c->stage_lens.ensure(n));
+	std::vector<u64> rel;
+	const u64 *offs_src = (const u64 *)word_offsets;
+	if (word_offsets[0] != 0) { rel.resize(n + 1); for (u64 i = 0; i <= n; i++) rel[i] = word_offsets[i] - word_offsets[0]; offs_src = rel.data(); }
+	CUDA_TRY(cudaEventRecord(c->ev[EV_PACK0], c->stream));
+	CUDA_TRY(cudaMemcpyAsync(c->stage_bytes.p, words + word_offsets[0], in_words * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(c->stage_offs.p, offs_src, (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(c->stage_lens.p, lengths, n * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+	u32 max_pw = ((c->max_len + 63) >> 6) << 1;
+	u64 threads = (u64)n * max_pw;
+	k_pack_words<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>((const u64 *)c->stage_bytes.p, c->stage_offs.p, c->stage_lens.p, c->words.p,
+	                                                                      c->uniform_len ? nullptr : c->meta.p, (u32)n, c->uniform_len, c->uniform_pw, max_pw);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaEventRecord(c->ev[EV_PACK1], c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->st.ms_pack = ev_ms(c, EV_PACK0, EV_PACK1);
+	c->st.n_reads = n;
+	return OGB_OK;
+}
+
+extern "C" int ogb_reads_upload_dataset(ogb_context *c, const ogb_dataset *ds)
+{
+	if (!c || !ds) { ogb_set_error("ogb_reads_upload_dataset: NULL argument"); return OGB_E_ARG; }
+	uint64_t nw = 0;
+	const uint64_t *w = ogb_dataset_words(ds, &nw);
+	return ogb_reads_upload_packed(c, w, ogb_dataset_word_offsets(ds), ogb_dataset_lengths(ds), ogb_dataset_n_unique(ds));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1
+// ------------------------------------------------------------------------------------------------
+extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
+{
+	if (!c) { ogb_set_error("NULL context"); return OGB_E_ARG; }
+	if (!c->have_reads) { ogb_set_error("ogb_hash_build: upload reads first"); return OGB_E_STATE; }
+	if (min_overlap < 2) { ogb_set_error("ogb_hash_build: minOverlap must be >= 2"); return OGB_E_ARG; }
+	if (c->n && c->min_len <= min_overlap) { ogb_set_error("ogb_hash_build: every read must be longer than minOverlap (Dataset.cpp:158); shortest is %u", c->min_len); return OGB_E_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	c->h = min_overlap - 1;                                                 // HashTable.cpp:54
+	// The reference sizes the table at the first listed prime > 8N+1 slots (HashTable.cpp:56), i.e.
+	// load factor <= 0.5 for its 4N entries. Same load here: 2N buckets of 4 slots.
+	u64 nb = std::max<u64>(2 * (u64)c->n + 1, 1024);
+	const char *lf = getenv("OGB_TABLE_BUCKETS_PER_READ");
+	if (lf && atof(lf) >= 1.0) nb = std::max<u64>((u64)(atof(lf) * c->n) + 1, 1024);
+	if (nb >= (1ull << 32)) { ogb_set_error("index too large"); return OGB_E_CAPACITY; }
+	c->nb = (u32)nb;
+	OGB_TRY(c->slots.ensure(nb * OGB_SLOTS));
+	c->launches = 0;
+	CUDA_TRY(cudaEventRecord(c->ev[EV_HASH0], c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->slots.p, 0, nb * OGB_SLOTS * sizeof(u64), c->stream));
+	if (c->n) {
+		u64 threads = (u64)c->n * 4;
+		k_hash_insert<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->rs(), c->tb());
+		CUDA_TRY(cudaGetLastError());
+		c->launches++;
+	}
+	CUDA_TRY(cudaEventRecord(c->ev[EV_HASH1], c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->st.ms_hash_build = ev_ms(c, EV_HASH0, EV_HASH1);
+	c->st.table_buckets = nb;
+	c->st.table_bytes = nb * OGB_SLOTS * sizeof(u64);
+	c->have_table = true; c->contain_done = false; c->any_contained = false; c->have_graph = false;
+	c->st.ms_contain = 0; c->st.n_contained = 0; c->st.contain_probes = 0; c->st.contain_hits = 0;
+	return OGB_OK;
+}
+
+extern "C" uint64_t ogb_hash_string_length(const ogb_context *c) { return c ? c->h : 0; }
+extern "C" uint64_t ogb_hash_table_size(const ogb_context *c) { return c ? (uint64_t)c->nb * OGB_SLOTS : 0; }
+
+extern "C" int ogb_hash_lookup(ogb_context *c, const char *keys, uint64_t n_keys, uint64_t *out, uint64_t out_cap, uint64_t *out_offsets)
+{
+	if (!c || !out_offsets || (n_keys && !keys)) { ogb_set_error("ogb_hash_lookup: NULL argument"); return OGB_E_ARG; }
+	if (!c->have_table) { ogb_set_error("ogb_hash_lookup: build the hash table first"); return OGB_E_STATE; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	const u32 h = c->h, kw = (h + 31) / 32;
+	out_offsets[0] = 0;
+	if (n_keys == 0) return OGB_OK;
+	std::vector<u64> packed(n_keys * (kw + 1), 0);
+	for (u64 k = 0; k < n_keys; k++)
+		for (u32 i = 0; i < h; i++) {
+			u64 code;
+			switch (keys[k * h + i]) {
+			case 'A': case 'a': code = 0; break;
+			case 'C': case 'c': code = 1; break;
+			case 'G': case 'g': code = 2; break;
+			case 'T': case 't': code = 3; break;
+			default: ogb_set_error("ogb_hash_lookup: key %llu is not ACGT", (unsigned long long)k); return OGB_E_ARG;
+			}
+			packed[k * (kw + 1) + (i >> 5)] |= code << (62 - 2 * (i & 31));
+		}
+	Pool<u64> d_keys, d_pos, d_out;
+	Pool<u32> d_cnt;
+	int rc = OGB_OK;
+	std::vector<u32> cnt(n_keys);
+	std::vector<u64> pos(n_keys + 1, 0);
+	auto run = [&]() -> int {
+		OGB_TRY(d_keys.ensure(packed.size())); OGB_TRY(d_cnt.ensure(n_keys)); OGB_TRY(d_pos.ensure(n_keys + 1));
+		CUDA_TRY(cudaMemcpyAsync(d_keys.p, packed.data(), packed.size() * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+		unsigned grid = (unsigned)((n_keys + 127) / 128);
+		k_lookup<<<grid, 128, 0, c->stream>>>(c->rs(), c->tb(), d_keys.p, kw, n_keys, d_cnt.p, nullptr, nullptr, 0);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpyAsync(cnt.data(), d_cnt.p, n_keys * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		for (u64 k = 0; k < n_keys; k++) pos[k + 1] = pos[k] + cnt[k];
+		for (u64 k = 0; k <= n_keys; k++) out_offsets[k] = pos[k];
+		if (pos[n_keys] > out_cap || (pos[n_keys] && !out)) { ogb_set_error("ogb_hash_lookup: output needs %llu entries", (unsigned long long)pos[n_keys]); return OGB_E_CAPACITY; }
+		if (pos[n_keys] == 0) return OGB_OK;
+		OGB_TRY(d_out.ensure(pos[n_keys]));
+		CUDA_TRY(cudaMemcpyAsync(d_pos.p, pos.data(), (n_keys + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+		k_lookup<<<grid, 128, 0, c->stream>>>(c->rs(), c->tb(), d_keys.p, kw, n_keys, d_cnt.p, d_pos.p, d_out.p, 1);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpyAsync(out, d_out.p, pos[n_keys] * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		// the reference's bucket order is insertion order: ascending id, then orientation
+		for (u64 k = 0; k < n_keys; k++)
+			std::sort(out + pos[k], out + pos[k + 1], [](u64 a, u64 b) {
+				u64 ia = a & 0x3FFFFFFFFFFFFFFFull, ib = b & 0x3FFFFFFFFFFFFFFFull;
+				return ia != ib ? ia < ib : (a >> 62) < (b >> 62);
+			});
+		return OGB_OK;
+	};
+	rc = run();
+	d_keys.release(); d_pos.release(); d_out.release(); d_cnt.release();
+	return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2
+// ------------------------------------------------------------------------------------------------
+static ScanArgs scan_args(ogb_context *c, u32 lo, u32 hi)
+{
+	ScanArgs a;
+	a.R = c->rs(); a.T = c->tb(); a.lo = lo; a.hi = hi;
+	a.contained = c->any_contained ? c->contained.p : nullptr;
+	a.sup = c->sup.p; a.edges = c->edges.p; a.edge_cap = c->edges.cap; a.nodes = c->nodes.p;
+	a.overflow_list = c->overflow.p; a.overflow_cap = (u32)c->overflow.cap; a.ctr = c->d_ctr;
+	return a;
+}
+
+extern "C" int ogb_mark_contained(ogb_context *c)
+{
+	if (!c) { ogb_set_error("NULL context"); return OGB_E_ARG; }
+	if (!c->have_table) { ogb_set_error("ogb_mark_contained: build the hash table first"); return OGB_E_STATE; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	c->contain_done = true; c->any_contained = false; c->have_graph = false;
+	c->st.n_contained = 0; c->st.contain_probes = 0; c->st.contain_hits = 0; c->st.ms_contain = 0;
+	OGB_TRY(c->sup.ensure((size_t)c->n + 1));
+	CUDA_TRY(cudaMemsetAsync(c->sup.p, 0, ((size_t)c->n + 1) * sizeof(u64), c->stream));
+	if (c->n == 0 || c->min_len == c->max_len) { CUDA_TRY(cudaStreamSynchronize(c->stream)); return OGB_OK; }   // OverlapGraph.cpp:228
+	OGB_TRY(c->contained.ensure(((size_t)c->n + 31) / 32 + 1));
+	OGB_TRY(ctr_zero(c));
+	u32 lo, hi;
+	c->shard(lo, hi);
+	CUDA_TRY(cudaEventRecord(c->ev[EV_CONT0], c->stream));
+	ScanArgs a = scan_args(c, lo, hi);
+	a.contained = nullptr;
+	k_scan<MODE_CONTAIN><<<grid_for(c, (const void *)k_scan<MODE_CONTAIN>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(a);
+	CUDA_TRY(cudaGetLastError());
+	c->launches++;
+	if (c->nranks > 1) NCCL_TRY(g_nccl.AllReduce(c->sup.p, c->sup.p, c->n, NCCL_UINT64, NCCL_MAX, c->comm, c->stream));   // C0
+	k_contained_bitmap<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->sup.p, c->n, c->contained.p, c->d_ctr);
+	CUDA_TRY(cudaGetLastError());
+	c->launches++;
+	CUDA_TRY(cudaEventRecord(c->ev[EV_CONT1], c->stream));
+	OGB_TRY(ctr_fetch(c));
+	c->st.ms_contain = ev_ms(c, EV_CONT0, EV_CONT1);
+	c->st.n_contained = c->h_ctr[CTR_N_CONTAINED];
+	c->st.contain_probes = c->h_ctr[CTR_PROBES];
+	c->st.contain_hits = c->h_ctr[CTR_CONTAIN_HITS];
+	c->any_contained = c->st.n_contained > 0;
+	return OGB_OK;
+}
+
+extern "C" int ogb_super_read_ids(ogb_context *c, uint64_t *out, uint64_t cap)
+{
+	if (!c || !out) { ogb_set_error("ogb_super_read_ids: NULL argument"); return OGB_E_ARG; }
+	if (cap < (uint64_t)c->n + 1) { ogb_set_error("ogb_super_read_ids: need %u entries", c->n + 1); return OGB_E_CAPACITY; }
+	out[0] = 0;
+	if (!c->contain_done || c->n == 0) { for (u32 i = 1; i <= c->n; i++) out[i] = 0; return OGB_OK; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	CUDA_TRY(cudaMemcpyAsync(out + 1, c->sup.p, (size_t)c->n * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	for (u32 i = 1; i <= c->n; i++) out[i] = out[i] ? (uint64_t)(0xFFFFFFFFu - (u32)(out[i] & 0xFFFFFFFFull)) + 1 : 0;   // idx -> id
+	return OGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3..K6
+// ------------------------------------------------------------------------------------------------
+static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *d_total)
+{
+	u32 nblocks = (n + OGB_SCAN_ITEMS - 1) / OGB_SCAN_ITEMS;
+	if (nblocks == 0) nblocks = 1;
+	OGB_TRY(c->sums.ensure(nblocks + 1));
+	k_scan_sums<<<nblocks, 256, 0, c->stream>>>(cnt, n, c->sums.p);
+	k_scan_top<<<1, 1024, 0, c->stream>>>(c->sums.p, nblocks, d_total);
+	k_scan_apply<<<nblocks, 256, 0, c->stream>>>(cnt, n, c->sums.p, out);
+	CUDA_TRY(cudaGetLastError());
+	c->launches += 3;
+	return OGB_OK;
+}
+
+// Gathers variable-sized per-rank segments into every rank's buffer: segment r of the element
+// array `buf` starts at seg_off[r] and has seg_cnt[r] elements (grouped ncclBroadcast = allgatherv).
+static int allgatherv(ogb_context *c, void *buf, size_t elem, const std::vector<u64> &seg_off, const std::vector<u64> &seg_cnt)
+{
+	NCCL_TRY(g_nccl.GroupStart());
+	for (int r = 0; r < c->nranks; r++) {
+		if (seg_cnt[r] == 0) continue;
+		char *p = (char *)buf + seg_off[r] * elem;
+		NCCL_TRY(g_nccl.Broadcast(p, p, seg_cnt[r] * elem, NCCL_UINT8, r, c->comm, c->stream));
+	}
+	NCCL_TRY(g_nccl.GroupEnd());
+	return OGB_OK;
+}
+
+__global__ void k_shift_nodes(u64 *nodes, u32 lo, u32 hi, u64 delta)
+{
+	u32 i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < hi) { u64 nd = nodes[i]; if (nd & OGB_DEG_MASK) nodes[i] = nd + (delta << OGB_DEG_BITS); }
+}
+
+extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
+{
+	if (!c) { ogb_set_error("NULL context"); return OGB_E_ARG; }
+	if (!c->have_table) { ogb_set_error("ogb_build_graph: build the hash table first"); return OGB_E_STATE; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	// buildOverlapGraphFromHashTable always marks contained reads first (OverlapGraph.cpp:140)
+	if (!c->contain_done) OGB_TRY(ogb_mark_contained(c));
+	c->have_graph = false; c->have_pre = false; c->n_final = 0; c->n_pre = 0;
+	const u32 n = c->n;
+	if (n == 0) { c->have_graph = true; c->have_pre = keep_pre != 0; c->st.edges_pre = c->st.edges_final = c->st.nodes_final = 0; return OGB_OK; }
+	u32 lo, hi;
+	c->shard(lo, hi);
+	const int G = c->nranks;
+	const u64 per = ((u64)n + G - 1) / G;
+	OGB_TRY(c->nodes.ensure(per * G + 1));
+	OGB_TRY(c->cnt.ensure(per * G + 1));
+	OGB_TRY(c->pos.ensure((size_t)n + 1));
+	if (c->overflow.cap == 0) OGB_TRY(c->overflow.ensure(1 << 16));
+	if (c->edges.cap == 0) OGB_TRY(c->edges.ensure(std::max<u64>(1 << 22, (u64)(hi - lo) * 40 * (G > 1 ? 2 : 1))));
+
+	// ---- K3 (+ slow path), retried with larger pools if a capacity was exceeded
+	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL0], c->stream));
+	u64 local_edges = 0;
+	for (int attempt = 0;; attempt++) {
+		if (attempt == 4) { ogb_set_error("ogb_build_graph: edge pool kept overflowing"); return OGB_E_CAPACITY; }
+		OGB_TRY(ctr_zero(c));
+		ScanArgs a = scan_args(c, lo, hi);
+		k_scan<MODE_OVERLAP><<<grid_for(c, (const void *)k_scan<MODE_OVERLAP>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(a);
+		CUDA_TRY(cudaGetLastError());
+		c->launches++;
+		OGB_TRY(ctr_fetch(c));
+		u64 n_over = c->h_ctr[CTR_OVERFLOW];
+		if (n_over > c->overflow.cap) { OGB_TRY(c->overflow.ensure(n_over + 1024)); continue; }
+		if (n_over) {
+			k_scan_big<<<(unsigned)std::min<u64>(n_over, 4096), 256, 0, c->stream>>>(a, (u32)n_over);
+			CUDA_TRY(cudaGetLastError());
+			c->launches++;
+			OGB_TRY(ctr_fetch(c));
+		}
+		local_edges = c->h_ctr[CTR_EDGE_CURSOR];
+		if (local_edges > c->edges.cap) { OGB_TRY(c->edges.ensure(local_edges + local_edges / 16 + 1024)); continue; }
+		c->st.overflow_reads = n_over;
+		break;
+	}
+	c->st.overlap_probes = c->h_ctr[CTR_PROBES];
+	c->st.probe_sectors = c->h_ctr[CTR_SECTORS];
+	c->st.candidates = c->h_ctr[CTR_CANDIDATES];
+	c->st.max_degree = c->h_ctr[CTR_MAX_DEGREE];
+	c->st.edges_pre_local = local_edges;
+	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL1], c->stream));
+
+	// ---- C1: every rank needs the whole pre-reduction adjacency (a pivot can live anywhere)
+	std::vector<u64> seg_cnt(G, 0), seg_off(G, 0);
+	u64 total_edges = local_edges;
+	if (G > 1) {
+		Pool<u64> d_counts;
+		OGB_TRY(d_counts.ensure(G));
+		std::vector<u64> counts(G, 0);
+		CUDA_TRY(cudaMemcpyAsync(d_counts.p + c->rank, &local_edges, sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+		NCCL_TRY(g_nccl.AllGather(d_counts.p + c->rank, d_counts.p, 1, NCCL_UINT64, c->comm, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(counts.data(), d_counts.p, G * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		d_counts.release();
+		total_edges = 0;
+		for (int r = 0; r < G; r++) { seg_cnt[r] = counts[r]; seg_off[r] = total_edges; total_edges += counts[r]; }
+		if (total_edges > c->edges.cap) {
+			// grow, keeping this rank's segment
+			Pool<u64> bigger;
+			OGB_TRY(bigger.ensure(total_edges + total_edges / 16 + 1024));
+			CUDA_TRY(cudaMemcpyAsync(bigger.p, c->edges.p, local_edges * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+			CUDA_TRY(cudaStreamSynchronize(c->stream));
+			c->edges.release();
+			c->edges = bigger;
+		}
+		if (seg_off[c->rank] != 0) {
+			// move the local segment to its global position (ranges may overlap: go through pos-sized temp only if needed)
+			Pool<u64> tmp;
+			OGB_TRY(tmp.ensure(std::max<u64>(local_edges, 1)));
+			CUDA_TRY(cudaMemcpyAsync(tmp.p, c->edges.p, local_edges * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+			CUDA_TRY(cudaMemcpyAsync(c->edges.p + seg_off[c->rank], tmp.p, local_edges * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+			if (hi > lo) { k_shift_nodes<<<(hi - lo + 255) / 256, 256, 0, c->stream>>>(c->nodes.p, lo, hi, seg_off[c->rank]); c->launches++; }
+			CUDA_TRY(cudaStreamSynchronize(c->stream));
+			tmp.release();
+		}
+		OGB_TRY(allgatherv(c, c->edges.p, sizeof(u64), seg_off, seg_cnt));
+		NCCL_TRY(g_nccl.AllGather(c->nodes.p + per * c->rank, c->nodes.p, per, NCCL_UINT64, c->comm, c->stream));
+	}
+	c->st.edges_pre = total_edges;
+	c->n_pre = total_edges;
+	CUDA_TRY(cudaEventRecord(c->ev[EV_XPRE1], c->stream));
+
+	if (keep_pre) {
+		// export the pre-reduction adjacency as records, in node order
+		OGB_TRY(c->pre.ensure(std::max<u64>(total_edges, 1)));
+		k_degrees<<<(n + 255) / 256, 256, 0, c->stream>>>(c->nodes.p, n, c->cnt.p);
+		OGB_TRY(exclusive_scan(c, c->cnt.p, n, c->pos.p, c->d_ctr + CTR_LOOKUP_TOTAL));
+		k_export_pre<<<grid_for(c, (const void *)k_export_pre, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->edges.p, c->pos.p, c->pre.p, n);
+		CUDA_TRY(cudaGetLastError());
+		c->have_pre = true;
+	}
+
+	// ---- K5
+	OGB_TRY(c->eflag.ensure(std::max<u64>(c->edges.cap, 1)));
+	OGB_TRY(c->keep.ensure(std::max<u64>(c->edges.cap, 1)));
+	if (c->scratch_keys.cap == 0) { OGB_TRY(c->scratch_keys.ensure(1 << 20)); OGB_TRY(c->scratch_state.ensure(1 << 20)); }
+	for (int attempt = 0;; attempt++) {
+		if (attempt == 4) { ogb_set_error("ogb_build_graph: neighbour-set scratch kept overflowing"); return OGB_E_CAPACITY; }
+		OGB_TRY(ctr_zero(c));
+		MarkArgs m;
+		m.nodes = c->nodes.p; m.edges = c->edges.p; m.eflag = c->eflag.p; m.lo = lo; m.hi = hi;
+		m.scratch_keys = c->scratch_keys.p; m.scratch_state = c->scratch_state.p; m.scratch_cap = c->scratch_keys.cap; m.ctr = c->d_ctr;
+		k_mark<<<grid_for(c, (const void *)k_mark, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
+		CUDA_TRY(cudaGetLastError());
+		c->launches++;
+		if (c->st.max_degree * 2 <= OGB_SETCAP) break;                      // no node can have used the scratch pool
+		OGB_TRY(ctr_fetch(c));
+		if (c->h_ctr[CTR_SCRATCH_FAIL] == 0) break;
+		u64 need = c->h_ctr[CTR_SCRATCH_CURSOR] + 1024;
+		OGB_TRY(c->scratch_keys.ensure(need)); OGB_TRY(c->scratch_state.ensure(need));
+	}
+	CUDA_TRY(cudaEventRecord(c->ev[EV_MARK1], c->stream));
+	if (G > 1) OGB_TRY(allgatherv(c, c->eflag.p, 1, seg_off, seg_cnt));   // C2
+
+	// ---- K6
+	k_twin_keep<<<grid_for(c, (const void *)k_twin_keep, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->edges.p, c->eflag.p, c->keep.p,
+	                                                                                                     c->cnt.p, lo, hi, c->d_ctr);
+	CUDA_TRY(cudaGetLastError());
+	c->launches++;
+	if (G > 1) NCCL_TRY(g_nccl.AllGather(c->cnt.p + per * c->rank, c->cnt.p, per, NCCL_UINT32, c->comm, c->stream));
+	OGB_TRY(exclusive_scan(c, c->cnt.p, n, c->pos.p, c->d_ctr + CTR_LOOKUP_TOTAL));
+	OGB_TRY(c->fin.ensure(std::max<u64>(c->edges.cap, 1)));                // E_final <= E_pre: no sync needed to size it
+	k_compact<<<grid_for(c, (const void *)k_compact, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->edges.p, c->keep.p, c->pos.p, c->fin.p, 0, lo, hi);
+	CUDA_TRY(cudaGetLastError());
+	c->launches++;
+	OGB_TRY(ctr_fetch(c));
+	c->n_final = c->h_ctr[CTR_LOOKUP_TOTAL];
+	if (G > 1) {
+		// C3: final edges of every rank's node range (allgatherv over the positions just scanned)
+		std::vector<u64> bounds(G + 1, 0);
+		for (int r = 0; r <= G; r++) {
+			u64 node = std::min<u64>(n, per * r);
+			if (node >= n) bounds[r] = c->n_final;
+			else CUDA_TRY(cudaMemcpyAsync(&bounds[r], c->pos.p + node, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		}
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		std::vector<u64> foff(G), fcnt(G);
+		for (int r = 0; r < G; r++) { foff[r] = bounds[r]; fcnt[r] = bounds[r + 1] - bounds[r]; }
+		OGB_TRY(allgatherv(c, c->fin.p, sizeof(ogb_edge), foff, fcnt));
+		Pool<u64> d_nodes_final;
+		OGB_TRY(d_nodes_final.ensure(1));
+		NCCL_TRY(g_nccl.AllReduce(c->d_ctr + CTR_NODES_FINAL, d_nodes_final.p, 1, NCCL_UINT64, 0 /*ncclSum*/, c->comm, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(&c->h_ctr[CTR_NODES_FINAL], d_nodes_final.p, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		d_nodes_final.release();
+	}
+	CUDA_TRY(cudaEventRecord(c->ev[EV_RED1], c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	if (c->h_ctr[CTR_ASYMMETRIC]) { ogb_set_error("ogb_build_graph: %llu edges without a twin (internal error)", (unsigned long long)c->h_ctr[CTR_ASYMMETRIC]); return OGB_E_STATE; }
+	c->st.pivot_entries = c->h_ctr[CTR_PIVOT_ENTRIES];
+	c->st.active_pivots = c->h_ctr[CTR_ACTIVE_PIVOTS];
+	c->st.edges_final = c->n_final;
+	c->st.nodes_final = c->h_ctr[CTR_NODES_FINAL];
+	c->st.ms_overlap = ev_ms(c, EV_OVL0, EV_OVL1);
+	c->st.ms_exchange_pre = ev_ms(c, EV_OVL1, EV_XPRE1);
+	c->st.ms_mark = ev_ms(c, EV_XPRE1, EV_MARK1);
+	c->st.ms_reduce = ev_ms(c, EV_MARK1, EV_RED1);
+	c->st.ms_total = c->st.ms_hash_build + c->st.ms_contain + ev_ms(c, EV_OVL0, EV_RED1);
+	c->st.kernel_launches = c->launches;
+	c->have_graph = true;
+	return OGB_OK;
+}
+
+extern "C" int ogb_graph_edge_count(ogb_context *c, int which, uint64_t *n)
+{
+	if (!c || !n) { ogb_set_error("ogb_graph_edge_count: NULL argument"); return OGB_E_ARG; }
+	if (!c->have_graph) { ogb_set_error("ogb_graph_edge_count: build the graph first"); return OGB_E_STATE; }
+	if (which == 1 && !c->have_pre) { ogb_set_error("ogb_graph_edge_count: pre-reduction edges were not kept"); return OGB_E_STATE; }
+	*n = which ? c->n_pre : c->n_final;
+	return OGB_OK;
+}
+
+extern "C" int ogb_graph_edges(ogb_context *c, int which, ogb_edge *out, uint64_t cap)
+{
+	uint64_t n = 0;
+	OGB_TRY(ogb_graph_edge_count(c, which, &n));
+	if (n == 0) return OGB_OK;
+	if (!out || cap < n) { ogb_set_error("ogb_graph_edges: need room for %llu edges", (unsigned long long)n); return OGB_E_CAPACITY; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	CUDA_TRY(cudaMemcpyAsync(out, which ? c->pre.p : c->fin.p, n * sizeof(ogb_edge), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return OGB_OK;
+}
+
+extern "C" int ogb_get_stats(ogb_context *c, ogb_stats *out)
+{
+	if (!c || !out) { ogb_set_error("ogb_get_stats: NULL argument"); return OGB_E_ARG; }
+	*out = c->st;
+	return OGB_OK;
+}

@@ -1,0 +1,817 @@
+// ogb_kernels.cuh -- hand-written sm_100a kernels of the overlap-graph build.
+//
+//   K0  k_pack_ascii / k_pack_words   Read::setRead + reverseComplement          (Read.cpp:75-127)
+//   K1  k_hash_insert                 HashTable::hashRead + insertIntoTable       (HashTable.cpp:88-195)
+//   K2  k_scan<MODE_CONTAIN>          markContainedReads + checkOverlapForContainedRead (OverlapGraph.cpp:225-340)
+//   K3  k_scan<MODE_OVERLAP>          insertAllEdgesOfRead + checkOverlap + per-node sort (OverlapGraph.cpp:354-383,529-565)
+//   K5  k_mark                        markTransitiveEdges                         (OverlapGraph.cpp:574-615)
+//   K6  k_twin_keep / k_compact       removeTransitiveEdges                       (OverlapGraph.cpp:623-661)
+//       k_lookup_*                    HashTable::getListOfReads                   (HashTable.cpp:202-221)
+//
+// Everything is integer / bit work bounded by HBM (random 32-byte sector gathers into the index
+// and the packed read store); there is no dense contraction, hence no tensor-core code.
+//
+// Data layout in HBM
+//   packed reads  u64 words, base k of a strand in bits 63-2(k%32)..62-2(k%32) of word k/32,
+//                 A0 C1 G2 T3 (complement = 3-x). Read idx (= id-1): forward strand at word
+//                 offset off, reverse complement at off + pw, pw = 2*ceil(L/64) words (16-byte
+//                 aligned strands; 100 bp -> 32 B = one sector). Uniform-length data sets use
+//                 off = idx*2*pw (no metadata load); mixed lengths use meta[idx] = off<<16 | L.
+//   index         nb buckets x 4 slots x u64 (one 32-byte sector per bucket). slot = fp32<<32 |
+//                 id<<2 | o, 0 = empty. One slot per (key,value); a key's entries sit in its home
+//                 bucket and, when that is full, in the following buckets (linear probing by
+//                 bucket). Only a 32-bit fingerprint of the key is stored: every consumer verifies
+//                 the complete overlap (window included) against the packed reads, which makes
+//                 the result exact and independent of hash values.
+//   edges         u64 = offset<<48 | dst<<16 | orient<<8, so integer order = (offset,dst,orient).
+//   nodes         u64 = start<<24 | degree  (adjacency of a node is contiguous and sorted).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#define OGB_SLOTS 4             // slots per bucket (32-byte sector)
+#define OGB_WARPS 8             // warps per block in the scan / mark kernels
+#define OGB_HQ 160              // per-warp candidate queue (<= 31 left over + 32 lanes x 4 slots)
+#define OGB_EC 256              // per-warp edge buffer (reads with more edges take the slow path)
+#define OGB_SETCAP 512          // per-warp neighbour set slots in shared memory (degree <= 256)
+#define OGB_DEG_BITS 24
+#define OGB_DEG_MASK 0xFFFFFFull
+#define OGB_NODE_OVERFLOW OGB_DEG_MASK   // degree field value marking "take the slow path"
+
+enum { MODE_OVERLAP = 0, MODE_CONTAIN = 1 };
+
+// device counters (u64 each)
+enum {
+	CTR_EDGE_CURSOR = 0, CTR_OVERFLOW, CTR_PROBES, CTR_SECTORS, CTR_CANDIDATES, CTR_CONTAIN_HITS,
+	CTR_PIVOT_ENTRIES, CTR_ACTIVE_PIVOTS, CTR_MAX_DEGREE, CTR_N_CONTAINED, CTR_NODES_FINAL,
+	CTR_ASYMMETRIC, CTR_SCRATCH_CURSOR, CTR_SCRATCH_FAIL, CTR_EDGES_DROPPED, CTR_LOOKUP_TOTAL, CTR_COUNT
+};
+
+struct ReadStore {
+	const u64 *words;
+	const u64 *meta;     // null when uniform
+	u32 n;
+	u32 uniform_len;     // 0 when lengths differ
+	u32 uniform_pw;      // padded words per strand when uniform
+};
+
+struct Table {
+	u64 *slots;
+	u32 nb;              // buckets
+	u32 h;               // hashStringLength = minOverlap-1 (HashTable.cpp:54)
+};
+
+__device__ __forceinline__ u32 padded_words(u32 L) { return ((L + 63) >> 6) << 1; }
+
+__device__ __forceinline__ void read_geom(const ReadStore &R, u32 idx, u64 &off, u32 &L)
+{
+	if (R.uniform_len) { L = R.uniform_len; off = (u64)idx * (2 * R.uniform_pw); }
+	else { u64 m = __ldg(R.meta + idx); L = (u32)(m & 0xFFFF); off = m >> 16; }
+}
+
+// 32 bases starting at base p of a packed strand (high bits first). The word after the strand is
+// always allocated, so the second load is unconditional; callers mask what they do not need.
+__device__ __forceinline__ u64 extract32(const u64 *__restrict__ w, u32 p)
+{
+	u32 wi = p >> 5, sh = (p & 31) << 1;
+	u64 a = __ldg(w + wi), b = __ldg(w + wi + 1);
+	return sh ? ((a << sh) | (b >> (64 - sh))) : a;
+}
+
+__device__ __forceinline__ u64 mix64(u64 acc, u64 x)
+{
+	acc ^= x;
+	acc *= 0xff51afd7ed558ccdULL;
+	acc ^= acc >> 33;
+	return acc;
+}
+
+// 64-bit hash of the h bases starting at base p. Low 32 bits pick the bucket, high 32 are the
+// stored fingerprint. (The reference's polynomial-mod hash, HashTable.cpp:135-155, is not
+// reproduced: its value is unobservable in the result.)
+__device__ __forceinline__ u64 key_hash(const u64 *__restrict__ w, u32 p, u32 h)
+{
+	u64 acc = 0x9E3779B97F4A7C15ULL;
+	u32 rem = h;
+	for (; rem > 32; rem -= 32, p += 32) acc = mix64(acc, extract32(w, p));
+	acc = mix64(acc, extract32(w, p) & (~0ULL << (64 - 2 * rem)));
+	acc *= 0xc4ceb9fe1a85ec53ULL;
+	acc ^= acc >> 29;
+	return acc;
+}
+
+__device__ __forceinline__ u32 bucket_of(u64 hash, u32 nb) { return (u32)(((hash & 0xFFFFFFFFull) * (u64)nb) >> 32); }
+
+// s[a..a+len) == t[b..b+len) on packed strands. No early exit: (almost) every candidate verifies,
+// and independent iterations keep all sector requests of the partner read in flight.
+__device__ __forceinline__ bool region_equal(const u64 *__restrict__ s, u32 a, const u64 *__restrict__ t, u32 b, u32 len)
+{
+	u64 diff = 0;
+	u32 k = 0;
+	for (; k + 32 <= len; k += 32) diff |= extract32(s, a + k) ^ extract32(t, b + k);
+	u32 rem = len - k;
+	if (rem) diff |= (extract32(s, a + k) ^ extract32(t, b + k)) & (~0ULL << (64 - 2 * rem));
+	return diff == 0;
+}
+
+__device__ __forceinline__ u64 make_edge(u32 offset, u32 dst, u32 orient) { return ((u64)offset << 48) | ((u64)dst << 16) | ((u64)orient << 8); }
+__device__ __forceinline__ u32 edge_dst(u64 e) { return (u32)(e >> 16); }
+__device__ __forceinline__ u32 edge_orient(u64 e) { return (u32)(e >> 8) & 3; }
+__device__ __forceinline__ u32 edge_offset(u64 e) { return (u32)(e >> 48); }
+// OverlapGraph.cpp:593-596: the pivot is entered and left on the same strand.
+__device__ __forceinline__ bool compatible(u32 t1, u32 t2) { return ((t1 & 1) == ((t2 >> 1) & 1)); }
+// OverlapGraph.cpp:841-855
+__device__ __forceinline__ u32 twin_orient(u32 o) { return o == 0 ? 3 : (o == 3 ? 0 : o); }
+
+// ------------------------------------------------------------------------------------------------
+// K0: pack + reverse complement.
+// ------------------------------------------------------------------------------------------------
+
+// One thread per (read, output word). ASCII input, already validated upper-case ACGT.
+__global__ void k_pack_ascii(const char *__restrict__ bases, const u64 *__restrict__ offsets, u64 *__restrict__ words,
+                             const u64 *__restrict__ meta, u32 n, u32 uniform_len, u32 uniform_pw, u32 max_pw)
+{
+	u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	u32 idx = (u32)(tid / max_pw), k = (u32)(tid % max_pw);
+	if (idx >= n) return;
+	u64 off; u32 L;
+	if (uniform_len) { L = uniform_len; off = (u64)idx * (2 * uniform_pw); }
+	else { u64 m = meta[idx]; L = (u32)(m & 0xFFFF); off = m >> 16; }
+	u32 pw = padded_words(L);
+	if (k >= pw) return;
+	const char *s = bases + offsets[idx];
+	u64 fw = 0, rc = 0;
+	for (u32 i = 0; i < 32; i++) {
+		u32 p = k * 32 + i;
+		if (p < L) {
+			// A=0x41 C=0x43 G=0x47 T=0x54: (c>>1)&3 = 0,1,3,2 (the reference's code, HashTable.cpp:149);
+			// x ^ (x>>1) turns that into the order-preserving 0,1,2,3.
+			u32 c = ((u32)s[p] >> 1) & 3; c ^= c >> 1;
+			fw |= (u64)c << (62 - 2 * i);
+			u32 d = ((u32)s[L - 1 - p] >> 1) & 3; d ^= d >> 1;
+			rc |= (u64)(3 - d) << (62 - 2 * i);
+		}
+	}
+	words[off + k] = fw;
+	words[off + pw + k] = rc;
+}
+
+__device__ __forceinline__ u64 reverse_groups(u64 x)
+{
+	x = __brevll(x);
+	return ((x & 0x5555555555555555ULL) << 1) | ((x >> 1) & 0x5555555555555555ULL);
+}
+
+// One thread per (read, output word). Input: tightly packed forward words (host Dataset layout).
+__global__ void k_pack_words(const u64 *__restrict__ in_words, const u64 *__restrict__ in_offsets, const unsigned short *__restrict__ lens,
+                             u64 *__restrict__ words, const u64 *__restrict__ meta, u32 n, u32 uniform_len, u32 uniform_pw, u32 max_pw)
+{
+	u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	u32 idx = (u32)(tid / max_pw), k = (u32)(tid % max_pw);
+	if (idx >= n) return;
+	u32 L = lens[idx];
+	u64 off;
+	if (uniform_len) off = (u64)idx * (2 * uniform_pw); else off = meta[idx] >> 16;
+	u32 pw = padded_words(L), nw = (L + 31) >> 5;
+	if (k >= pw) return;
+	const u64 *src = in_words + in_offsets[idx];
+	u64 fw = k < nw ? src[k] : 0;
+	// rc bases [32k, 32k+32) = complement of forward bases (L-32k-32 .. L-32k], reversed
+	u64 rc = 0;
+	if (k < nw) {
+		int hi = (int)L - 32 * (int)k;       // exclusive end in forward coordinates, >= 1
+		int lo = hi - 32;
+		u32 cnt = 32;
+		if (lo < 0) { cnt = (u32)hi; lo = 0; }
+		u32 wi = (u32)lo >> 5, sh = ((u32)lo & 31) << 1;
+		u64 a = src[wi], b = (wi + 1 < nw) ? src[wi + 1] : 0;
+		u64 x = sh ? ((a << sh) | (b >> (64 - sh))) : a;       // forward bases lo..lo+31 at the top
+		if (cnt < 32) x &= ~0ULL << (64 - 2 * cnt);            // keep forward bases lo..hi-1
+		u64 r = ~reverse_groups(x);                            // reversed + complemented; valid groups are the LOW cnt
+		if (cnt < 32) r <<= (64 - 2 * cnt);
+		rc = cnt < 32 ? (r & (~0ULL << (64 - 2 * cnt))) : r;
+	}
+	words[off + k] = fw;
+	words[off + pw + k] = rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: hash insert. One thread per (read, orientation): o=0 prefix(fwd), 1 suffix(fwd),
+// 2 prefix(rc), 3 suffix(rc) (HashTable.cpp:93-101). Claims the first empty slot along the probe
+// sequence with a 64-bit CAS. Slot order inside a bucket is arbitrary (unobservable).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_hash_insert(ReadStore R, Table T)
+{
+	u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (tid >= (u64)R.n * 4) return;
+	u32 idx = (u32)(tid >> 2), o = (u32)(tid & 3);
+	u64 off; u32 L;
+	read_geom(R, idx, off, L);
+	const u64 *w = R.words + off + (o >> 1) * padded_words(L);
+	u32 p = (o & 1) ? L - T.h : 0;
+	u64 hash = key_hash(w, p, T.h);
+	u64 val = (hash & 0xFFFFFFFF00000000ull) | ((u64)(idx + 1) << 2) | o;
+	u32 b = bucket_of(hash, T.nb);
+	for (;;) {
+		u64 *slot = T.slots + (u64)b * OGB_SLOTS;
+		bool done = false;
+		#pragma unroll
+		for (int s = 0; s < OGB_SLOTS && !done; s++) {
+			u64 cur = slot[s];
+			if (cur == 0) cur = atomicCAS(slot + s, 0ull, val);
+			done = (cur == 0);
+		}
+		if (done) break;
+		b = (b + 1 == T.nb) ? 0 : b + 1;
+	}
+}
+
+__device__ __forceinline__ void load_bucket(const u64 *__restrict__ slots, u32 b, u64 (&s)[OGB_SLOTS])
+{
+	const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(slots + (u64)b * OGB_SLOTS);
+	ulonglong2 x = __ldg(p), y = __ldg(p + 1);
+	s[0] = x.x; s[1] = x.y; s[2] = y.x; s[3] = y.y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 / K3: sliding-window scan, one warp per query read.
+//
+// Phase A  lane l probes windows j = 1+l, 33+l, ... (j = 1 .. L-h-1, OverlapGraph.cpp:534): key hash
+//          -> bucket sector -> fingerprint compare; matches go to a per-warp candidate queue in
+//          shared memory (ballot + popc compaction, warp-synchronous).
+// Phase B  whenever >= 32 candidates are queued (and at the end) each lane verifies one candidate
+//          against the partner's packed strand (one random sector for 100 bp) -- checkOverlap /
+//          checkOverlapForContainedRead restated on packed words.
+// Phase C  (overlap mode) verified edges are sorted by (offset,dst,orient) in shared memory
+//          (bitonic), a contiguous range of the global edge array is claimed with one atomicAdd and
+//          the node record start<<24|deg is written: the adjacency comes out sorted (:563) with no
+//          global sort. Reads with more than OGB_EC edges are queued for k_scan_big.
+// ------------------------------------------------------------------------------------------------
+
+struct ScanArgs {
+	ReadStore R;
+	Table T;
+	u32 lo, hi;                 // query read indices [lo, hi) (this rank's shard)
+	const u32 *contained;       // bitmap by read index (null when no read is contained)
+	u64 *sup;                   // MODE_CONTAIN: per read idx, max over hits of (L_super<<32 | ~super_idx)
+	u64 *edges;                 // MODE_OVERLAP outputs
+	u64 edge_cap;
+	u64 *nodes;
+	u32 *overflow_list;
+	u32 overflow_cap;
+	u64 *ctr;
+};
+
+// Verifies candidate (j, val) of query read qi (strand words s, length L1). Returns the number of
+// edges produced (0, 1, or 2 for a self-overlap) in e0/e1; in MODE_CONTAIN performs the atomicMax.
+template <int MODE>
+__device__ __forceinline__ int verify_candidate(const ScanArgs &A, const u64 *__restrict__ s, u32 qi, u32 L1, u32 j, u32 val, u64 &e0, u64 &e1)
+{
+	const u32 h = A.T.h;
+	u32 ri = (val >> 2) - 1, o = val & 3;
+	u64 roff; u32 L2;
+	read_geom(A.R, ri, roff, L2);
+	const u64 *t = A.R.words + roff + (o >> 1) * padded_words(L2);
+	if (MODE == MODE_CONTAIN) {
+		// OverlapGraph.cpp:256: read1 must be longer; :302-340 restated on the whole of read2.
+		if (L1 <= L2) return 0;
+		u32 a;
+		if ((o & 1) == 0) { if (L1 - j < L2) return 0; a = j; }              // :316-321
+		else { if (j < L2 - h) return 0; a = j - (L2 - h); }                // :331-336
+		if (!region_equal(s, a, t, 0, L2)) return 0;
+		atomicMax(A.sup + ri, ((u64)L1 << 32) | (u64)(0xFFFFFFFFu - qi));   // :259-268
+		return 1;
+	} else {
+		if (A.contained && ((__ldg(A.contained + (ri >> 5)) >> (ri & 31)) & 1)) return 0;   // :548 superReadID == 0
+		u32 a, b, len, orient, offset;
+		if ((o & 1) == 0) {               // key = prefix of t: s[j..L1) must equal t[0..L1-j)      (:359-370)
+			if (L1 - j >= L2) return 0;
+			a = j; b = 0; len = L1 - j;
+			orient = o == 0 ? 3 : 2;      // :552,:554
+			offset = j;                   // L1 - overlap, overlap = L1 - j
+		} else {                          // key = suffix of t: s[0..j+h) must equal t[L2-h-j..L2)  (:371-382)
+			if (L2 - h < j) return 0;
+			a = 0; b = L2 - h - j; len = h + j;
+			orient = o == 1 ? 0 : 1;      // :553,:555
+			offset = L1 - h - j;          // L1 - overlap, overlap = h + j
+		}
+		if (!region_equal(s, a, t, b, len)) return 0;
+		e0 = make_edge(offset & 0xFFFF, ri + 1, orient);
+		if (ri != qi) return 1;
+		// Self-overlap: the reference inserts the edge and its twin object into the same list
+		// (OverlapGraph.cpp:409-417); twin offset = (UINT16)(L2 + offset - L1) = offset.
+		e1 = make_edge(offset & 0xFFFF, ri + 1, twin_orient(orient));
+		return 2;
+	}
+}
+
+// In-place ascending bitonic sort of n u64 keys in shared memory by one warp (n <= cap, cap a power
+// of two; the tail is padded with ~0).
+__device__ __forceinline__ void warp_sort(u64 *buf, u32 n, u32 lane)
+{
+	u32 m = 32;
+	while (m < n) m <<= 1;
+	for (u32 i = n + lane; i < m; i += 32) buf[i] = ~0ull;
+	__syncwarp();
+	for (u32 k = 2; k <= m; k <<= 1) {
+		for (u32 jj = k >> 1; jj > 0; jj >>= 1) {
+			for (u32 t = lane; t < (m >> 1); t += 32) {
+				u32 i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+				u32 l = i | jj;
+				bool up = (i & k) == 0;
+				u64 x = buf[i], y = buf[l];
+				if ((x > y) == up) { buf[i] = y; buf[l] = x; }
+			}
+			__syncwarp();
+		}
+	}
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(OGB_WARPS * 32) k_scan(ScanArgs A)
+{
+	__shared__ u64 s_hq[OGB_WARPS][OGB_HQ];
+	__shared__ u64 s_edges[MODE == MODE_OVERLAP ? OGB_WARPS : 1][MODE == MODE_OVERLAP ? OGB_EC : 1];
+	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const u32 gw = blockIdx.x * OGB_WARPS + wib, nwarps = gridDim.x * OGB_WARPS;
+	u64 *hq = s_hq[wib];
+	u64 *eb = s_edges[MODE == MODE_OVERLAP ? wib : 0];
+	const u32 h = A.T.h;
+	u64 c_probes = 0, c_sectors = 0, c_cand = 0, c_hits = 0;
+	u32 c_maxdeg = 0;
+
+	for (u32 qi = A.lo + gw; qi < A.hi; qi += nwarps) {
+		if (MODE == MODE_OVERLAP && A.contained && ((__ldg(A.contained + (qi >> 5)) >> (qi & 31)) & 1)) {
+			if (lane == 0) A.nodes[qi] = 0;                                  // contained reads have no edges (:548)
+			continue;
+		}
+		u64 off; u32 L1;
+		read_geom(A.R, qi, off, L1);
+		const u64 *s = A.R.words + off;
+		const u32 nwin = L1 - h - 1;                                         // j = 1 .. L1-h-1 (:534)
+		u32 qn = 0;        // queued candidates (warp-uniform)
+		u32 en = 0;        // buffered edges (warp-uniform); keeps counting past OGB_EC
+		c_probes += nwin;
+
+		// ---- phase B: each lane verifies one queued candidate (taken from the tail of the queue)
+		auto verify_batch = [&]() {
+			u32 take = qn < 32 ? qn : 32;
+			u32 base = qn - take;
+			u64 e0 = 0, e1 = 0; int ne = 0;
+			if (lane < take) {
+				u64 c = hq[base + lane];
+				ne = verify_candidate<MODE>(A, s, qi, L1, (u32)(c >> 32), (u32)c, e0, e1);
+				c_cand++;
+			}
+			qn = base;
+			if (MODE == MODE_OVERLAP) {
+				u32 b0 = __ballot_sync(0xFFFFFFFFu, ne >= 1), b1 = __ballot_sync(0xFFFFFFFFu, ne >= 2);
+				u32 p0 = en + __popc(b0 & ((1u << lane) - 1));
+				if (ne >= 1 && p0 < OGB_EC) eb[p0] = e0;
+				en += __popc(b0);
+				u32 p1 = en + __popc(b1 & ((1u << lane) - 1));
+				if (ne >= 2 && p1 < OGB_EC) eb[p1] = e1;
+				en += __popc(b1);
+			} else {
+				c_hits += ne;
+			}
+			__syncwarp();
+		};
+
+		for (u32 jb = 1; jb <= nwin; jb += 32) {
+			// ---- phase A: one window per lane
+			u32 j = jb + lane;
+			bool active = j <= nwin;
+			u64 hash = 0; u32 b = 0;
+			if (active) { hash = key_hash(s, j, h); b = bucket_of(hash, A.T.nb); }
+			const u32 fp = (u32)(hash >> 32);
+			while (__any_sync(0xFFFFFFFFu, active)) {
+				u64 sl[OGB_SLOTS] = {0, 0, 0, 0};
+				bool full = false;
+				if (active) {
+					load_bucket(A.T.slots, b, sl);
+					full = true;
+					c_sectors++;
+				}
+				#pragma unroll
+				for (int k = 0; k < OGB_SLOTS; k++) {
+					bool m = active && sl[k] != 0 && (u32)(sl[k] >> 32) == fp;
+					if (active && sl[k] == 0) full = false;
+					u32 bal = __ballot_sync(0xFFFFFFFFu, m);
+					if (m) hq[qn + __popc(bal & ((1u << lane) - 1))] = ((u64)j << 32) | (u32)sl[k];
+					qn += __popc(bal);
+				}
+				active = active && full;                                     // a full bucket spills into the next one
+				if (active) b = (b + 1 == A.T.nb) ? 0 : b + 1;
+				__syncwarp();
+				while (qn >= 32) verify_batch();                             // keeps room for 32 lanes x 4 slots
+			}
+		}
+		while (qn > 0) verify_batch();
+
+		if (MODE == MODE_OVERLAP) {
+			// ---- phase C
+			if (en > c_maxdeg) c_maxdeg = en;
+			if (en == 0) { if (lane == 0) A.nodes[qi] = 0; }
+			else if (en <= OGB_EC) {
+				warp_sort(eb, en, lane);
+				u64 start = 0;
+				if (lane == 0) start = atomicAdd(A.ctr + CTR_EDGE_CURSOR, (u64)en);
+				start = __shfl_sync(0xFFFFFFFFu, start, 0);
+				if (start + en <= A.edge_cap) {
+					for (u32 t = lane; t < en; t += 32) A.edges[start + t] = eb[t];
+				} else if (lane == 0) atomicAdd(A.ctr + CTR_EDGES_DROPPED, (u64)en);
+				if (lane == 0) A.nodes[qi] = (start << OGB_DEG_BITS) | en;
+				__syncwarp();
+			} else if (lane == 0) {
+				u64 pos = atomicAdd(A.ctr + CTR_OVERFLOW, 1ull);
+				if (pos < A.overflow_cap) A.overflow_list[pos] = qi;
+				A.nodes[qi] = OGB_NODE_OVERFLOW;
+			}
+		}
+	}
+	// per-warp counters -> global (one atomic per warp per counter)
+	for (int d = 16; d > 0; d >>= 1) {
+		c_sectors += __shfl_down_sync(0xFFFFFFFFu, c_sectors, d);
+		c_cand += __shfl_down_sync(0xFFFFFFFFu, c_cand, d);
+		c_hits += __shfl_down_sync(0xFFFFFFFFu, c_hits, d);
+	}
+	if (lane == 0) {
+		atomicAdd(A.ctr + CTR_PROBES, c_probes);
+		atomicAdd(A.ctr + CTR_SECTORS, c_sectors);
+		atomicAdd(A.ctr + CTR_CANDIDATES, c_cand);
+		if (MODE == MODE_CONTAIN) atomicAdd(A.ctr + CTR_CONTAIN_HITS, c_hits);
+		else atomicMax(A.ctr + CTR_MAX_DEGREE, (u64)c_maxdeg);
+	}
+}
+
+// Slow path for reads with more than OGB_EC edges (repeats): one block per queued read, two
+// passes over its windows. Pass 0 counts, then a global range is claimed, pass 1 stores, and the
+// block sorts the range in global memory (bitonic). Simple on purpose: it only ever sees a handful
+// of reads.
+__global__ void __launch_bounds__(256) k_scan_big(ScanArgs A, u32 n_over)
+{
+	__shared__ u32 s_count;
+	__shared__ u64 s_start;
+	const u32 h = A.T.h;
+	for (u32 it = blockIdx.x; it < n_over; it += gridDim.x) {
+		u32 qi = A.overflow_list[it];
+		u64 off; u32 L1;
+		read_geom(A.R, qi, off, L1);
+		const u64 *s = A.R.words + off;
+		const u32 nwin = L1 - h - 1;
+		for (int pass = 0; pass < 2; pass++) {
+			if (threadIdx.x == 0) s_count = 0;
+			__syncthreads();
+			for (u32 j = 1 + threadIdx.x; j <= nwin; j += blockDim.x) {
+				u64 hash = key_hash(s, j, h);
+				u32 fp = (u32)(hash >> 32), b = bucket_of(hash, A.T.nb);
+				for (;;) {
+					u64 sl[OGB_SLOTS];
+					load_bucket(A.T.slots, b, sl);
+					bool full = true;
+					for (int k = 0; k < OGB_SLOTS; k++) {
+						if (sl[k] == 0) { full = false; continue; }
+						if ((u32)(sl[k] >> 32) != fp) continue;
+						u64 e0 = 0, e1 = 0;
+						int ne = verify_candidate<MODE_OVERLAP>(A, s, qi, L1, j, (u32)sl[k], e0, e1);
+						if (ne) {
+							u32 pos = atomicAdd(&s_count, (u32)ne);
+							if (pass == 1 && s_start + pos + ne <= A.edge_cap) {
+								A.edges[s_start + pos] = e0;
+								if (ne == 2) A.edges[s_start + pos + 1] = e1;
+							}
+						}
+					}
+					if (!full) break;
+					b = (b + 1 == A.T.nb) ? 0 : b + 1;
+				}
+			}
+			__syncthreads();
+			if (pass == 0) {
+				if (threadIdx.x == 0) {
+					u32 m = 1; while (m < s_count) m <<= 1;                  // padded to a power of two for the sort
+					s_start = atomicAdd(A.ctr + CTR_EDGE_CURSOR, (u64)m);
+					atomicMax(A.ctr + CTR_MAX_DEGREE, (u64)s_count);
+				}
+				__syncthreads();
+			}
+		}
+		u32 n = s_count, m = 1;
+		while (m < n) m <<= 1;
+		u64 start = s_start;
+		if (start + m <= A.edge_cap) {
+			u64 *buf = A.edges + start;
+			for (u32 i = n + threadIdx.x; i < m; i += blockDim.x) buf[i] = ~0ull;
+			__syncthreads();
+			for (u32 k = 2; k <= m; k <<= 1)
+				for (u32 jj = k >> 1; jj > 0; jj >>= 1) {
+					for (u32 t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+						u32 i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1)), l = i | jj;
+						bool up = (i & k) == 0;
+						u64 x = buf[i], y = buf[l];
+						if ((x > y) == up) { buf[i] = y; buf[l] = x; }
+					}
+					__syncthreads();
+				}
+		} else if (threadIdx.x == 0) atomicAdd(A.ctr + CTR_EDGES_DROPPED, (u64)n);
+		if (threadIdx.x == 0) A.nodes[qi] = (start << OGB_DEG_BITS) | n;
+		__syncthreads();
+	}
+}
+
+// superReadID decode + contained bitmap: one thread per read.
+__global__ void k_contained_bitmap(const u64 *__restrict__ sup, u32 n, u32 *__restrict__ bitmap, u64 *ctr)
+{
+	u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+	bool c = idx < n && sup[idx] != 0;
+	u32 bal = __ballot_sync(0xFFFFFFFFu, c);
+	if ((threadIdx.x & 31) == 0 && idx < n) {
+		bitmap[idx >> 5] = bal;
+		if (bal) atomicAdd(ctr + CTR_N_CONTAINED, (u64)__popc(bal));
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: transitive-edge marking, one warp per node (OverlapGraph.cpp:574-615).
+// The neighbour set (destination node -> INPLAY/ELIMINATED) is an open-addressing set in shared
+// memory (degree <= 256) or in a global scratch pool (larger). Pivots are walked sequentially in
+// adjacency order; the adjacency of an in-play pivot is scanned by all lanes.
+// ------------------------------------------------------------------------------------------------
+struct MarkArgs {
+	const u64 *nodes;
+	const u64 *edges;
+	unsigned char *eflag;       // per edge: 1 = eliminated in the marking of its own node
+	u32 lo, hi;                 // node indices [lo, hi) handled by this rank
+	u32 *scratch_keys;          // global pool for big nodes
+	unsigned char *scratch_state;
+	u64 scratch_cap;
+	u64 *ctr;
+};
+
+__device__ __forceinline__ u32 set_hash(u32 key, u32 capmask) { return (key * 2654435761u) >> 7 & capmask; }
+
+__device__ __forceinline__ u32 set_insert(u32 *keys, u32 capmask, u32 key)
+{
+	u32 s = set_hash(key, capmask);
+	for (;;) {
+		u32 cur = atomicCAS(keys + s, 0u, key);
+		if (cur == 0 || cur == key) return s;
+		s = (s + 1) & capmask;
+	}
+}
+__device__ __forceinline__ int set_find(const u32 *keys, u32 capmask, u32 key)
+{
+	u32 s = set_hash(key, capmask);
+	for (;;) {
+		u32 cur = keys[s];
+		if (cur == key) return (int)s;
+		if (cur == 0) return -1;
+		s = (s + 1) & capmask;
+	}
+}
+
+__global__ void __launch_bounds__(OGB_WARPS * 32) k_mark(MarkArgs A)
+{
+	__shared__ u32 s_keys[OGB_WARPS][OGB_SETCAP];
+	__shared__ unsigned char s_state[OGB_WARPS][OGB_SETCAP];
+	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const u32 gw = blockIdx.x * OGB_WARPS + wib, nwarps = gridDim.x * OGB_WARPS;
+	u64 c_entries = 0, c_pivots = 0;
+
+	for (u32 u = A.lo + gw; u < A.hi; u += nwarps) {
+		u64 nd = __ldg(A.nodes + u);
+		u32 deg = (u32)(nd & OGB_DEG_MASK);
+		if (deg == 0) continue;
+		const u64 start = nd >> OGB_DEG_BITS;
+		u32 cap = 64;
+		while (cap < 2 * deg) cap <<= 1;
+		u32 *keys; unsigned char *st;
+		if (cap <= OGB_SETCAP) { keys = s_keys[wib]; st = s_state[wib]; }
+		else {
+			u64 base = 0;
+			if (lane == 0) base = atomicAdd(A.ctr + CTR_SCRATCH_CURSOR, (u64)cap);
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			if (base + cap > A.scratch_cap) { if (lane == 0) atomicAdd(A.ctr + CTR_SCRATCH_FAIL, 1ull); continue; }
+			keys = A.scratch_keys + base; st = A.scratch_state + base;
+		}
+		const u32 capmask = cap - 1;
+		for (u32 i = lane; i < cap; i += 32) keys[i] = 0;
+		__syncwarp();
+		// mark all neighbours INPLAY (:577-578)
+		for (u32 k = lane; k < deg; k += 32) {
+			u32 s = set_insert(keys, capmask, edge_dst(__ldg(A.edges + start + k)));
+			st[s] = 1;
+		}
+		__syncwarp();
+		// pivots in adjacency (offset) order (:580-600)
+		for (u32 i = 0; i < deg; i++) {
+			u64 e = __ldg(A.edges + start + i);
+			u32 v = edge_dst(e), t1 = edge_orient(e);
+			int sv = set_find(keys, capmask, v);
+			if (st[sv] != 1) continue;                                       // eliminated pivots are skipped (:583)
+			u64 ndv = __ldg(A.nodes + (v - 1));
+			u32 degv = (u32)(ndv & OGB_DEG_MASK);
+			u64 startv = ndv >> OGB_DEG_BITS;
+			c_pivots++; c_entries += degv;
+			for (u32 k = lane; k < degv; k += 32) {
+				u64 f = __ldg(A.edges + startv + k);
+				if (compatible(t1, edge_orient(f))) {
+					int sw = set_find(keys, capmask, edge_dst(f));
+					if (sw >= 0 && st[sw] == 1) st[sw] = 2;                  // :588-596
+				}
+			}
+			__syncwarp();
+		}
+		// flag own edges to eliminated nodes (:601-607; the twin half is applied in k_twin_keep)
+		for (u32 k = lane; k < deg; k += 32) {
+			int s = set_find(keys, capmask, edge_dst(__ldg(A.edges + start + k)));
+			A.eflag[start + k] = st[s] == 2;
+		}
+		__syncwarp();
+	}
+	if (lane == 0) { atomicAdd(A.ctr + CTR_PIVOT_ENTRIES, c_entries); atomicAdd(A.ctr + CTR_ACTIVE_PIVOTS, c_pivots); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: an edge (u,w) survives iff it was not flagged by u's marking and its twin was not flagged by
+// w's marking (:605-606, :623-661). Marks are per destination NODE, so w's verdict on u is read off
+// any (w,u) entry of w's adjacency -- no twin pointers are needed.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OGB_WARPS * 32) k_twin_keep(const u64 *__restrict__ nodes, const u64 *__restrict__ edges,
+                                                              const unsigned char *__restrict__ eflag, unsigned char *__restrict__ keep,
+                                                              u32 *__restrict__ cnt, u32 lo, u32 hi, u64 *ctr)
+{
+	const u32 lane = threadIdx.x & 31;
+	const u32 gw = blockIdx.x * OGB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * OGB_WARPS;
+	u32 c_nodes = 0;
+	for (u32 u = lo + gw; u < hi; u += nwarps) {
+		u64 nd = __ldg(nodes + u);
+		u32 deg = (u32)(nd & OGB_DEG_MASK);
+		u64 start = nd >> OGB_DEG_BITS;
+		u32 total = 0;
+		for (u32 kb = 0; kb < deg; kb += 32) {
+			u32 k = kb + lane;
+			bool kp = false;
+			if (k < deg && !eflag[start + k]) {
+				u32 w = edge_dst(__ldg(edges + start + k));
+				u64 ndw = __ldg(nodes + (w - 1));
+				u32 degw = (u32)(ndw & OGB_DEG_MASK);
+				u64 startw = ndw >> OGB_DEG_BITS;
+				kp = true;
+				bool found = false;
+				for (u32 x = 0; x < degw; x++)
+					if (edge_dst(__ldg(edges + startw + x)) == u + 1) { kp = !eflag[startw + x]; found = true; break; }
+				if (!found) atomicAdd(ctr + CTR_ASYMMETRIC, 1ull);
+			}
+			if (k < deg) keep[start + k] = kp;
+			total += __popc(__ballot_sync(0xFFFFFFFFu, kp));
+		}
+		if (lane == 0) { cnt[u] = total; c_nodes += total > 0; }
+	}
+	if (lane == 0 && c_nodes) atomicAdd(ctr + CTR_NODES_FINAL, (u64)c_nodes);
+}
+
+// Exclusive scan of u32 counts into u64 offsets: (1) per-block sums, (2) one block scans the sums,
+// (3) per-block scan + base.
+#define OGB_SCAN_ITEMS 2048     // per block of 256 threads (8 per thread)
+__global__ void __launch_bounds__(256) k_scan_sums(const u32 *__restrict__ cnt, u32 n, u64 *__restrict__ sums)
+{
+	__shared__ u64 sh[8];
+	u64 base = (u64)blockIdx.x * OGB_SCAN_ITEMS, acc = 0;
+	for (u32 i = threadIdx.x; i < OGB_SCAN_ITEMS; i += 256) if (base + i < n) acc += cnt[base + i];
+	for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d);
+	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0) { u64 t = 0; for (int i = 0; i < 8; i++) t += sh[i]; sums[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) k_scan_top(u64 *__restrict__ sums, u32 nblocks, u64 *__restrict__ total)
+{
+	__shared__ u64 sh[1024];
+	__shared__ u64 carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (u32 base = 0; base < nblocks; base += 1024) {
+		u32 i = base + threadIdx.x;
+		u64 v = i < nblocks ? sums[i] : 0;
+		sh[threadIdx.x] = v;
+		__syncthreads();
+		for (u32 d = 1; d < 1024; d <<= 1) {
+			u64 x = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+			__syncthreads();
+			sh[threadIdx.x] += x;
+			__syncthreads();
+		}
+		if (i < nblocks) sums[i] = carry + sh[threadIdx.x] - v;              // exclusive
+		__syncthreads();
+		if (threadIdx.x == 1023) carry += sh[1023];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(256) k_scan_apply(const u32 *__restrict__ cnt, u32 n, const u64 *__restrict__ sums, u64 *__restrict__ out)
+{
+	__shared__ u64 sh[256];
+	u64 base = (u64)blockIdx.x * OGB_SCAN_ITEMS;
+	u32 v[8]; u64 local = 0;
+	for (int i = 0; i < 8; i++) { u64 p = base + threadIdx.x * 8 + i; v[i] = p < n ? cnt[p] : 0; local += v[i]; }
+	sh[threadIdx.x] = local;
+	__syncthreads();
+	for (u32 d = 1; d < 256; d <<= 1) {
+		u64 x = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+		__syncthreads();
+		sh[threadIdx.x] += x;
+		__syncthreads();
+	}
+	u64 run = sums[blockIdx.x] + sh[threadIdx.x] - local;
+	for (int i = 0; i < 8; i++) { u64 p = base + threadIdx.x * 8 + i; if (p < n) out[p] = run; run += v[i]; }
+}
+
+// Final edge records, sorted by (src, offset, dst, orient): node order x adjacency order.
+__global__ void __launch_bounds__(OGB_WARPS * 32) k_compact(const u64 *__restrict__ nodes, const u64 *__restrict__ edges,
+                                                            const unsigned char *__restrict__ keep, const u64 *__restrict__ pos,
+                                                            ogb_edge *__restrict__ out, u64 out_base, u32 lo, u32 hi)
+{
+	const u32 lane = threadIdx.x & 31;
+	const u32 gw = blockIdx.x * OGB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * OGB_WARPS;
+	for (u32 u = lo + gw; u < hi; u += nwarps) {
+		u64 nd = __ldg(nodes + u);
+		u32 deg = (u32)(nd & OGB_DEG_MASK);
+		if (deg == 0) continue;
+		u64 start = nd >> OGB_DEG_BITS;
+		u64 p = pos[u] - out_base;
+		for (u32 kb = 0; kb < deg; kb += 32) {
+			u32 k = kb + lane;
+			bool kp = k < deg && keep[start + k];
+			u32 bal = __ballot_sync(0xFFFFFFFFu, kp);
+			if (kp) {
+				u64 e = __ldg(edges + start + k);
+				ogb_edge r;
+				r.src = u + 1; r.dst = edge_dst(e); r.offset = (uint16_t)edge_offset(e); r.orient = (uint8_t)edge_orient(e); r.reserved = 0;
+				out[p + __popc(bal & ((1u << lane) - 1))] = r;
+			}
+			p += __popc(bal);
+		}
+	}
+}
+
+// Pre-reduction edges as records (tests / keep_pre): one warp per node, position = start.
+__global__ void __launch_bounds__(OGB_WARPS * 32) k_export_pre(const u64 *__restrict__ nodes, const u64 *__restrict__ edges,
+                                                               const u64 *__restrict__ pos, ogb_edge *__restrict__ out, u32 n)
+{
+	const u32 lane = threadIdx.x & 31;
+	const u32 gw = blockIdx.x * OGB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * OGB_WARPS;
+	for (u32 u = gw; u < n; u += nwarps) {
+		u64 nd = __ldg(nodes + u);
+		u32 deg = (u32)(nd & OGB_DEG_MASK);
+		u64 start = nd >> OGB_DEG_BITS, p = pos[u];
+		for (u32 k = lane; k < deg; k += 32) {
+			u64 e = __ldg(edges + start + k);
+			ogb_edge r;
+			r.src = u + 1; r.dst = edge_dst(e); r.offset = (uint16_t)edge_offset(e); r.orient = (uint8_t)edge_orient(e); r.reserved = 0;
+			out[p + k] = r;
+		}
+	}
+}
+__global__ void k_degrees(const u64 *__restrict__ nodes, u32 n, u32 *__restrict__ cnt)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) cnt[i] = (u32)(nodes[i] & OGB_DEG_MASK);
+}
+
+// ------------------------------------------------------------------------------------------------
+// HashTable::getListOfReads (HashTable.cpp:202-221) for a batch of packed keys: one thread per key.
+// pass 0 counts matches into cnt[k]; pass 1 writes id | o<<62 at out[pos[k]..]. Matches are
+// verified exactly against the stored read's prefix/suffix.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_lookup(ReadStore R, Table T, const u64 *__restrict__ keys, u32 kw, u64 n_keys, u32 *__restrict__ cnt,
+                         const u64 *__restrict__ pos, u64 *__restrict__ out, int pass)
+{
+	u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_keys) return;
+	const u64 *key = keys + k * (kw + 1);
+	u64 hash = key_hash(key, 0, T.h);
+	u32 fp = (u32)(hash >> 32), b = bucket_of(hash, T.nb), c = 0;
+	for (;;) {
+		u64 sl[OGB_SLOTS];
+		load_bucket(T.slots, b, sl);
+		bool full = true;
+		for (int s = 0; s < OGB_SLOTS; s++) {
+			if (sl[s] == 0) { full = false; continue; }
+			if ((u32)(sl[s] >> 32) != fp) continue;
+			u32 val = (u32)sl[s], ri = (val >> 2) - 1, o = val & 3;
+			u64 off; u32 L;
+			read_geom(R, ri, off, L);
+			const u64 *t = R.words + off + (o >> 1) * padded_words(L);
+			if (!region_equal(key, 0, t, (o & 1) ? L - T.h : 0, T.h)) continue;
+			if (pass == 1) out[pos[k] + c] = (u64)(ri + 1) | ((u64)o << 62);
+			c++;
+		}
+		if (!full) break;
+		b = (b + 1 == T.nb) ? 0 : b + 1;
+	}
+	if (pass == 0) cnt[k] = c;
+}

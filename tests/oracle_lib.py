@@ -1,0 +1,168 @@
+"""TEST INFRASTRUCTURE: ctypes binding of oracle/liboracle.so (the CPU restatement) and a runner for
+oracle/_ref/ref_overlap (the unmodified reference behind oracle/ref_harness.cpp)."""
+import ctypes as C
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_overlap")
+
+_lib = None
+
+
+def _olib():
+    global _lib
+    if _lib is None:
+        l = C.CDLL(ORACLE_SO)
+        vp, u64 = C.c_void_p, C.c_uint64
+        l.oracle_create.restype = vp
+        l.oracle_destroy.argtypes = [vp]
+        l.oracle_load_reads.argtypes = [vp, vp, vp, u64, C.c_uint32]
+        for f in ("oracle_n_unique", "oracle_n_good", "oracle_shortest", "oracle_longest", "oracle_total_bases"):
+            getattr(l, f).restype = u64
+            getattr(l, f).argtypes = [vp]
+        l.oracle_read_info.argtypes = [vp, vp, vp, vp, vp]
+        l.oracle_get_read.argtypes = [vp, u64, C.c_int, vp]
+        l.oracle_sorted_reads.argtypes = [vp, vp, vp]
+        l.oracle_build_index.argtypes = [vp]
+        l.oracle_hash_string_length.argtypes = [vp]
+        l.oracle_hash_string_length.restype = C.c_uint32
+        l.oracle_lookup.argtypes = [vp, C.c_char_p, C.c_uint32, vp, C.c_uint32]
+        l.oracle_lookup.restype = C.c_uint32
+        l.oracle_mark_contained.argtypes = [vp]
+        l.oracle_build_graph.argtypes = [vp, C.c_int, C.c_int]
+        l.oracle_n_edges.argtypes = [vp, C.c_int]
+        l.oracle_n_edges.restype = u64
+        l.oracle_get_edges.argtypes = [vp, C.c_int, vp]
+        l.oracle_counters.argtypes = [vp, vp]
+        _lib = l
+    return _lib
+
+
+class Oracle:
+    """CPU restatement of Dataset -> HashTable -> OverlapGraph (see oracle/omega_oracle.cpp)."""
+    BFS, THREE_PHASE = 0, 1
+
+    def __init__(self, bases, offsets, min_overlap):
+        self.l = _olib()
+        self.h = self.l.oracle_create()
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.l.oracle_load_reads(self.h, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, min_overlap)
+        self.n = self.l.oracle_n_unique(self.h)
+        self.n_good = self.l.oracle_n_good(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.l.oracle_destroy(self.h)
+            self.h = None
+
+    def read_info(self):
+        sup = np.zeros(self.n, np.uint64); ln = np.zeros(self.n, np.uint32)
+        fr = np.zeros(self.n, np.uint32); fnv = np.zeros(self.n, np.uint64)
+        self.l.oracle_read_info(self.h, sup.ctypes.data, ln.ctypes.data, fr.ctypes.data, fnv.ctypes.data)
+        return dict(sup=sup, len=ln, freq=fr, fnv=fnv)
+
+    def get_read(self, rid, reverse=False):
+        buf = C.create_string_buffer(65536)
+        n = self.l.oracle_get_read(self.h, rid, 1 if reverse else 0, buf)
+        return buf.raw[:n].decode()
+
+    def sorted_reads(self):
+        tot = self.l.oracle_total_bases(self.h)
+        bases = np.zeros(tot, np.uint8); offs = np.zeros(self.n + 1, np.uint64)
+        self.l.oracle_sorted_reads(self.h, bases.ctypes.data, offs.ctypes.data)
+        return bases, offs
+
+    def build_index(self):
+        self.l.oracle_build_index(self.h)
+        return self.l.oracle_hash_string_length(self.h)
+
+    def lookup(self, key):
+        k = key.encode() if isinstance(key, str) else bytes(key)
+        cap = 64
+        while True:
+            out = np.zeros(cap, np.uint64)
+            n = self.l.oracle_lookup(self.h, k, len(k), out.ctypes.data, cap)
+            if n <= cap:
+                return out[:n]
+            cap = n
+
+    def mark_contained(self):
+        self.l.oracle_mark_contained(self.h)
+
+    def build_graph(self, mode=0, threads=1):
+        self.l.oracle_build_graph(self.h, mode, threads)
+
+    def edges(self, pre=False):
+        n = self.l.oracle_n_edges(self.h, 1 if pre else 0)
+        out = np.zeros((n, 4), np.uint32)
+        self.l.oracle_get_edges(self.h, 1 if pre else 0, out.ctypes.data)
+        return out
+
+    def counters(self):
+        out = np.zeros(10, np.uint64)
+        self.l.oracle_counters(self.h, out.ctypes.data)
+        keys = ["number_of_nodes", "number_of_edges", "P_c", "P_e", "C_c", "C_e", "T", "active_pivots", "max_degree", "E_pre"]
+        return dict(zip(keys, (int(x) for x in out)))
+
+    def run_all(self, mode=0, threads=1):
+        self.build_index()
+        self.mark_contained()
+        self.build_graph(mode, threads)
+        return self
+
+
+def have_reference():
+    return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
+
+
+DUMP_READ = np.dtype([("sup", "<u8"), ("len", "<u4"), ("freq", "<u4"), ("fnv", "<u8")])
+
+
+def read_dump(path):
+    with open(path, "rb") as f:
+        hdr = np.frombuffer(f.read(48), dtype="<u8")
+        assert hdr[0] == 0x31504d554442474f, "bad dump magic"
+        n, ne = int(hdr[1]), int(hdr[2])
+        reads = np.frombuffer(f.read(n * DUMP_READ.itemsize), dtype=DUMP_READ)
+        edges = np.frombuffer(f.read(ne * 16), dtype="<u4").reshape(ne, 4)
+    return dict(n=n, number_of_nodes=int(hdr[3]), number_of_edges=int(hdr[4]), h=int(hdr[5]), reads=reads,
+                edges=sort_tuples(edges))
+
+
+def sort_tuples(e):
+    """canonical order (src, offset, dst, orient) of an (n,4) [src,dst,offset,orient] array."""
+    e = np.asarray(e, dtype=np.uint32).reshape(-1, 4)
+    if len(e) == 0:
+        return e
+    idx = np.lexsort((e[:, 3], e[:, 1], e[:, 2], e[:, 0]))
+    return np.ascontiguousarray(e[idx])
+
+
+def run_reference(fasta_paths, min_overlap, paired=False, want_table=False, binary=REF_BIN, timeout=3600):
+    """Runs the unmodified reference on FASTA files; returns (dump dict, timing json, table lists|None)."""
+    with tempfile.TemporaryDirectory() as td:
+        dump, js, tab = os.path.join(td, "d.bin"), os.path.join(td, "t.json"), os.path.join(td, "tab.bin")
+        cmd = [binary, "-l", str(min_overlap), "--dump", dump, "--json", js]
+        for p in fasta_paths:
+            cmd += ["-pe" if paired else "-se", p]
+        if want_table:
+            cmd += ["--table", tab]
+        subprocess.run(cmd, check=True, timeout=timeout, cwd=td)
+        d = read_dump(dump)
+        with open(js) as f:
+            t = json.load(f)
+        table = None
+        if want_table:
+            raw = np.fromfile(tab, dtype=np.uint8)
+            table, p = [], 0
+            for _ in range(d["n"] * 4):
+                c = int(np.frombuffer(raw[p:p + 4].tobytes(), "<u4")[0]); p += 4
+                table.append(np.frombuffer(raw[p:p + 8 * c].tobytes(), "<u8").copy()); p += 8 * c
+        return d, t, table

@@ -1,0 +1,159 @@
+"""GPU parity (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, must be
+bit-exact with the oracle for every stage of the hot path -- K1 index content, K2 superReadID, K3
+pre-reduction edges, K5/K6 post-reduction edges -- on seeded data sets and the committed goldens."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import datasets
+from oracle_lib import Oracle, sort_tuples
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from metagenomics_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def build_gpu(ctx, cfg, keep_pre=True):
+    from metagenomics_b200 import Dataset, HashTable, OverlapGraph
+    ds = Dataset(bases=cfg["bases"], offsets=cfg["offsets"], minOverlap=cfg["min_overlap"])
+    ht = HashTable(ctx)
+    ht.insertDataset(ds, cfg["min_overlap"])
+    og = OverlapGraph(ht, keep_pre=keep_pre)
+    return ds, ht, og
+
+
+def assert_same_edges(got, want, what):
+    got = sort_tuples(got)
+    if got.shape != want.shape or not np.array_equal(got, want):
+        a = set(map(tuple, got.tolist())); b = set(map(tuple, want.tolist()))
+        raise AssertionError(f"{what}: {len(got)} vs {len(want)} edges; only-gpu {sorted(a - b)[:5]} only-oracle {sorted(b - a)[:5]}")
+
+
+ALL = datasets.small_configs() + datasets.adversarial()
+
+
+@pytest.mark.parametrize("cfg", ALL, ids=[c["name"][:28] for c in ALL])
+def test_graph_matches_oracle(ctx, cfg):
+    from metagenomics_b200 import edges_as_tuples
+    ds, ht, og = build_gpu(ctx, cfg)
+    orc = Oracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"]).run_all(Oracle.BFS)
+    assert ds.getNumberOfUniqueReads() == orc.n
+    # K2: contained-read flags (superReadID, Read.h:50)
+    assert np.array_equal(og.superReadIDs()[1:], orc.read_info()["sup"])
+    # K3: pre-reduction edge multiset (every insertEdge of the reference, OverlapGraph.cpp:416-417)
+    assert_same_edges(edges_as_tuples(og.edges(pre=True)), orc.edges(pre=True), "pre-reduction")
+    # K5+K6: post-reduction edge multiset, node and edge counters (OverlapGraph.cpp:394-397,638-659)
+    fin = og.edges()
+    assert_same_edges(edges_as_tuples(fin), orc.edges(), "post-reduction")
+    c = orc.counters()
+    assert og.getNumberOfEdges() == c["number_of_edges"]
+    assert og.getNumberOfNodes() == c["number_of_nodes"]
+    # the C ABI promises canonical order (src, offset, dst, orient)
+    t = edges_as_tuples(fin)
+    assert np.array_equal(t, sort_tuples(t))
+
+
+@pytest.mark.parametrize("cfg", [datasets.small_configs()[0], datasets.small_configs()[4], datasets.tandem(), datasets.even_h()],
+                         ids=["config1", "config5", "tandem", "even_h"])
+def test_hash_table_content(ctx, cfg):
+    """K1: every key's bucket = the reference's getListOfReads (id | o<<62, ascending id then o)."""
+    ds, ht, og = build_gpu(ctx, cfg, keep_pre=False)
+    orc = Oracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"])
+    h = orc.build_index()
+    assert ht.getHashStringLength() == h == cfg["min_overlap"] - 1
+    assert ht.getHashTableSize() > 8 * orc.n           # at least the reference's slot budget (HashTable.cpp:56)
+    keys = []
+    for i in range(1, orc.n + 1, max(1, orc.n // 700)):
+        f, r = orc.get_read(i), orc.get_read(i, True)
+        keys += [f[:h], f[-h:], r[:h], r[-h:], f[1:1 + h]]
+    keys.append("ACGT" * 100)
+    keys = [k[:h] for k in keys]
+    got = ht.getListsOfReads(keys)
+    for k, g in zip(keys, got):
+        assert np.array_equal(g, orc.lookup(k)), k
+
+
+def test_golden_vectors(ctx):
+    """Fixtures dumped from the UNMODIFIED reference (tests/golden/make_golden.py)."""
+    from metagenomics_b200 import edges_as_tuples
+    files = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+    assert files, "no golden fixtures committed"
+    for f in files:
+        z = np.load(f)
+        cfg = dict(bases=z["bases"], offsets=z["offsets"], min_overlap=int(z["min_overlap"]))
+        ds, ht, og = build_gpu(ctx, cfg, keep_pre=False)
+        assert ds.getNumberOfUniqueReads() == len(z["sup"]), f
+        assert np.array_equal(og.superReadIDs()[1:], z["sup"]), f
+        assert np.array_equal(ds.frequencies(), z["freq"]), f
+        assert_same_edges(edges_as_tuples(og.edges()), z["edges"], os.path.basename(f))
+        assert og.getNumberOfNodes() == int(z["number_of_nodes"]) and og.getNumberOfEdges() == int(z["number_of_edges"])
+
+
+def test_ascii_upload_equals_packed_upload(ctx):
+    """K0 both ways: ogb_reads_upload (ASCII) and ogb_reads_upload_packed give the same graph."""
+    import ctypes as C
+    from metagenomics_b200 import edges_as_tuples
+    from metagenomics_b200._lib import check, lib
+    from metagenomics_b200.api import EDGE_DTYPE
+    for cfg in (datasets.small_configs()[0], datasets.small_configs()[4]):
+        ds, ht, og = build_gpu(ctx, cfg, keep_pre=False)
+        want = og.edges()
+        orc = Oracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"])
+        bases, offs = orc.sorted_reads()
+        check(lib().ogb_reads_upload(ctx._h, bases.ctypes.data, offs.ctypes.data, orc.n))
+        check(lib().ogb_hash_build(ctx._h, cfg["min_overlap"]))
+        check(lib().ogb_build_graph(ctx._h, 0))
+        n = C.c_uint64()
+        check(lib().ogb_graph_edge_count(ctx._h, 0, C.byref(n)))
+        got = np.zeros(n.value, dtype=EDGE_DTYPE)
+        check(lib().ogb_graph_edges(ctx._h, 0, got.ctypes.data, n.value))
+        assert np.array_equal(edges_as_tuples(got), edges_as_tuples(want))
+
+
+def test_rebuild_is_idempotent_and_symmetric(ctx):
+    """Size-independent properties on a larger input (config-2 shape, ~75k reads): building twice gives
+    identical output; every surviving edge has its twin (u,v,o,off) <-> (v,u,twin(o),off) for equal
+    lengths (OverlapGraph.cpp:410-412); output is sorted."""
+    from metagenomics_b200 import edges_as_tuples, synth
+    cfg = synth.config(2, scale=0.05)
+    ds, ht, og = build_gpu(ctx, cfg, keep_pre=False)
+    a = edges_as_tuples(og.edges())
+    og.buildOverlapGraphFromHashTable()
+    b = edges_as_tuples(og.edges())
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, sort_tuples(a))
+    twin = a.copy()
+    twin[:, 0], twin[:, 1] = a[:, 1], a[:, 0]
+    twin[:, 3] = np.array([3, 1, 2, 0], dtype=np.uint32)[a[:, 3]]
+    assert np.array_equal(sort_tuples(twin), a)
+    st = ctx.stats()
+    assert st["edges_final"] == len(a) and st["edges_pre"] >= len(a)
+    orc = Oracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"]).run_all(Oracle.THREE_PHASE, threads=8)
+    assert np.array_equal(a, orc.edges())
+    c = orc.counters()
+    assert st["edges_pre"] == c["E_pre"] and st["pivot_entries"] == c["T"] and st["overlap_probes"] == c["P_e"]
+
+
+def test_empty_and_tiny_inputs(ctx):
+    """Edge cases: no good reads; one read; two overlapping reads."""
+    from metagenomics_b200 import edges_as_tuples
+    for reads, m, n_edges in ((["ACGT"], 10, 0), (["ACGTTGCAAGGCTTAACCGGATATCGCGAATTC"], 10, 0)):
+        cfg = datasets.from_strings(reads, m, "tiny")
+        ds, ht, og = build_gpu(ctx, cfg)
+        assert og.getNumberOfEdges() == n_edges and len(og.edges(pre=True)) == 0
+    g = "ACGTTGCAAGGCTTAACCGGATATCGCGAATTCAGGTCCATGCAAGT"
+    cfg = datasets.from_strings([g[:36], g[8:44]], 12, "pair")
+    ds, ht, og = build_gpu(ctx, cfg)
+    orc = Oracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"]).run_all(Oracle.BFS)
+    assert len(orc.edges()) == 2
+    assert_same_edges(edges_as_tuples(og.edges()), orc.edges(), "pair")
