@@ -84,6 +84,8 @@ typedef struct ogb_stats {
 	float ms_mark;             /* K5 */
 	float ms_reduce;           /* K6 (+C2/C3) */
 	float ms_total;            /* hash_build + mark_contained + build_graph, device time */
+	float ms_scan_kernel;      /* the K3 kernel launch alone (the roofline kernel) */
+	float reserved2;
 } ogb_stats;
 
 int ogb_version(void);
@@ -191,6 +193,13 @@ int ogb_graph_edge_count(ogb_context *ctx, int which, uint64_t *n);
 int ogb_graph_edges(ogb_context *ctx, int which, ogb_edge *out, uint64_t cap);
 
 int ogb_get_stats(ogb_context *ctx, ogb_stats *out);
+
+/* Measurement helpers: CUDA events on the context's stream (the stream every kernel of this library
+ * is launched on). ogb_timer_end synchronises and returns the elapsed device time. ogb_l2_flush
+ * overwrites a scratch buffer of `bytes` (> L2) so that the next build starts cold. */
+int ogb_timer_begin(ogb_context *ctx);
+int ogb_timer_end(ogb_context *ctx, float *ms);
+int ogb_l2_flush(ogb_context *ctx, size_t bytes);
 
 /* Pinned host memory for upload/download staging (released by ogb_free_host). */
 int ogb_alloc_host(void **out, size_t bytes);

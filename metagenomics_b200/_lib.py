@@ -27,10 +27,10 @@ class Stats(C.Structure):
         "active_pivots", "edges_final", "nodes_final", "max_degree", "overflow_reads")] + [
         ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)] + [(n, C.c_float) for n in (
             "ms_pack", "ms_hash_build", "ms_contain", "ms_overlap", "ms_exchange_pre", "ms_mark", "ms_reduce",
-            "ms_total")]
+            "ms_total", "ms_scan_kernel", "reserved2")]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
 
 
 # every symbol include/ogb.h declares: name -> (restype, argtypes)
@@ -73,6 +73,9 @@ PROTOTYPES = {
     "ogb_graph_edge_count": (C.c_int, [_vp, C.c_int, _u64p]),
     "ogb_graph_edges": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
     "ogb_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "ogb_timer_begin": (C.c_int, [_vp]),
+    "ogb_timer_end": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "ogb_l2_flush": (C.c_int, [_vp, C.c_size_t]),
     "ogb_alloc_host": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "ogb_free_host": (None, [_vp]),
     "ogb_synth_genome": (C.c_int, [C.c_uint64, C.c_uint64, _vp]),

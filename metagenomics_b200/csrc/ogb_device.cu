@@ -83,7 +83,7 @@ template <class T> struct Pool {
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum { EV_BEGIN = 0, EV_PACK0, EV_PACK1, EV_HASH0, EV_HASH1, EV_CONT0, EV_CONT1, EV_OVL0, EV_OVL1, EV_XPRE1, EV_MARK1, EV_RED1, EV_COUNT };
+enum { EV_BEGIN = 0, EV_PACK0, EV_PACK1, EV_HASH0, EV_HASH1, EV_CONT0, EV_CONT1, EV_OVL0, EV_OVL1, EV_XPRE1, EV_MARK1, EV_RED1, EV_K3A, EV_K3B, EV_T0, EV_T1, EV_COUNT };
 
 struct ogb_context {
 	int device = 0, rank = 0, nranks = 1, sm_count = 148;
@@ -110,9 +110,11 @@ struct ogb_context {
 	Pool<unsigned char> eflag, keep, scratch_state;
 	Pool<u32> cnt, overflow, scratch_keys;
 	Pool<ogb_edge> fin, pre;
+	Pool<char> flush;
 	u64 n_final = 0, n_pre = 0;
 	bool have_graph = false, have_pre = false;
 	u64 *d_ctr = nullptr, *h_ctr = nullptr;
+	u64 *d_tot = nullptr;            // [0] scan total of pre-reduction degrees, [1] of surviving edges
 	ogb_stats st = {};
 	u32 launches = 0;
 
@@ -162,6 +164,8 @@ static int context_create_common(ogb_context **out, int device)
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (int i = 0; i < EV_COUNT; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
 	CUDA_TRY(cudaMalloc((void **)&c->d_ctr, CTR_COUNT * sizeof(u64)));
+	CUDA_TRY(cudaMalloc((void **)&c->d_tot, 2 * sizeof(u64)));
+	CUDA_TRY(cudaMemset(c->d_tot, 0, 2 * sizeof(u64)));
 	CUDA_TRY(cudaMallocHost((void **)&c->h_ctr, CTR_COUNT * sizeof(u64)));
 	CUDA_TRY(cudaMemset(c->d_ctr, 0, CTR_COUNT * sizeof(u64)));
 	*out = c;
@@ -205,8 +209,9 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	c->words.release(); c->meta.release(); c->stage_bytes.release(); c->stage_offs.release(); c->stage_lens.release();
 	c->slots.release(); c->sup.release(); c->contained.release(); c->nodes.release(); c->edges.release(); c->pos.release();
 	c->sums.release(); c->eflag.release(); c->keep.release(); c->scratch_state.release(); c->cnt.release(); c->overflow.release();
-	c->scratch_keys.release(); c->fin.release(); c->pre.release();
+	c->scratch_keys.release(); c->fin.release(); c->pre.release(); c->flush.release();
 	if (c->d_ctr) cudaFree(c->d_ctr);
+	if (c->d_tot) cudaFree(c->d_tot);
 	if (c->h_ctr) cudaFreeHost(c->h_ctr);
 	for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -575,8 +580,10 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		if (attempt == 4) { ogb_set_error("ogb_build_graph: edge pool kept overflowing"); return OGB_E_CAPACITY; }
 		OGB_TRY(ctr_zero(c));
 		ScanArgs a = scan_args(c, lo, hi);
+		CUDA_TRY(cudaEventRecord(c->ev[EV_K3A], c->stream));
 		k_scan<MODE_OVERLAP><<<grid_for(c, (const void *)k_scan<MODE_OVERLAP>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(a);
 		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaEventRecord(c->ev[EV_K3B], c->stream));
 		c->launches++;
 		OGB_TRY(ctr_fetch(c));
 		u64 n_over = c->h_ctr[CTR_OVERFLOW];
@@ -596,7 +603,8 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	c->st.probe_sectors = c->h_ctr[CTR_SECTORS];
 	c->st.candidates = c->h_ctr[CTR_CANDIDATES];
 	c->st.max_degree = c->h_ctr[CTR_MAX_DEGREE];
-	c->st.edges_pre_local = local_edges;
+	const u64 local_exact = local_edges - c->h_ctr[CTR_PAD];              // the slow path pads to powers of two
+	c->st.edges_pre_local = local_exact;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL1], c->stream));
 
 	// ---- C1: every rank needs the whole pre-reduction adjacency (a pivot can live anywhere)
@@ -635,15 +643,25 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		OGB_TRY(allgatherv(c, c->edges.p, sizeof(u64), seg_off, seg_cnt));
 		NCCL_TRY(g_nccl.AllGather(c->nodes.p + per * c->rank, c->nodes.p, per, NCCL_UINT64, c->comm, c->stream));
 	}
-	c->st.edges_pre = total_edges;
-	c->n_pre = total_edges;
+	u64 exact_total = local_exact;
+	if (G > 1) {
+		Pool<u64> d_x;
+		OGB_TRY(d_x.ensure(2));
+		CUDA_TRY(cudaMemcpyAsync(d_x.p, &local_exact, sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+		NCCL_TRY(g_nccl.AllReduce(d_x.p, d_x.p + 1, 1, NCCL_UINT64, 0 /*ncclSum*/, c->comm, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(&exact_total, d_x.p + 1, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		d_x.release();
+	}
+	c->st.edges_pre = exact_total;
+	c->n_pre = exact_total;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_XPRE1], c->stream));
 
 	if (keep_pre) {
 		// export the pre-reduction adjacency as records, in node order
 		OGB_TRY(c->pre.ensure(std::max<u64>(total_edges, 1)));
 		k_degrees<<<(n + 255) / 256, 256, 0, c->stream>>>(c->nodes.p, n, c->cnt.p);
-		OGB_TRY(exclusive_scan(c, c->cnt.p, n, c->pos.p, c->d_ctr + CTR_LOOKUP_TOTAL));
+		OGB_TRY(exclusive_scan(c, c->cnt.p, n, c->pos.p, c->d_tot));
 		k_export_pre<<<grid_for(c, (const void *)k_export_pre, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->edges.p, c->pos.p, c->pre.p, n);
 		CUDA_TRY(cudaGetLastError());
 		c->have_pre = true;
@@ -677,13 +695,19 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	CUDA_TRY(cudaGetLastError());
 	c->launches++;
 	if (G > 1) NCCL_TRY(g_nccl.AllGather(c->cnt.p + per * c->rank, c->cnt.p, per, NCCL_UINT32, c->comm, c->stream));
-	OGB_TRY(exclusive_scan(c, c->cnt.p, n, c->pos.p, c->d_ctr + CTR_LOOKUP_TOTAL));
+	OGB_TRY(exclusive_scan(c, c->cnt.p, n, c->pos.p, c->d_tot + 1));
 	OGB_TRY(c->fin.ensure(std::max<u64>(c->edges.cap, 1)));                // E_final <= E_pre: no sync needed to size it
 	k_compact<<<grid_for(c, (const void *)k_compact, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->edges.p, c->keep.p, c->pos.p, c->fin.p, 0, lo, hi);
 	CUDA_TRY(cudaGetLastError());
 	c->launches++;
 	OGB_TRY(ctr_fetch(c));
-	c->n_final = c->h_ctr[CTR_LOOKUP_TOTAL];
+	{
+		u64 tot[2] = {0, 0};
+		CUDA_TRY(cudaMemcpyAsync(tot, c->d_tot, 2 * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		c->n_final = tot[1];
+		if (keep_pre) c->n_pre = tot[0];
+	}
 	if (G > 1) {
 		// C3: final edges of every rank's node range (allgatherv over the positions just scanned)
 		std::vector<u64> bounds(G + 1, 0);
@@ -711,6 +735,7 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	c->st.edges_final = c->n_final;
 	c->st.nodes_final = c->h_ctr[CTR_NODES_FINAL];
 	c->st.ms_overlap = ev_ms(c, EV_OVL0, EV_OVL1);
+	c->st.ms_scan_kernel = ev_ms(c, EV_K3A, EV_K3B);
 	c->st.ms_exchange_pre = ev_ms(c, EV_OVL1, EV_XPRE1);
 	c->st.ms_mark = ev_ms(c, EV_XPRE1, EV_MARK1);
 	c->st.ms_reduce = ev_ms(c, EV_MARK1, EV_RED1);
@@ -745,5 +770,33 @@ extern "C" int ogb_get_stats(ogb_context *c, ogb_stats *out)
 {
 	if (!c || !out) { ogb_set_error("ogb_get_stats: NULL argument"); return OGB_E_ARG; }
 	*out = c->st;
+	return OGB_OK;
+}
+
+extern "C" int ogb_timer_begin(ogb_context *c)
+{
+	if (!c) { ogb_set_error("NULL context"); return OGB_E_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	CUDA_TRY(cudaEventRecord(c->ev[EV_T0], c->stream));
+	return OGB_OK;
+}
+
+extern "C" int ogb_timer_end(ogb_context *c, float *ms)
+{
+	if (!c || !ms) { ogb_set_error("ogb_timer_end: NULL argument"); return OGB_E_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	CUDA_TRY(cudaEventRecord(c->ev[EV_T1], c->stream));
+	CUDA_TRY(cudaEventSynchronize(c->ev[EV_T1]));
+	CUDA_TRY(cudaEventElapsedTime(ms, c->ev[EV_T0], c->ev[EV_T1]));
+	return OGB_OK;
+}
+
+extern "C" int ogb_l2_flush(ogb_context *c, size_t bytes)
+{
+	if (!c) { ogb_set_error("NULL context"); return OGB_E_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	OGB_TRY(c->flush.ensure(bytes));
+	CUDA_TRY(cudaMemsetAsync(c->flush.p, 0x5a, bytes, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	return OGB_OK;
 }

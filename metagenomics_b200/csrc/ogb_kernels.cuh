@@ -47,7 +47,7 @@ enum { MODE_OVERLAP = 0, MODE_CONTAIN = 1 };
 enum {
 	CTR_EDGE_CURSOR = 0, CTR_OVERFLOW, CTR_PROBES, CTR_SECTORS, CTR_CANDIDATES, CTR_CONTAIN_HITS,
 	CTR_PIVOT_ENTRIES, CTR_ACTIVE_PIVOTS, CTR_MAX_DEGREE, CTR_N_CONTAINED, CTR_NODES_FINAL,
-	CTR_ASYMMETRIC, CTR_SCRATCH_CURSOR, CTR_SCRATCH_FAIL, CTR_EDGES_DROPPED, CTR_LOOKUP_TOTAL, CTR_COUNT
+	CTR_ASYMMETRIC, CTR_SCRATCH_CURSOR, CTR_SCRATCH_FAIL, CTR_EDGES_DROPPED, CTR_PAD, CTR_COUNT
 };
 
 struct ReadStore {
@@ -495,6 +495,7 @@ __global__ void __launch_bounds__(256) k_scan_big(ScanArgs A, u32 n_over)
 				if (threadIdx.x == 0) {
 					u32 m = 1; while (m < s_count) m <<= 1;                  // padded to a power of two for the sort
 					s_start = atomicAdd(A.ctr + CTR_EDGE_CURSOR, (u64)m);
+					atomicAdd(A.ctr + CTR_PAD, (u64)(m - s_count));          // padding is not an edge
 					atomicMax(A.ctr + CTR_MAX_DEGREE, (u64)s_count);
 				}
 				__syncthreads();
