@@ -161,6 +161,13 @@ static int context_create_common(ogb_context **out, int device)
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
 	c->sm_count = prop.multiProcessorCount;
+	// Experiment knob: OGB_L2_FETCH=32|64|128 sets cudaLimitMaxL2FetchGranularity (a hint).
+	{
+		const char *g = getenv("OGB_L2_FETCH");
+		size_t gran = g ? (size_t)atoi(g) : 0;                              // measured: no effect on B200 (profiles/exp_r1_table.txt)
+		if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+		cudaGetLastError();
+	}
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (int i = 0; i < EV_COUNT; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
 	CUDA_TRY(cudaMalloc((void **)&c->d_ctr, CTR_COUNT * sizeof(u64)));
@@ -371,8 +378,10 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 	CUDA_TRY(cudaSetDevice(c->device));
 	c->h = min_overlap - 1;                                                 // HashTable.cpp:54
 	// The reference sizes the table at the first listed prime > 8N+1 slots (HashTable.cpp:56), i.e.
-	// load factor <= 0.5 for its 4N entries. Same load here: 2N buckets of 4 slots.
-	u64 nb = std::max<u64>(2 * (u64)c->n + 1, 1024);
+	// load factor <= 0.5 for its 4N entries. Here: 4N buckets of 4 slots (load 0.25, 128 B per read):
+	// measured on B200 (profiles/exp_r1_table.txt) the scan needs 1.09 sectors per probe instead of
+	// 1.46 at load 0.5, and a warp rarely loops for a lane whose bucket spilled.
+	u64 nb = std::max<u64>(4 * (u64)c->n + 1, 1024);
 	const char *lf = getenv("OGB_TABLE_BUCKETS_PER_READ");
 	if (lf && atof(lf) >= 1.0) nb = std::max<u64>((u64)(atof(lf) * c->n) + 1, 1024);
 	if (nb >= (1ull << 32)) { ogb_set_error("index too large"); return OGB_E_CAPACITY; }

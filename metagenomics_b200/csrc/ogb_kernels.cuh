@@ -100,6 +100,7 @@ __device__ __forceinline__ u64 key_hash(const u64 *__restrict__ w, u32 p, u32 h)
 	acc = mix64(acc, extract32(w, p) & (~0ULL << (64 - 2 * rem)));
 	acc *= 0xc4ceb9fe1a85ec53ULL;
 	acc ^= acc >> 29;
+	if ((acc >> 32) == 0) acc |= 1ull << 32;     // fingerprint 0 is reserved: an empty slot never matches
 	return acc;
 }
 
@@ -330,6 +331,21 @@ __device__ __forceinline__ void warp_sort(u64 *buf, u32 n, u32 lane)
 	}
 }
 
+// Ascending bitonic sort of one u64 per lane with shuffles (pad unused lanes with ~0).
+__device__ __forceinline__ u64 warp_sort32(u64 v, u32 lane)
+{
+	#pragma unroll
+	for (u32 k = 2; k <= 32; k <<= 1) {
+		#pragma unroll
+		for (u32 jj = k >> 1; jj > 0; jj >>= 1) {
+			u64 o = __shfl_xor_sync(0xFFFFFFFFu, v, jj);
+			bool keep_min = ((lane & jj) == 0) == ((lane & k) == 0);
+			v = (keep_min == (v < o)) ? v : o;
+		}
+	}
+	return v;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(OGB_WARPS * 32) k_scan(ScanArgs A)
 {
@@ -390,22 +406,27 @@ __global__ void __launch_bounds__(OGB_WARPS * 32) k_scan(ScanArgs A)
 			const u32 fp = (u32)(hash >> 32);
 			while (__any_sync(0xFFFFFFFFu, active)) {
 				u64 sl[OGB_SLOTS] = {0, 0, 0, 0};
-				bool full = false;
+				u32 mm = 0;                                                  // slots of this lane's bucket whose fingerprint matches
 				if (active) {
 					load_bucket(A.T.slots, b, sl);
-					full = true;
 					c_sectors++;
+					#pragma unroll
+					for (int k = 0; k < OGB_SLOTS; k++) mm |= ((u32)(sl[k] >> 32) == fp) << k;
+					// K1 fills a bucket front to back, so "last slot taken" = full = the key may continue in the next bucket
+					active = sl[OGB_SLOTS - 1] != 0;
+					if (active) b = (b + 1 == A.T.nb) ? 0 : b + 1;
 				}
-				#pragma unroll
-				for (int k = 0; k < OGB_SLOTS; k++) {
-					bool m = active && sl[k] != 0 && (u32)(sl[k] >> 32) == fp;
-					if (active && sl[k] == 0) full = false;
-					u32 bal = __ballot_sync(0xFFFFFFFFu, m);
-					if (m) hq[qn + __popc(bal & ((1u << lane) - 1))] = ((u64)j << 32) | (u32)sl[k];
+				// queue the matches: one ballot per round; a second match in the same bucket is rare
+				u32 bal;
+				while ((bal = __ballot_sync(0xFFFFFFFFu, mm != 0)) != 0) {
+					if (mm) {
+						int k = __ffs(mm) - 1;
+						u64 v = k == 0 ? sl[0] : k == 1 ? sl[1] : k == 2 ? sl[2] : sl[3];
+						hq[qn + __popc(bal & ((1u << lane) - 1))] = ((u64)j << 32) | (u32)v;
+						mm &= mm - 1;
+					}
 					qn += __popc(bal);
 				}
-				active = active && full;                                     // a full bucket spills into the next one
-				if (active) b = (b + 1 == A.T.nb) ? 0 : b + 1;
 				__syncwarp();
 				while (qn >= 32) verify_batch();                             // keeps room for 32 lanes x 4 slots
 			}
@@ -417,12 +438,15 @@ __global__ void __launch_bounds__(OGB_WARPS * 32) k_scan(ScanArgs A)
 			if (en > c_maxdeg) c_maxdeg = en;
 			if (en == 0) { if (lane == 0) A.nodes[qi] = 0; }
 			else if (en <= OGB_EC) {
-				warp_sort(eb, en, lane);
+				u64 mine = ~0ull;
+				if (en <= 32) { if (lane < en) mine = eb[lane]; mine = warp_sort32(mine, lane); }
+				else warp_sort(eb, en, lane);
 				u64 start = 0;
 				if (lane == 0) start = atomicAdd(A.ctr + CTR_EDGE_CURSOR, (u64)en);
 				start = __shfl_sync(0xFFFFFFFFu, start, 0);
 				if (start + en <= A.edge_cap) {
-					for (u32 t = lane; t < en; t += 32) A.edges[start + t] = eb[t];
+					if (en <= 32) { if (lane < en) A.edges[start + lane] = mine; }
+					else for (u32 t = lane; t < en; t += 32) A.edges[start + t] = eb[t];
 				} else if (lane == 0) atomicAdd(A.ctr + CTR_EDGES_DROPPED, (u64)en);
 				if (lane == 0) A.nodes[qi] = (start << OGB_DEG_BITS) | en;
 				__syncwarp();
@@ -575,7 +599,7 @@ __device__ __forceinline__ int set_find(const u32 *keys, u32 capmask, u32 key)
 	}
 }
 
-__global__ void __launch_bounds__(OGB_WARPS * 32) k_mark(MarkArgs A)
+__global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 {
 	__shared__ u32 s_keys[OGB_WARPS][OGB_SETCAP];
 	__shared__ unsigned char s_state[OGB_WARPS][OGB_SETCAP];
@@ -608,24 +632,35 @@ __global__ void __launch_bounds__(OGB_WARPS * 32) k_mark(MarkArgs A)
 			st[s] = 1;
 		}
 		__syncwarp();
-		// pivots in adjacency (offset) order (:580-600)
-		for (u32 i = 0; i < deg; i++) {
-			u64 e = __ldg(A.edges + start + i);
-			u32 v = edge_dst(e), t1 = edge_orient(e);
-			int sv = set_find(keys, capmask, v);
-			if (st[sv] != 1) continue;                                       // eliminated pivots are skipped (:583)
-			u64 ndv = __ldg(A.nodes + (v - 1));
-			u32 degv = (u32)(ndv & OGB_DEG_MASK);
-			u64 startv = ndv >> OGB_DEG_BITS;
-			c_pivots++; c_entries += degv;
-			for (u32 k = lane; k < degv; k += 32) {
-				u64 f = __ldg(A.edges + startv + k);
-				if (compatible(t1, edge_orient(f))) {
-					int sw = set_find(keys, capmask, edge_dst(f));
-					if (sw >= 0 && st[sw] == 1) st[sw] = 2;                  // :588-596
+		// Pivots in adjacency (offset) order (:580-600). The reference walks every edge and skips
+		// the ones whose destination is no longer INPLAY (:583); states only ever go INPLAY ->
+		// ELIMINATED, so "the next pivot" is simply the lowest-index edge after the current one whose
+		// destination is INPLAY now: one ballot + ffs per ACTIVE pivot (~2 per node) instead of a
+		// dependent shared-memory round trip per edge.
+		for (u32 cb = 0; cb < deg; cb += 32) {
+			const u32 k = cb + lane;
+			u64 e = 0; int sk = -1;
+			if (k < deg) { e = __ldg(A.edges + start + k); sk = set_find(keys, capmask, edge_dst(e)); }
+			int cur = -1;
+			for (;;) {
+				u32 m = __ballot_sync(0xFFFFFFFFu, k < deg && (int)lane > cur && st[sk] == 1);
+				if (m == 0) break;
+				cur = __ffs(m) - 1;
+				u64 ei = __shfl_sync(0xFFFFFFFFu, e, cur);
+				u32 v = edge_dst(ei), t1 = edge_orient(ei);
+				u64 ndv = __ldg(A.nodes + (v - 1));
+				u32 degv = (u32)(ndv & OGB_DEG_MASK);
+				u64 startv = ndv >> OGB_DEG_BITS;
+				c_pivots++; c_entries += degv;
+				for (u32 kk = lane; kk < degv; kk += 32) {
+					u64 f = __ldg(A.edges + startv + kk);
+					if (compatible(t1, edge_orient(f))) {
+						int sw = set_find(keys, capmask, edge_dst(f));
+						if (sw >= 0 && st[sw] == 1) st[sw] = 2;              // :588-596
+					}
 				}
+				__syncwarp();
 			}
-			__syncwarp();
 		}
 		// flag own edges to eliminated nodes (:601-607; the twin half is applied in k_twin_keep)
 		for (u32 k = lane; k < deg; k += 32) {
