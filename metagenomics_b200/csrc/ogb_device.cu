@@ -107,9 +107,9 @@ struct ogb_context {
 	bool contain_done = false, any_contained = false;
 	// graph
 	Pool<u64> nodes, edges, pos, sums;
-	Pool<unsigned char> eflag, keep, scratch_state;
+	Pool<unsigned char> eflag, scratch_state;
 	Pool<u32> cnt, overflow, scratch_keys;
-	Pool<ogb_edge> fin, pre;
+	Pool<ogb_edge> fin, pre, surv;
 	Pool<char> flush;
 	u64 n_final = 0, n_pre = 0;
 	bool have_graph = false, have_pre = false;
@@ -215,7 +215,7 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	if (c->comm) g_nccl.CommDestroy(c->comm);
 	c->words.release(); c->meta.release(); c->stage_bytes.release(); c->stage_offs.release(); c->stage_lens.release();
 	c->slots.release(); c->sup.release(); c->contained.release(); c->nodes.release(); c->edges.release(); c->pos.release();
-	c->sums.release(); c->eflag.release(); c->keep.release(); c->scratch_state.release(); c->cnt.release(); c->overflow.release();
+	c->sums.release(); c->eflag.release(); c->surv.release(); c->scratch_state.release(); c->cnt.release(); c->overflow.release();
 	c->scratch_keys.release(); c->fin.release(); c->pre.release(); c->flush.release();
 	if (c->d_ctr) cudaFree(c->d_ctr);
 	if (c->d_tot) cudaFree(c->d_tot);
@@ -274,7 +274,7 @@ static int layout_reads(ogb_context *c, const std::vector<u32> &lens, u64 &total
 
 static int upload_common(ogb_context *c, u64 total_words, const std::vector<u64> &meta_host)
 {
-	OGB_TRY(c->words.ensure(total_words + 8));          // +8: extract32 may touch one word past a strand
+	OGB_TRY(c->words.ensure(total_words + 8));          // +8: window extraction may touch two words past a strand
 	CUDA_TRY(cudaMemsetAsync(c->words.p + total_words, 0, 8 * sizeof(u64), c->stream));
 	if (!meta_host.empty()) {
 		OGB_TRY(c->meta.ensure(meta_host.size()));
@@ -378,12 +378,10 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 	CUDA_TRY(cudaSetDevice(c->device));
 	c->h = min_overlap - 1;                                                 // HashTable.cpp:54
 	// The reference sizes the table at the first listed prime > 8N+1 slots (HashTable.cpp:56), i.e.
-	// load factor <= 0.5 for its 4N entries. Here: 4N buckets of 4 slots (load 0.25, 128 B per read):
-	// measured on B200 (profiles/exp_r1_table.txt) the scan needs 1.09 sectors per probe instead of
-	// 1.46 at load 0.5, and a warp rarely loops for a lane whose bucket spilled.
-	u64 nb = std::max<u64>(4 * (u64)c->n + 1, 1024);
+	// load factor <= 0.5 for its 4N entries. Same budget here: N buckets of 8 slots (64 B per read).
+	u64 nb = std::max<u64>((u64)c->n + 1, 512);
 	const char *lf = getenv("OGB_TABLE_BUCKETS_PER_READ");
-	if (lf && atof(lf) >= 1.0) nb = std::max<u64>((u64)(atof(lf) * c->n) + 1, 1024);
+	if (lf && atof(lf) >= 0.5) nb = std::max<u64>((u64)(atof(lf) * c->n) + 1, 512);
 	if (nb >= (1ull << 32)) { ogb_set_error("index too large"); return OGB_E_CAPACITY; }
 	c->nb = (u32)nb;
 	OGB_TRY(c->slots.ensure(nb * OGB_SLOTS));
@@ -417,7 +415,7 @@ extern "C" int ogb_hash_lookup(ogb_context *c, const char *keys, uint64_t n_keys
 	const u32 h = c->h, kw = (h + 31) / 32;
 	out_offsets[0] = 0;
 	if (n_keys == 0) return OGB_OK;
-	std::vector<u64> packed(n_keys * (kw + 1), 0);
+	std::vector<u64> packed(n_keys * (kw + 2) + 4, 0);
 	for (u64 k = 0; k < n_keys; k++)
 		for (u32 i = 0; i < h; i++) {
 			u64 code;
@@ -428,7 +426,7 @@ extern "C" int ogb_hash_lookup(ogb_context *c, const char *keys, uint64_t n_keys
 			case 'T': case 't': code = 3; break;
 			default: ogb_set_error("ogb_hash_lookup: key %llu is not ACGT", (unsigned long long)k); return OGB_E_ARG;
 			}
-			packed[k * (kw + 1) + (i >> 5)] |= code << (62 - 2 * (i & 31));
+			packed[k * (kw + 2) + (i >> 5)] |= code << (62 - 2 * (i & 31));
 		}
 	Pool<u64> d_keys, d_pos, d_out;
 	Pool<u32> d_cnt;
@@ -678,7 +676,7 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 
 	// ---- K5
 	OGB_TRY(c->eflag.ensure(std::max<u64>(c->edges.cap, 1)));
-	OGB_TRY(c->keep.ensure(std::max<u64>(c->edges.cap, 1)));
+	OGB_TRY(c->surv.ensure(std::max<u64>(c->edges.cap, 1)));
 	if (c->scratch_keys.cap == 0) { OGB_TRY(c->scratch_keys.ensure(1 << 20)); OGB_TRY(c->scratch_state.ensure(1 << 20)); }
 	for (int attempt = 0;; attempt++) {
 		if (attempt == 4) { ogb_set_error("ogb_build_graph: neighbour-set scratch kept overflowing"); return OGB_E_CAPACITY; }
@@ -699,14 +697,14 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	if (G > 1) OGB_TRY(allgatherv(c, c->eflag.p, 1, seg_off, seg_cnt));   // C2
 
 	// ---- K6
-	k_twin_keep<<<grid_for(c, (const void *)k_twin_keep, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->edges.p, c->eflag.p, c->keep.p,
+	k_twin_keep<<<grid_for(c, (const void *)k_twin_keep, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->edges.p, c->eflag.p, c->surv.p,
 	                                                                                                     c->cnt.p, lo, hi, c->d_ctr);
 	CUDA_TRY(cudaGetLastError());
 	c->launches++;
 	if (G > 1) NCCL_TRY(g_nccl.AllGather(c->cnt.p + per * c->rank, c->cnt.p, per, NCCL_UINT32, c->comm, c->stream));
 	OGB_TRY(exclusive_scan(c, c->cnt.p, n, c->pos.p, c->d_tot + 1));
 	OGB_TRY(c->fin.ensure(std::max<u64>(c->edges.cap, 1)));                // E_final <= E_pre: no sync needed to size it
-	k_compact<<<grid_for(c, (const void *)k_compact, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->edges.p, c->keep.p, c->pos.p, c->fin.p, 0, lo, hi);
+	if (hi > lo) k_compact<<<(hi - lo + 255) / 256, 256, 0, c->stream>>>(c->nodes.p, c->surv.p, c->cnt.p, c->pos.p, c->fin.p, lo, hi);
 	CUDA_TRY(cudaGetLastError());
 	c->launches++;
 	OGB_TRY(ctr_fetch(c));

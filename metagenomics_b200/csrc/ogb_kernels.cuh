@@ -17,12 +17,13 @@
 //                 offset off, reverse complement at off + pw, pw = 2*ceil(L/64) words (16-byte
 //                 aligned strands; 100 bp -> 32 B = one sector). Uniform-length data sets use
 //                 off = idx*2*pw (no metadata load); mixed lengths use meta[idx] = off<<16 | L.
-//   index         nb buckets x 4 slots x u64 (one 32-byte sector per bucket). slot = fp32<<32 |
-//                 id<<2 | o, 0 = empty. One slot per (key,value); a key's entries sit in its home
-//                 bucket and, when that is full, in the following buckets (linear probing by
-//                 bucket). Only a 32-bit fingerprint of the key is stored: every consumer verifies
-//                 the complete overlap (window included) against the packed reads, which makes
-//                 the result exact and independent of hash values.
+//   index         nb buckets x 8 slots x u64 (one 64-byte DRAM burst per bucket: measured on B200, a
+//                 random 32-byte sector read costs a 64-byte HBM fetch anyway, profiles/exp_r1_l2fetch.txt).
+//                 slot = fp32<<32 | id<<2 | o, 0 = empty. One slot per (key,value); a key's entries
+//                 sit in its home bucket and, when that is full, in the following buckets (linear
+//                 probing by bucket). Only a 32-bit fingerprint of the key is stored: every consumer
+//                 verifies the complete overlap (window included) against the packed reads, which
+//                 makes the result exact and independent of hash values.
 //   edges         u64 = offset<<48 | dst<<16 | orient<<8, so integer order = (offset,dst,orient).
 //   nodes         u64 = start<<24 | degree  (adjacency of a node is contiguous and sorted).
 #pragma once
@@ -32,9 +33,13 @@
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-#define OGB_SLOTS 4             // slots per bucket (32-byte sector)
+#define OGB_SLOTS 8             // slots per bucket (64 bytes = one HBM burst)
 #define OGB_WARPS 8             // warps per block in the scan / mark kernels
-#define OGB_HQ 160              // per-warp candidate queue (<= 31 left over + 32 lanes x 4 slots)
+#ifndef OGB_SCAN_BLOCKS
+#define OGB_SCAN_BLOCKS 4       // resident blocks per SM the scan kernel is compiled for (register cap)
+#endif
+#define OGB_HQ 288              // per-warp candidate queue (<= 31 left over + 32 lanes x 8 slots)
+#define OGB_STAGE_WORDS 32      // query reads up to 1024 bp are staged in shared memory (longer: slow path)
 #define OGB_EC 256              // per-warp edge buffer (reads with more edges take the slow path)
 #define OGB_SETCAP 512          // per-warp neighbour set slots in shared memory (degree <= 256)
 #define OGB_DEG_BITS 24
@@ -72,13 +77,26 @@ __device__ __forceinline__ void read_geom(const ReadStore &R, u32 idx, u64 &off,
 	else { u64 m = __ldg(R.meta + idx); L = (u32)(m & 0xFFFF); off = m >> 16; }
 }
 
-// 32 bases starting at base p of a packed strand (high bits first). The word after the strand is
-// always allocated, so the second load is unconditional; callers mask what they do not need.
-__device__ __forceinline__ u64 extract32(const u64 *__restrict__ w, u32 p)
+// Load flavours. Random gathers (index buckets, partner reads) bypass L1 allocation so that they do
+// not evict anything useful; the query read itself is staged in shared memory.
+__device__ __forceinline__ u64 ld_na(const u64 *p)
+{
+	u64 v;
+	asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+	return v;
+}
+struct LdShared { static __device__ __forceinline__ u64 ld(const u64 *p) { return *p; } };
+struct LdGlobal { static __device__ __forceinline__ u64 ld(const u64 *p) { return __ldg(p); } };
+struct LdStream { static __device__ __forceinline__ u64 ld(const u64 *p) { return ld_na(p); } };
+
+__device__ __forceinline__ u64 funnel(u64 a, u64 b, u32 sh) { return sh ? ((a << sh) | (b >> (64 - sh))) : a; }
+
+// 32 bases starting at base p of a packed strand (high bits first). The words after a strand are
+// always allocated, so loads past its end are safe; callers mask what they do not need.
+template <class LD> __device__ __forceinline__ u64 extract32(const u64 *__restrict__ w, u32 p)
 {
 	u32 wi = p >> 5, sh = (p & 31) << 1;
-	u64 a = __ldg(w + wi), b = __ldg(w + wi + 1);
-	return sh ? ((a << sh) | (b >> (64 - sh))) : a;
+	return funnel(LD::ld(w + wi), LD::ld(w + wi + 1), sh);
 }
 
 __device__ __forceinline__ u64 mix64(u64 acc, u64 x)
@@ -89,32 +107,57 @@ __device__ __forceinline__ u64 mix64(u64 acc, u64 x)
 	return acc;
 }
 
-// 64-bit hash of the h bases starting at base p. Low 32 bits pick the bucket, high 32 are the
+// Multilinear hash of a key of up to 64 bases held in (k0,k1): sum of 32-bit digits times odd 64-bit
+// constants, mod 2^64. The high half (strongly universal) picks the bucket, the low half is the
 // stored fingerprint. (The reference's polynomial-mod hash, HashTable.cpp:135-155, is not
 // reproduced: its value is unobservable in the result.)
-__device__ __forceinline__ u64 key_hash(const u64 *__restrict__ w, u32 p, u32 h)
+__device__ __forceinline__ u64 hash2(u64 k0, u64 k1)
 {
 	u64 acc = 0x9E3779B97F4A7C15ULL;
-	u32 rem = h;
-	for (; rem > 32; rem -= 32, p += 32) acc = mix64(acc, extract32(w, p));
-	acc = mix64(acc, extract32(w, p) & (~0ULL << (64 - 2 * rem)));
-	acc *= 0xc4ceb9fe1a85ec53ULL;
-	acc ^= acc >> 29;
-	if ((acc >> 32) == 0) acc |= 1ull << 32;     // fingerprint 0 is reserved: an empty slot never matches
+	acc += (u64)(u32)(k0 >> 32) * 0xD6E8FEB86659FD93ULL;
+	acc += (u64)(u32)k0 * 0xA0761D6478BD642FULL;
+	acc += (u64)(u32)(k1 >> 32) * 0xE7037ED1A0B428DBULL;
+	acc += (u64)(u32)k1 * 0x8EBC6AF09C88C6E3ULL;
 	return acc;
 }
 
-__device__ __forceinline__ u32 bucket_of(u64 hash, u32 nb) { return (u32)(((hash & 0xFFFFFFFFull) * (u64)nb) >> 32); }
+// Hash of the h bases starting at base p of a packed strand.
+template <class LD> __device__ __forceinline__ u64 key_hash(const u64 *__restrict__ w, u32 p, u32 h)
+{
+	const u32 wi = p >> 5, sh = (p & 31) << 1;
+	const u64 a = LD::ld(w + wi), b = LD::ld(w + wi + 1);
+	u64 k0 = funnel(a, b, sh);
+	if (h <= 32) return hash2(k0 & (~0ULL << (64 - 2 * h)), 0);
+	const u64 c = LD::ld(w + wi + 2);
+	u64 k1 = funnel(b, c, sh);
+	if (h <= 64) return hash2(k0, k1 & (~0ULL << (128 - 2 * h)));
+	u64 acc = hash2(k0, k1);
+	u32 rem = h - 64;
+	p += 64;
+	for (; rem > 32; rem -= 32, p += 32) acc = mix64(acc, extract32<LD>(w, p));
+	return mix64(acc, extract32<LD>(w, p) & (~0ULL << (64 - 2 * rem)));
+}
 
-// s[a..a+len) == t[b..b+len) on packed strands. No early exit: (almost) every candidate verifies,
-// and independent iterations keep all sector requests of the partner read in flight.
+__device__ __forceinline__ u32 hash_fp(u64 hash) { u32 f = (u32)hash; return f ? f : 1u; }   // 0 is reserved for "empty"
+__device__ __forceinline__ u32 bucket_of(u64 hash, u32 nb) { return __umulhi((u32)(hash >> 32), nb); }
+
+// s[a..a+len) == t[b..b+len) on packed strands, streaming one new word per side and 32 bases. No
+// early exit: (almost) every candidate verifies, and independent iterations keep the sector
+// requests of the partner read in flight together.
+template <class LDS, class LDT>
 __device__ __forceinline__ bool region_equal(const u64 *__restrict__ s, u32 a, const u64 *__restrict__ t, u32 b, u32 len)
 {
-	u64 diff = 0;
+	const u32 sa = (a & 31) << 1, sb = (b & 31) << 1;
+	const u64 *ws = s + (a >> 5), *wt = t + (b >> 5);
+	u64 s0 = LDS::ld(ws), t0 = LDT::ld(wt), diff = 0;
 	u32 k = 0;
-	for (; k + 32 <= len; k += 32) diff |= extract32(s, a + k) ^ extract32(t, b + k);
+	for (; k + 32 <= len; k += 32) {
+		u64 s1 = LDS::ld(++ws), t1 = LDT::ld(++wt);
+		diff |= funnel(s0, s1, sa) ^ funnel(t0, t1, sb);
+		s0 = s1; t0 = t1;
+	}
 	u32 rem = len - k;
-	if (rem) diff |= (extract32(s, a + k) ^ extract32(t, b + k)) & (~0ULL << (64 - 2 * rem));
+	if (rem) diff |= (funnel(s0, LDS::ld(ws + 1), sa) ^ funnel(t0, LDT::ld(wt + 1), sb)) & (~0ULL << (64 - 2 * rem));
 	return diff == 0;
 }
 
@@ -213,28 +256,34 @@ __global__ void k_hash_insert(ReadStore R, Table T)
 	read_geom(R, idx, off, L);
 	const u64 *w = R.words + off + (o >> 1) * padded_words(L);
 	u32 p = (o & 1) ? L - T.h : 0;
-	u64 hash = key_hash(w, p, T.h);
-	u64 val = (hash & 0xFFFFFFFF00000000ull) | ((u64)(idx + 1) << 2) | o;
+	u64 hash = key_hash<LdGlobal>(w, p, T.h);
+	u64 val = ((u64)hash_fp(hash) << 32) | ((u64)(idx + 1) << 2) | o;
 	u32 b = bucket_of(hash, T.nb);
 	for (;;) {
 		u64 *slot = T.slots + (u64)b * OGB_SLOTS;
-		bool done = false;
+		// one L2-coherent look at the whole bucket, then a CAS on its first empty slot; buckets fill
+		// front to back, so a lost race just moves on to the next slot
+		u64 cur[OGB_SLOTS];
 		#pragma unroll
-		for (int s = 0; s < OGB_SLOTS && !done; s++) {
-			u64 cur = slot[s];
-			if (cur == 0) cur = atomicCAS(slot + s, 0ull, val);
-			done = (cur == 0);
-		}
+		for (int q = 0; q < OGB_SLOTS; q += 2)
+			asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(cur[q]), "=l"(cur[q + 1]) : "l"(slot + q) : "memory");
+		int s = 0;
+		#pragma unroll
+		for (int q = OGB_SLOTS - 1; q >= 0; q--) s = cur[q] == 0 ? q : s;
+		bool done = false;
+		if (cur[OGB_SLOTS - 1] == 0)
+			for (; s < OGB_SLOTS && !done; s++) done = atomicCAS(slot + s, 0ull, val) == 0;
 		if (done) break;
 		b = (b + 1 == T.nb) ? 0 : b + 1;
 	}
 }
 
+// One bucket = 64 bytes = two 256-bit non-allocating loads.
 __device__ __forceinline__ void load_bucket(const u64 *__restrict__ slots, u32 b, u64 (&s)[OGB_SLOTS])
 {
-	const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(slots + (u64)b * OGB_SLOTS);
-	ulonglong2 x = __ldg(p), y = __ldg(p + 1);
-	s[0] = x.x; s[1] = x.y; s[2] = y.x; s[3] = y.y;
+	const u64 *p = slots + (u64)b * OGB_SLOTS;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(s[0]), "=l"(s[1]), "=l"(s[2]), "=l"(s[3]) : "l"(p));
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(s[4]), "=l"(s[5]), "=l"(s[6]), "=l"(s[7]) : "l"(p + 4));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -268,7 +317,7 @@ struct ScanArgs {
 
 // Verifies candidate (j, val) of query read qi (strand words s, length L1). Returns the number of
 // edges produced (0, 1, or 2 for a self-overlap) in e0/e1; in MODE_CONTAIN performs the atomicMax.
-template <int MODE>
+template <int MODE, class LDS>
 __device__ __forceinline__ int verify_candidate(const ScanArgs &A, const u64 *__restrict__ s, u32 qi, u32 L1, u32 j, u32 val, u64 &e0, u64 &e1)
 {
 	const u32 h = A.T.h;
@@ -282,7 +331,7 @@ __device__ __forceinline__ int verify_candidate(const ScanArgs &A, const u64 *__
 		u32 a;
 		if ((o & 1) == 0) { if (L1 - j < L2) return 0; a = j; }              // :316-321
 		else { if (j < L2 - h) return 0; a = j - (L2 - h); }                // :331-336
-		if (!region_equal(s, a, t, 0, L2)) return 0;
+		if (!region_equal<LDS, LdStream>(s, a, t, 0, L2)) return 0;
 		atomicMax(A.sup + ri, ((u64)L1 << 32) | (u64)(0xFFFFFFFFu - qi));   // :259-268
 		return 1;
 	} else {
@@ -299,7 +348,7 @@ __device__ __forceinline__ int verify_candidate(const ScanArgs &A, const u64 *__
 			orient = o == 1 ? 0 : 1;      // :553,:555
 			offset = L1 - h - j;          // L1 - overlap, overlap = h + j
 		}
-		if (!region_equal(s, a, t, b, len)) return 0;
+		if (!region_equal<LDS, LdStream>(s, a, t, b, len)) return 0;
 		e0 = make_edge(offset & 0xFFFF, ri + 1, orient);
 		if (ri != qi) return 1;
 		// Self-overlap: the reference inserts the edge and its twin object into the same list
@@ -347,10 +396,11 @@ __device__ __forceinline__ u64 warp_sort32(u64 v, u32 lane)
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(OGB_WARPS * 32) k_scan(ScanArgs A)
+__global__ void __launch_bounds__(OGB_WARPS * 32, OGB_SCAN_BLOCKS) k_scan(ScanArgs A)
 {
 	__shared__ u64 s_hq[OGB_WARPS][OGB_HQ];
 	__shared__ u64 s_edges[MODE == MODE_OVERLAP ? OGB_WARPS : 1][MODE == MODE_OVERLAP ? OGB_EC : 1];
+	__shared__ u64 s_read[OGB_WARPS][OGB_STAGE_WORDS + 4];
 	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const u32 gw = blockIdx.x * OGB_WARPS + wib, nwarps = gridDim.x * OGB_WARPS;
 	u64 *hq = s_hq[wib];
@@ -366,7 +416,22 @@ __global__ void __launch_bounds__(OGB_WARPS * 32) k_scan(ScanArgs A)
 		}
 		u64 off; u32 L1;
 		read_geom(A.R, qi, off, L1);
-		const u64 *s = A.R.words + off;
+		if (L1 > OGB_STAGE_WORDS * 32) {                                     // very long read: slow path
+			if (lane == 0) {
+				u64 pos = atomicAdd(A.ctr + CTR_OVERFLOW, 1ull);
+				if (pos < A.overflow_cap) A.overflow_list[pos] = qi;
+				if (MODE == MODE_OVERLAP) A.nodes[qi] = OGB_NODE_OVERFLOW;
+			}
+			continue;
+		}
+		// stage the query strand (+2 words of slack for the window extraction) in shared memory
+		u64 *s = s_read[wib];
+		{
+			const u32 nw = (L1 + 31) >> 5;
+			__syncwarp();
+			for (u32 i = lane; i < nw + 3; i += 32) s[i] = i < nw ? __ldg(A.R.words + off + i) : 0;
+			__syncwarp();
+		}
 		const u32 nwin = L1 - h - 1;                                         // j = 1 .. L1-h-1 (:534)
 		u32 qn = 0;        // queued candidates (warp-uniform)
 		u32 en = 0;        // buffered edges (warp-uniform); keeps counting past OGB_EC
@@ -379,7 +444,7 @@ __global__ void __launch_bounds__(OGB_WARPS * 32) k_scan(ScanArgs A)
 			u64 e0 = 0, e1 = 0; int ne = 0;
 			if (lane < take) {
 				u64 c = hq[base + lane];
-				ne = verify_candidate<MODE>(A, s, qi, L1, (u32)(c >> 32), (u32)c, e0, e1);
+				ne = verify_candidate<MODE, LdShared>(A, s, qi, L1, (u32)(c >> 32), (u32)c, e0, e1);
 				c_cand++;
 			}
 			qn = base;
@@ -402,10 +467,10 @@ __global__ void __launch_bounds__(OGB_WARPS * 32) k_scan(ScanArgs A)
 			u32 j = jb + lane;
 			bool active = j <= nwin;
 			u64 hash = 0; u32 b = 0;
-			if (active) { hash = key_hash(s, j, h); b = bucket_of(hash, A.T.nb); }
-			const u32 fp = (u32)(hash >> 32);
+			if (active) { hash = key_hash<LdShared>(s, j, h); b = bucket_of(hash, A.T.nb); }
+			const u32 fp = hash_fp(hash);
 			while (__any_sync(0xFFFFFFFFu, active)) {
-				u64 sl[OGB_SLOTS] = {0, 0, 0, 0};
+				u64 sl[OGB_SLOTS];
 				u32 mm = 0;                                                  // slots of this lane's bucket whose fingerprint matches
 				if (active) {
 					load_bucket(A.T.slots, b, sl);
@@ -421,14 +486,16 @@ __global__ void __launch_bounds__(OGB_WARPS * 32) k_scan(ScanArgs A)
 				while ((bal = __ballot_sync(0xFFFFFFFFu, mm != 0)) != 0) {
 					if (mm) {
 						int k = __ffs(mm) - 1;
-						u64 v = k == 0 ? sl[0] : k == 1 ? sl[1] : k == 2 ? sl[2] : sl[3];
+						u64 v = sl[0];
+						#pragma unroll
+						for (int q = 1; q < OGB_SLOTS; q++) v = (k == q) ? sl[q] : v;
 						hq[qn + __popc(bal & ((1u << lane) - 1))] = ((u64)j << 32) | (u32)v;
 						mm &= mm - 1;
 					}
 					qn += __popc(bal);
 				}
 				__syncwarp();
-				while (qn >= 32) verify_batch();                             // keeps room for 32 lanes x 4 slots
+				while (qn >= 32) verify_batch();                             // keeps room for 32 lanes x 8 slots
 			}
 		}
 		while (qn > 0) verify_batch();
@@ -491,8 +558,8 @@ __global__ void __launch_bounds__(256) k_scan_big(ScanArgs A, u32 n_over)
 			if (threadIdx.x == 0) s_count = 0;
 			__syncthreads();
 			for (u32 j = 1 + threadIdx.x; j <= nwin; j += blockDim.x) {
-				u64 hash = key_hash(s, j, h);
-				u32 fp = (u32)(hash >> 32), b = bucket_of(hash, A.T.nb);
+				u64 hash = key_hash<LdGlobal>(s, j, h);
+				u32 fp = hash_fp(hash), b = bucket_of(hash, A.T.nb);
 				for (;;) {
 					u64 sl[OGB_SLOTS];
 					load_bucket(A.T.slots, b, sl);
@@ -501,7 +568,7 @@ __global__ void __launch_bounds__(256) k_scan_big(ScanArgs A, u32 n_over)
 						if (sl[k] == 0) { full = false; continue; }
 						if ((u32)(sl[k] >> 32) != fp) continue;
 						u64 e0 = 0, e1 = 0;
-						int ne = verify_candidate<MODE_OVERLAP>(A, s, qi, L1, j, (u32)sl[k], e0, e1);
+						int ne = verify_candidate<MODE_OVERLAP, LdGlobal>(A, s, qi, L1, j, (u32)sl[k], e0, e1);
 						if (ne) {
 							u32 pos = atomicAdd(&s_count, (u32)ne);
 							if (pass == 1 && s_start + pos + ne <= A.edge_cap) {
@@ -626,10 +693,12 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 		const u32 capmask = cap - 1;
 		for (u32 i = lane; i < cap; i += 32) keys[i] = 0;
 		__syncwarp();
-		// mark all neighbours INPLAY (:577-578)
-		for (u32 k = lane; k < deg; k += 32) {
-			u32 s = set_insert(keys, capmask, edge_dst(__ldg(A.edges + start + k)));
-			st[s] = 1;
+		// mark all neighbours INPLAY (:577-578); a lane keeps the set slot of its own edge
+		u64 e = 0; int sk = -1;
+		if (deg <= 32) {
+			if (lane < deg) { e = __ldg(A.edges + start + lane); sk = (int)set_insert(keys, capmask, edge_dst(e)); st[sk] = 1; }
+		} else {
+			for (u32 k = lane; k < deg; k += 32) st[set_insert(keys, capmask, edge_dst(__ldg(A.edges + start + k)))] = 1;
 		}
 		__syncwarp();
 		// Pivots in adjacency (offset) order (:580-600). The reference walks every edge and skips
@@ -639,8 +708,10 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 		// dependent shared-memory round trip per edge.
 		for (u32 cb = 0; cb < deg; cb += 32) {
 			const u32 k = cb + lane;
-			u64 e = 0; int sk = -1;
-			if (k < deg) { e = __ldg(A.edges + start + k); sk = set_find(keys, capmask, edge_dst(e)); }
+			if (deg > 32) {
+				e = 0; sk = -1;
+				if (k < deg) { e = __ldg(A.edges + start + k); sk = set_find(keys, capmask, edge_dst(e)); }
+			}
 			int cur = -1;
 			for (;;) {
 				u32 m = __ballot_sync(0xFFFFFFFFu, k < deg && (int)lane > cur && st[sk] == 1);
@@ -663,10 +734,8 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 			}
 		}
 		// flag own edges to eliminated nodes (:601-607; the twin half is applied in k_twin_keep)
-		for (u32 k = lane; k < deg; k += 32) {
-			int s = set_find(keys, capmask, edge_dst(__ldg(A.edges + start + k)));
-			A.eflag[start + k] = st[s] == 2;
-		}
+		if (deg <= 32) { if (lane < deg) A.eflag[start + lane] = st[sk] == 2; }
+		else for (u32 k = lane; k < deg; k += 32) A.eflag[start + k] = st[set_find(keys, capmask, edge_dst(__ldg(A.edges + start + k)))] == 2;
 		__syncwarp();
 	}
 	if (lane == 0) { atomicAdd(A.ctr + CTR_PIVOT_ENTRIES, c_entries); atomicAdd(A.ctr + CTR_ACTIVE_PIVOTS, c_pivots); }
@@ -675,15 +744,18 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 // ------------------------------------------------------------------------------------------------
 // K6: an edge (u,w) survives iff it was not flagged by u's marking and its twin was not flagged by
 // w's marking (:605-606, :623-661). Marks are per destination NODE, so w's verdict on u is read off
-// any (w,u) entry of w's adjacency -- no twin pointers are needed.
+// any (w,u) entry of w's adjacency -- no twin pointers are needed. One warp per node: the few edges
+// that u itself kept (~2) are checked one after another, each by a warp-wide scan of w's adjacency;
+// survivors are written compacted to surv[start .. start+cnt) as final records, so that the copy
+// kernel after the scan touches survivors only.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(OGB_WARPS * 32) k_twin_keep(const u64 *__restrict__ nodes, const u64 *__restrict__ edges,
-                                                              const unsigned char *__restrict__ eflag, unsigned char *__restrict__ keep,
+                                                              const unsigned char *__restrict__ eflag, ogb_edge *__restrict__ surv,
                                                               u32 *__restrict__ cnt, u32 lo, u32 hi, u64 *ctr)
 {
 	const u32 lane = threadIdx.x & 31;
 	const u32 gw = blockIdx.x * OGB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * OGB_WARPS;
-	u32 c_nodes = 0;
+	u32 c_nodes = 0, c_asym = 0;
 	for (u32 u = lo + gw; u < hi; u += nwarps) {
 		u64 nd = __ldg(nodes + u);
 		u32 deg = (u32)(nd & OGB_DEG_MASK);
@@ -691,24 +763,43 @@ __global__ void __launch_bounds__(OGB_WARPS * 32) k_twin_keep(const u64 *__restr
 		u32 total = 0;
 		for (u32 kb = 0; kb < deg; kb += 32) {
 			u32 k = kb + lane;
-			bool kp = false;
-			if (k < deg && !eflag[start + k]) {
-				u32 w = edge_dst(__ldg(edges + start + k));
-				u64 ndw = __ldg(nodes + (w - 1));
-				u32 degw = (u32)(ndw & OGB_DEG_MASK);
-				u64 startw = ndw >> OGB_DEG_BITS;
-				kp = true;
-				bool found = false;
-				for (u32 x = 0; x < degw; x++)
-					if (edge_dst(__ldg(edges + startw + x)) == u + 1) { kp = !eflag[startw + x]; found = true; break; }
-				if (!found) atomicAdd(ctr + CTR_ASYMMETRIC, 1ull);
+			u64 e = 0, ndw = 0;
+			bool mine = k < deg && !eflag[start + k];
+			if (mine) { e = __ldg(edges + start + k); ndw = __ldg(nodes + (edge_dst(e) - 1)); }   // all twin nodes fetched together
+			u32 todo = __ballot_sync(0xFFFFFFFFu, mine);
+			while (todo) {
+				int src = __ffs(todo) - 1;
+				todo &= todo - 1;
+				u64 ee = __shfl_sync(0xFFFFFFFFu, e, src), nw = __shfl_sync(0xFFFFFFFFu, ndw, src);
+				u32 degw = (u32)(nw & OGB_DEG_MASK);
+				u64 startw = nw >> OGB_DEG_BITS;
+				int verdict = -1;                                            // -1 not found, 0 keep, 1 twin flagged
+				for (u32 xb = 0; xb < degw && verdict < 0; xb += 32) {
+					u32 x = xb + lane;
+					bool hit = x < degw && edge_dst(__ldg(edges + startw + x)) == u + 1;
+					u32 hm = __ballot_sync(0xFFFFFFFFu, hit);
+					if (hm) {
+						int hl = __ffs(hm) - 1;
+						int f = 0;
+						if ((int)lane == hl) f = eflag[startw + x];
+						verdict = __shfl_sync(0xFFFFFFFFu, f, hl);
+					}
+				}
+				if (verdict < 0) { c_asym++; verdict = 0; }
+				if (verdict == 0) {
+					if (lane == 0) {
+						ogb_edge r;
+						r.src = u + 1; r.dst = edge_dst(ee); r.offset = (uint16_t)edge_offset(ee); r.orient = (uint8_t)edge_orient(ee); r.reserved = 0;
+						surv[start + total] = r;
+					}
+					total++;
+				}
 			}
-			if (k < deg) keep[start + k] = kp;
-			total += __popc(__ballot_sync(0xFFFFFFFFu, kp));
 		}
 		if (lane == 0) { cnt[u] = total; c_nodes += total > 0; }
 	}
 	if (lane == 0 && c_nodes) atomicAdd(ctr + CTR_NODES_FINAL, (u64)c_nodes);
+	if (lane == 0 && c_asym) atomicAdd(ctr + CTR_ASYMMETRIC, (u64)c_asym);
 }
 
 // Exclusive scan of u32 counts into u64 offsets: (1) per-block sums, (2) one block scans the sums,
@@ -766,32 +857,17 @@ __global__ void __launch_bounds__(256) k_scan_apply(const u32 *__restrict__ cnt,
 	for (int i = 0; i < 8; i++) { u64 p = base + threadIdx.x * 8 + i; if (p < n) out[p] = run; run += v[i]; }
 }
 
-// Final edge records, sorted by (src, offset, dst, orient): node order x adjacency order.
-__global__ void __launch_bounds__(OGB_WARPS * 32) k_compact(const u64 *__restrict__ nodes, const u64 *__restrict__ edges,
-                                                            const unsigned char *__restrict__ keep, const u64 *__restrict__ pos,
-                                                            ogb_edge *__restrict__ out, u64 out_base, u32 lo, u32 hi)
+// Final edge records, sorted by (src, offset, dst, orient) = node order x adjacency order: one
+// thread per node copies its cnt[u] survivors from surv[start..] to out[pos[u]..].
+__global__ void __launch_bounds__(256) k_compact(const u64 *__restrict__ nodes, const ogb_edge *__restrict__ surv, const u32 *__restrict__ cnt,
+                                                 const u64 *__restrict__ pos, ogb_edge *__restrict__ out, u32 lo, u32 hi)
 {
-	const u32 lane = threadIdx.x & 31;
-	const u32 gw = blockIdx.x * OGB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * OGB_WARPS;
-	for (u32 u = lo + gw; u < hi; u += nwarps) {
-		u64 nd = __ldg(nodes + u);
-		u32 deg = (u32)(nd & OGB_DEG_MASK);
-		if (deg == 0) continue;
-		u64 start = nd >> OGB_DEG_BITS;
-		u64 p = pos[u] - out_base;
-		for (u32 kb = 0; kb < deg; kb += 32) {
-			u32 k = kb + lane;
-			bool kp = k < deg && keep[start + k];
-			u32 bal = __ballot_sync(0xFFFFFFFFu, kp);
-			if (kp) {
-				u64 e = __ldg(edges + start + k);
-				ogb_edge r;
-				r.src = u + 1; r.dst = edge_dst(e); r.offset = (uint16_t)edge_offset(e); r.orient = (uint8_t)edge_orient(e); r.reserved = 0;
-				out[p + __popc(bal & ((1u << lane) - 1))] = r;
-			}
-			p += __popc(bal);
-		}
-	}
+	u32 u = lo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= hi) return;
+	u32 c = cnt[u];
+	if (c == 0) return;
+	u64 start = __ldg(nodes + u) >> OGB_DEG_BITS, p = pos[u];
+	for (u32 i = 0; i < c; i++) out[p + i] = surv[start + i];
 }
 
 // Pre-reduction edges as records (tests / keep_pre): one warp per node, position = start.
@@ -828,9 +904,9 @@ __global__ void k_lookup(ReadStore R, Table T, const u64 *__restrict__ keys, u32
 {
 	u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= n_keys) return;
-	const u64 *key = keys + k * (kw + 1);
-	u64 hash = key_hash(key, 0, T.h);
-	u32 fp = (u32)(hash >> 32), b = bucket_of(hash, T.nb), c = 0;
+	const u64 *key = keys + k * (kw + 2);
+	u64 hash = key_hash<LdGlobal>(key, 0, T.h);
+	u32 fp = hash_fp(hash), b = bucket_of(hash, T.nb), c = 0;
 	for (;;) {
 		u64 sl[OGB_SLOTS];
 		load_bucket(T.slots, b, sl);
@@ -842,7 +918,7 @@ __global__ void k_lookup(ReadStore R, Table T, const u64 *__restrict__ keys, u32
 			u64 off; u32 L;
 			read_geom(R, ri, off, L);
 			const u64 *t = R.words + off + (o >> 1) * padded_words(L);
-			if (!region_equal(key, 0, t, (o & 1) ? L - T.h : 0, T.h)) continue;
+			if (!region_equal<LdGlobal, LdGlobal>(key, 0, t, (o & 1) ? L - T.h : 0, T.h)) continue;
 			if (pass == 1) out[pos[k] + c] = (u64)(ri + 1) | ((u64)o << 62);
 			c++;
 		}

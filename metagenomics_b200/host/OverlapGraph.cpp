@@ -7,13 +7,13 @@ static bool byDestination(Edge *a, Edge *b) { return a->getDestinationRead()->ge
 static bool byOffset(Edge *a, Edge *b) { return a->getOverlapOffset() < b->getOverlapOffset(); }
 
 OverlapGraph::OverlapGraph(void)
-	: dataSet(NULL), hashTable(NULL), graph(new vector<vector<Edge *> *>), numberOfNodes(0), numberOfEdges(0), flowComputed(false)
+	: dataSet(NULL), hashTable(NULL), graph(new vector<vector<Edge *> *>), numberOfNodes(0), numberOfEdges(0), hashStringLength(0), flowComputed(false)
 {
 	memset(&lastStats, 0, sizeof lastStats);
 }
 
 OverlapGraph::OverlapGraph(HashTable *ht)
-	: dataSet(NULL), hashTable(NULL), graph(new vector<vector<Edge *> *>), numberOfNodes(0), numberOfEdges(0), flowComputed(false)
+	: dataSet(NULL), hashTable(NULL), graph(new vector<vector<Edge *> *>), numberOfNodes(0), numberOfEdges(0), hashStringLength(0), flowComputed(false)
 {
 	memset(&lastStats, 0, sizeof lastStats);
 	buildOverlapGraphFromHashTable(ht);
@@ -44,6 +44,7 @@ bool OverlapGraph::buildOverlapGraphFromHashTable(HashTable *ht)
 	flowComputed = false;
 	hashTable = ht;
 	dataSet = ht->getDataset();
+	hashStringLength = ht->getHashStringLength();
 	for (size_t i = 0; i < graph->size(); i++) {
 		for (size_t j = 0; j < graph->at(i)->size(); j++) delete graph->at(i)->at(j);
 		delete graph->at(i);
@@ -140,7 +141,7 @@ bool OverlapGraph::checkOverlap(Read *read1, Read *read2, UINT64 orient, UINT64 
 {
 	string s1 = read1->getStringForward();
 	string s2 = (orient < 2) ? read2->getStringForward() : read2->getStringReverse();
-	UINT64 h = hashTable ? hashTable->getHashStringLength() : lastStats.reserved;
+	UINT64 h = hashStringLength;
 	if ((orient & 1) == 0) {
 		if (s1.size() - start - h >= s2.size() - h) return false;
 		UINT64 n = s1.size() - (start + h);
@@ -155,7 +156,7 @@ bool OverlapGraph::checkOverlapForContainedRead(Read *read1, Read *read2, UINT64
 {
 	string s1 = read1->getStringForward();
 	string s2 = (orient < 2) ? read2->getStringForward() : read2->getStringReverse();
-	UINT64 h = hashTable ? hashTable->getHashStringLength() : lastStats.reserved;
+	UINT64 h = hashStringLength;
 	UINT64 rest2 = s2.size() - h;
 	if ((orient & 1) == 0) {
 		UINT64 rest1 = s1.size() - start - h;

@@ -31,6 +31,7 @@ class OverlapGraph
 		vector<vector<Edge *> *> *graph;
 		UINT64 numberOfNodes;
 		UINT64 numberOfEdges;
+		UINT64 hashStringLength;						// kept after the table is freed (checkOverlap needs it)
 		ogb_stats lastStats;
 		UINT8 twinEdgeOrientation(UINT8 orientation);
 		void materialise(const ogb_edge *edges, UINT64 n);

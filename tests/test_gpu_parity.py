@@ -157,3 +157,24 @@ def test_empty_and_tiny_inputs(ctx):
     orc = Oracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"]).run_all(Oracle.BFS)
     assert len(orc.edges()) == 2
     assert_same_edges(edges_as_tuples(og.edges()), orc.edges(), "pair")
+
+
+def test_cpp_dropin_matches_reference_dump(ctx, tmp_path):
+    """The C++ drop-in classes (metagenomics_b200/host: Dataset, HashTable, OverlapGraph, Edge) driven
+    exactly like MetaGenomics/main.cpp:33,45-47 by host/ogb_overlap produce the reference's dump."""
+    import subprocess
+    from metagenomics_b200 import synth
+    from oracle_lib import read_dump
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "metagenomics_b200", "host", "ogb_overlap")
+    assert os.path.exists(exe), "metagenomics_b200/host/ogb_overlap not built"
+    for name in ("config2_small", "config5_small", "palindromes", "tandem_mixed"):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        fa, dump = str(tmp_path / (name + ".fa")), str(tmp_path / (name + ".bin"))
+        synth.write_fasta(fa, z["bases"], z["offsets"])
+        kind = "-pe" if name == "config2_small" else "-se"          # paired input also fills the mate-pair lists
+        subprocess.run([exe, "-l", str(int(z["min_overlap"])), kind, "1", fa, "--dump", dump], check=True, timeout=120)
+        d = read_dump(dump)
+        assert d["n"] == len(z["sup"]) and np.array_equal(d["reads"]["fnv"], z["fnv"]), name
+        assert np.array_equal(d["reads"]["sup"], z["sup"]) and np.array_equal(d["reads"]["freq"], z["freq"]), name
+        assert np.array_equal(d["edges"], z["edges"]), name
+        assert d["number_of_nodes"] == int(z["number_of_nodes"]) and d["number_of_edges"] == int(z["number_of_edges"]), name
