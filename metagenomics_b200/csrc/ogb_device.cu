@@ -98,7 +98,7 @@ struct ogb_context {
 	u32 n = 0, uniform_len = 0, uniform_pw = 0, min_len = 0, max_len = 0;
 	bool have_reads = false;
 	// index
-	Pool<u64> slots;
+	Pool<u32> slots;
 	u32 nb = 0, h = 0;
 	bool have_table = false;
 	// containment
@@ -108,8 +108,14 @@ struct ogb_context {
 	// graph
 	Pool<u64> nodes, edges, pos, sums;
 	Pool<unsigned char> eflag, scratch_state;
-	Pool<u32> cnt, overflow, scratch_keys;
+	Pool<u32> cnt, scratch_keys;
 	Pool<ogb_edge> fin, pre, surv;
+	// scan staging: candidate queue of one chunk, per-read slot regions, spill list of heavy nodes
+	Pool<u32> cand_q, deg, fill, ov_q, big_list;
+	Pool<u64> cand_v, slots_e, ov_e, sort_scratch;
+	u64 *d_cursor = nullptr;         // candidate-queue cursor
+	u32 slot_cap = 64;               // slots per read (adapted to the largest degree seen)
+	u32 chunk_reads = 1u << 16;      // query reads per probe/verify launch pair
 	Pool<char> flush;
 	u64 n_final = 0, n_pre = 0;
 	bool have_graph = false, have_pre = false;
@@ -172,6 +178,7 @@ static int context_create_common(ogb_context **out, int device)
 	for (int i = 0; i < EV_COUNT; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
 	CUDA_TRY(cudaMalloc((void **)&c->d_ctr, CTR_COUNT * sizeof(u64)));
 	CUDA_TRY(cudaMalloc((void **)&c->d_tot, 2 * sizeof(u64)));
+	CUDA_TRY(cudaMalloc((void **)&c->d_cursor, sizeof(u64)));
 	CUDA_TRY(cudaMemset(c->d_tot, 0, 2 * sizeof(u64)));
 	CUDA_TRY(cudaMallocHost((void **)&c->h_ctr, CTR_COUNT * sizeof(u64)));
 	CUDA_TRY(cudaMemset(c->d_ctr, 0, CTR_COUNT * sizeof(u64)));
@@ -215,10 +222,13 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	if (c->comm) g_nccl.CommDestroy(c->comm);
 	c->words.release(); c->meta.release(); c->stage_bytes.release(); c->stage_offs.release(); c->stage_lens.release();
 	c->slots.release(); c->sup.release(); c->contained.release(); c->nodes.release(); c->edges.release(); c->pos.release();
-	c->sums.release(); c->eflag.release(); c->surv.release(); c->scratch_state.release(); c->cnt.release(); c->overflow.release();
+	c->sums.release(); c->eflag.release(); c->surv.release(); c->scratch_state.release(); c->cnt.release();
 	c->scratch_keys.release(); c->fin.release(); c->pre.release(); c->flush.release();
 	if (c->d_ctr) cudaFree(c->d_ctr);
 	if (c->d_tot) cudaFree(c->d_tot);
+	if (c->d_cursor) cudaFree(c->d_cursor);
+	c->cand_q.release(); c->deg.release(); c->fill.release(); c->ov_q.release(); c->big_list.release();
+	c->cand_v.release(); c->slots_e.release(); c->ov_e.release(); c->sort_scratch.release();
 	if (c->h_ctr) cudaFreeHost(c->h_ctr);
 	for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -280,6 +290,7 @@ static int upload_common(ogb_context *c, u64 total_words, const std::vector<u64>
 		OGB_TRY(c->meta.ensure(meta_host.size()));
 		CUDA_TRY(cudaMemcpyAsync(c->meta.p, meta_host.data(), meta_host.size() * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
 	}
+	c->slot_cap = 64;
 	c->have_reads = true; c->have_table = false; c->contain_done = false; c->any_contained = false; c->have_graph = false; c->have_pre = false;
 	return OGB_OK;
 }
@@ -378,16 +389,16 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 	CUDA_TRY(cudaSetDevice(c->device));
 	c->h = min_overlap - 1;                                                 // HashTable.cpp:54
 	// The reference sizes the table at the first listed prime > 8N+1 slots (HashTable.cpp:56), i.e.
-	// load factor <= 0.5 for its 4N entries. Same budget here: N buckets of 8 slots (64 B per read).
+	// load factor <= 0.5 for its 4N entries. Here: N buckets of 10 slots (64 B per read, load 0.4).
 	u64 nb = std::max<u64>((u64)c->n + 1, 512);
 	const char *lf = getenv("OGB_TABLE_BUCKETS_PER_READ");
 	if (lf && atof(lf) >= 0.5) nb = std::max<u64>((u64)(atof(lf) * c->n) + 1, 512);
 	if (nb >= (1ull << 32)) { ogb_set_error("index too large"); return OGB_E_CAPACITY; }
 	c->nb = (u32)nb;
-	OGB_TRY(c->slots.ensure(nb * OGB_SLOTS));
+	OGB_TRY(c->slots.ensure(nb * OGB_BWORDS));
 	c->launches = 0;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_HASH0], c->stream));
-	CUDA_TRY(cudaMemsetAsync(c->slots.p, 0, nb * OGB_SLOTS * sizeof(u64), c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->slots.p, 0, nb * OGB_BWORDS * sizeof(u32), c->stream));
 	if (c->n) {
 		u64 threads = (u64)c->n * 4;
 		k_hash_insert<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->rs(), c->tb());
@@ -398,7 +409,7 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	c->st.ms_hash_build = ev_ms(c, EV_HASH0, EV_HASH1);
 	c->st.table_buckets = nb;
-	c->st.table_bytes = nb * OGB_SLOTS * sizeof(u64);
+	c->st.table_bytes = nb * OGB_BWORDS * sizeof(u32);
 	c->have_table = true; c->contain_done = false; c->any_contained = false; c->have_graph = false;
 	c->st.ms_contain = 0; c->st.n_contained = 0; c->st.contain_probes = 0; c->st.contain_hits = 0;
 	return OGB_OK;
@@ -472,9 +483,41 @@ static ScanArgs scan_args(ogb_context *c, u32 lo, u32 hi)
 	ScanArgs a;
 	a.R = c->rs(); a.T = c->tb(); a.lo = lo; a.hi = hi;
 	a.contained = c->any_contained ? c->contained.p : nullptr;
-	a.sup = c->sup.p; a.edges = c->edges.p; a.edge_cap = c->edges.cap; a.nodes = c->nodes.p;
-	a.overflow_list = c->overflow.p; a.overflow_cap = (u32)c->overflow.cap; a.ctr = c->d_ctr;
+	a.cand_q = c->cand_q.p; a.cand_v = c->cand_v.p; a.cand_cap = c->cand_q.cap; a.cand_cursor = c->d_cursor;
+	a.sup = c->sup.p; a.slots_e = c->slots_e.p; a.slot_lo = lo; a.cap = c->slot_cap; a.deg = c->deg.p;
+	a.ov_q = c->ov_q.p; a.ov_e = c->ov_e.p; a.ov_cap = c->ov_q.cap; a.ctr = c->d_ctr;
 	return a;
+}
+
+// k_probe + k_verify over [lo,hi) in chunks of c->chunk_reads reads, so that the candidate queue of a
+// chunk stays L2-resident. Nothing here synchronises with the host.
+template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
+{
+	{
+		const char *e = getenv("OGB_CHUNK_READS");                           // experiment knob
+		if (e && atoll(e) >= 256) c->chunk_reads = (u32)std::min<long long>(atoll(e), 1ll << 30);
+		u64 want = e && atoll(e) > (1 << 16) ? 64ull << 20 : 8ull << 20;
+		if (c->cand_q.cap < want) { OGB_TRY(c->cand_q.ensure(want)); OGB_TRY(c->cand_v.ensure(want)); }
+	}
+	const int gp = grid_for(c, (const void *)k_probe<MODE>, 256), gv = grid_for(c, (const void *)k_verify<MODE>, 256);
+	const int gu = grid_for(c, (const void *)k_probe_uniform<MODE>, 256);
+	if (c->chunk_reads > (1u << 16)) c->chunk_reads = 1u << 16;             // k_probe_uniform indexes windows with 32 bits
+	ScanArgs a = scan_args(c, lo, hi);
+	for (u32 b0 = lo; b0 < hi; b0 += c->chunk_reads) {
+		a.lo = b0; a.hi = std::min<u64>(hi, (u64)b0 + c->chunk_reads);
+		CUDA_TRY(cudaMemsetAsync(c->d_cursor, 0, sizeof(u64), c->stream));
+		const u32 warps = a.hi - a.lo;
+		if (c->uniform_len && !a.contained) {
+			const u32 nwin = c->uniform_len - c->h - 1;
+			const u64 rounds = ((u64)warps * nwin + 31) / 32;
+			k_probe_uniform<MODE><<<(unsigned)std::min<u64>(gu, (rounds * 32 + 255) / 256), 256, 0, c->stream>>>(a, nwin, ~0ull / nwin + 1);
+		} else
+			k_probe<MODE><<<(unsigned)std::min<u64>(gp, ((u64)warps * 32 + 255) / 256), 256, 0, c->stream>>>(a);
+		k_verify<MODE><<<gv, 256, 0, c->stream>>>(a);
+		c->launches += 2;
+	}
+	CUDA_TRY(cudaGetLastError());
+	return OGB_OK;
 }
 
 extern "C" int ogb_mark_contained(ogb_context *c)
@@ -488,15 +531,25 @@ extern "C" int ogb_mark_contained(ogb_context *c)
 	CUDA_TRY(cudaMemsetAsync(c->sup.p, 0, ((size_t)c->n + 1) * sizeof(u64), c->stream));
 	if (c->n == 0 || c->min_len == c->max_len) { CUDA_TRY(cudaStreamSynchronize(c->stream)); return OGB_OK; }   // OverlapGraph.cpp:228
 	OGB_TRY(c->contained.ensure(((size_t)c->n + 31) / 32 + 1));
-	OGB_TRY(ctr_zero(c));
 	u32 lo, hi;
 	c->shard(lo, hi);
 	CUDA_TRY(cudaEventRecord(c->ev[EV_CONT0], c->stream));
-	ScanArgs a = scan_args(c, lo, hi);
-	a.contained = nullptr;
-	k_scan<MODE_CONTAIN><<<grid_for(c, (const void *)k_scan<MODE_CONTAIN>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(a);
-	CUDA_TRY(cudaGetLastError());
-	c->launches++;
+	for (int attempt = 0;; attempt++) {
+		if (attempt == 12) { ogb_set_error("ogb_mark_contained: candidate queue kept overflowing"); return OGB_E_CAPACITY; }
+		OGB_TRY(ctr_zero(c));
+		CUDA_TRY(cudaMemsetAsync(c->sup.p, 0, ((size_t)c->n + 1) * sizeof(u64), c->stream));
+		bool saved = c->any_contained;
+		c->any_contained = false;
+		int rc = scan_chunks<MODE_CONTAIN>(c, lo, hi);
+		c->any_contained = saved;
+		OGB_TRY(rc);
+		OGB_TRY(ctr_fetch(c));
+		if (c->h_ctr[CTR_CAND_MAX] > c->cand_q.cap) { c->chunk_reads = std::max<u32>(256, c->chunk_reads / 2); continue; }
+		break;
+	}
+	c->st.contain_probes = c->h_ctr[CTR_PROBES];
+	c->st.contain_hits = c->h_ctr[CTR_CONTAIN_HITS];
+	OGB_TRY(ctr_zero(c));
 	if (c->nranks > 1) NCCL_TRY(g_nccl.AllReduce(c->sup.p, c->sup.p, c->n, NCCL_UINT64, NCCL_MAX, c->comm, c->stream));   // C0
 	k_contained_bitmap<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->sup.p, c->n, c->contained.p, c->d_ctr);
 	CUDA_TRY(cudaGetLastError());
@@ -505,8 +558,6 @@ extern "C" int ogb_mark_contained(ogb_context *c)
 	OGB_TRY(ctr_fetch(c));
 	c->st.ms_contain = ev_ms(c, EV_CONT0, EV_CONT1);
 	c->st.n_contained = c->h_ctr[CTR_N_CONTAINED];
-	c->st.contain_probes = c->h_ctr[CTR_PROBES];
-	c->st.contain_hits = c->h_ctr[CTR_CONTAIN_HITS];
 	c->any_contained = c->st.n_contained > 0;
 	return OGB_OK;
 }
@@ -577,40 +628,68 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	OGB_TRY(c->nodes.ensure(per * G + 1));
 	OGB_TRY(c->cnt.ensure(per * G + 1));
 	OGB_TRY(c->pos.ensure((size_t)n + 1));
-	if (c->overflow.cap == 0) OGB_TRY(c->overflow.ensure(1 << 16));
-	if (c->edges.cap == 0) OGB_TRY(c->edges.ensure(std::max<u64>(1 << 22, (u64)(hi - lo) * 40 * (G > 1 ? 2 : 1))));
+	OGB_TRY(c->deg.ensure((size_t)n + 1));
+	OGB_TRY(c->fill.ensure(per + 1));
+	if (c->ov_q.cap == 0) { OGB_TRY(c->ov_q.ensure(1 << 20)); OGB_TRY(c->ov_e.ensure(1 << 20)); }
+	if (c->big_list.cap == 0) OGB_TRY(c->big_list.ensure(1 << 16));
+	const u32 nloc = hi - lo;
 
-	// ---- K3 (+ slow path), retried with larger pools if a capacity was exceeded
+	// ---- K3 (probe + verify in chunks) and K4 (node records, heavy nodes, per-node sort into the dense
+	// adjacency array); retried with larger pools when a capacity was exceeded
 	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL0], c->stream));
 	u64 local_edges = 0;
 	for (int attempt = 0;; attempt++) {
-		if (attempt == 4) { ogb_set_error("ogb_build_graph: edge pool kept overflowing"); return OGB_E_CAPACITY; }
+		if (attempt == 16) { ogb_set_error("ogb_build_graph: staging pools kept overflowing"); return OGB_E_CAPACITY; }
+		OGB_TRY(c->slots_e.ensure(std::max<u64>((u64)nloc * c->slot_cap, 1)));
 		OGB_TRY(ctr_zero(c));
-		ScanArgs a = scan_args(c, lo, hi);
+		CUDA_TRY(cudaMemsetAsync(c->deg.p + lo, 0, (size_t)nloc * sizeof(u32), c->stream));
 		CUDA_TRY(cudaEventRecord(c->ev[EV_K3A], c->stream));
-		k_scan<MODE_OVERLAP><<<grid_for(c, (const void *)k_scan<MODE_OVERLAP>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(a);
-		CUDA_TRY(cudaGetLastError());
+		OGB_TRY(scan_chunks<MODE_OVERLAP>(c, lo, hi));
 		CUDA_TRY(cudaEventRecord(c->ev[EV_K3B], c->stream));
-		c->launches++;
+		OGB_TRY(exclusive_scan(c, c->deg.p + lo, nloc, c->pos.p, c->d_tot));
+		if (nloc) { k_nodes<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->deg.p, c->pos.p, c->nodes.p, c->fill.p, lo, hi, c->slot_cap, c->d_ctr); c->launches++; }
+		CUDA_TRY(cudaMemcpyAsync(&local_edges, c->d_tot, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 		OGB_TRY(ctr_fetch(c));
-		u64 n_over = c->h_ctr[CTR_OVERFLOW];
-		if (n_over > c->overflow.cap) { OGB_TRY(c->overflow.ensure(n_over + 1024)); continue; }
-		if (n_over) {
-			k_scan_big<<<(unsigned)std::min<u64>(n_over, 4096), 256, 0, c->stream>>>(a, (u32)n_over);
+		if (c->h_ctr[CTR_CAND_MAX] > c->cand_q.cap) { c->chunk_reads = std::max<u32>(256, c->chunk_reads / 2); continue; }
+		const u64 n_over = c->h_ctr[CTR_OVERFLOW];
+		if (n_over > c->ov_q.cap) {                                          // many heavy nodes: more slots per read, bigger spill list
+			if (c->slot_cap < 256) c->slot_cap *= 2;
+			else { OGB_TRY(c->ov_q.ensure(n_over + n_over / 8 + 1024)); OGB_TRY(c->ov_e.ensure(n_over + n_over / 8 + 1024)); }
+			continue;
+		}
+		OGB_TRY(c->edges.ensure(std::max<u64>(local_edges + local_edges / 8 + 1024, 1 << 20)));
+		if (n_over) { k_place_overflow<<<(unsigned)((n_over + 255) / 256), 256, 0, c->stream>>>(c->ov_q.p, c->ov_e.p, n_over, c->nodes.p, c->edges.p, c->fill.p, lo); c->launches++; }
+		k_sort_nodes<<<grid_for(c, (const void *)k_sort_nodes, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->slots_e.p, c->edges.p, lo, hi, c->slot_cap,
+		                                                                                                       c->big_list.p, (u32)c->big_list.cap, c->d_ctr);
+		CUDA_TRY(cudaGetLastError());
+		c->launches++;
+		c->st.max_degree = c->h_ctr[CTR_MAX_DEGREE];
+		c->st.overflow_reads = 0;
+		if (c->st.max_degree > OGB_EC) {                                     // repeats: a few very large nodes
+			OGB_TRY(ctr_fetch(c));
+			u64 n_big = c->h_ctr[CTR_BIG_NODES];
+			if (n_big > c->big_list.cap) { OGB_TRY(c->big_list.ensure(n_big + 1024)); continue; }
+			u64 need = 0, m = 1;
+			while (m < c->st.max_degree) m <<= 1;
+			need = n_big * m;
+			OGB_TRY(c->sort_scratch.ensure(std::max<u64>(need, 1)));
+			k_sort_big<<<(unsigned)std::min<u64>(n_big, 2048), 256, 0, c->stream>>>(c->nodes.p, c->edges.p, c->big_list.p, (u32)n_big, c->sort_scratch.p, c->sort_scratch.cap, c->d_ctr);
 			CUDA_TRY(cudaGetLastError());
 			c->launches++;
-			OGB_TRY(ctr_fetch(c));
+			c->st.overflow_reads = n_big;
 		}
-		local_edges = c->h_ctr[CTR_EDGE_CURSOR];
-		if (local_edges > c->edges.cap) { OGB_TRY(c->edges.ensure(local_edges + local_edges / 16 + 1024)); continue; }
-		c->st.overflow_reads = n_over;
+		// next build on these reads: slots sized to the degrees actually seen
+		{
+			u32 want = (u32)std::min<u64>(256, std::max<u64>(16, (c->st.max_degree * 5 / 4 + 7) / 8 * 8));
+			if (n_over == 0 && want < c->slot_cap) c->slot_cap = want;
+			else if (n_over > 0 && c->slot_cap < 256 && n_over > local_edges / 64) c->slot_cap = std::min<u32>(256, c->slot_cap * 2);
+		}
 		break;
 	}
 	c->st.overlap_probes = c->h_ctr[CTR_PROBES];
 	c->st.probe_sectors = c->h_ctr[CTR_SECTORS];
 	c->st.candidates = c->h_ctr[CTR_CANDIDATES];
-	c->st.max_degree = c->h_ctr[CTR_MAX_DEGREE];
-	const u64 local_exact = local_edges - c->h_ctr[CTR_PAD];              // the slow path pads to powers of two
+	const u64 local_exact = local_edges;
 	c->st.edges_pre_local = local_exact;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL1], c->stream));
 

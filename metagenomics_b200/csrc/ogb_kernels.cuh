@@ -2,8 +2,9 @@
 //
 //   K0  k_pack_ascii / k_pack_words   Read::setRead + reverseComplement          (Read.cpp:75-127)
 //   K1  k_hash_insert                 HashTable::hashRead + insertIntoTable       (HashTable.cpp:88-195)
-//   K2  k_scan<MODE_CONTAIN>          markContainedReads + checkOverlapForContainedRead (OverlapGraph.cpp:225-340)
-//   K3  k_scan<MODE_OVERLAP>          insertAllEdgesOfRead + checkOverlap + per-node sort (OverlapGraph.cpp:354-383,529-565)
+//   K2  k_probe/k_verify<CONTAIN>     markContainedReads + checkOverlapForContainedRead (OverlapGraph.cpp:225-340)
+//   K3  k_probe/k_verify<OVERLAP>     insertAllEdgesOfRead + checkOverlap (OverlapGraph.cpp:354-383,529-565)
+//   K4  k_nodes/k_sort_nodes          per-node sort by offset (OverlapGraph.cpp:563) + CSR
 //   K5  k_mark                        markTransitiveEdges                         (OverlapGraph.cpp:574-615)
 //   K6  k_twin_keep / k_compact       removeTransitiveEdges                       (OverlapGraph.cpp:623-661)
 //       k_lookup_*                    HashTable::getListOfReads                   (HashTable.cpp:202-221)
@@ -17,13 +18,16 @@
 //                 offset off, reverse complement at off + pw, pw = 2*ceil(L/64) words (16-byte
 //                 aligned strands; 100 bp -> 32 B = one sector). Uniform-length data sets use
 //                 off = idx*2*pw (no metadata load); mixed lengths use meta[idx] = off<<16 | L.
-//   index         nb buckets x 8 slots x u64 (one 64-byte DRAM burst per bucket: measured on B200, a
-//                 random 32-byte sector read costs a 64-byte HBM fetch anyway, profiles/exp_r1_l2fetch.txt).
-//                 slot = fp32<<32 | id<<2 | o, 0 = empty. One slot per (key,value); a key's entries
-//                 sit in its home bucket and, when that is full, in the following buckets (linear
-//                 probing by bucket). Only a 32-bit fingerprint of the key is stored: every consumer
-//                 verifies the complete overlap (window included) against the packed reads, which
-//                 makes the result exact and independent of hash values.
+//   index         nb buckets of 64 bytes (one HBM burst: measured on B200, a random 32-byte sector read
+//                 costs a 64-byte fetch anyway, profiles/exp_r1_l2fetch.txt). A bucket is 16 u32 words:
+//                 words 0..4 hold ten 16-bit key fingerprints (slot i in half i&1 of word i>>1), words
+//                 5..14 the ten values id<<2|o (0 = empty), word 15 is unused. One slot per (key,value);
+//                 a key's entries sit in its home bucket and, when that is full, in the following
+//                 buckets (linear probing by bucket). Only a fingerprint of the key is stored: every
+//                 consumer verifies the complete overlap (window included) against the packed reads,
+//                 which makes the result exact and independent of hash values.
+//                 4N entries in N buckets = load 0.4: the ten-slot compare is five SIMD instructions
+//                 and fewer than 1 % of the buckets spill.
 //   edges         u64 = offset<<48 | dst<<16 | orient<<8, so integer order = (offset,dst,orient).
 //   nodes         u64 = start<<24 | degree  (adjacency of a node is contiguous and sorted).
 #pragma once
@@ -33,18 +37,13 @@
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-#define OGB_SLOTS 8             // slots per bucket (64 bytes = one HBM burst)
+#define OGB_SLOTS 10            // slots per bucket (64 bytes = one HBM burst)
+#define OGB_BWORDS 16           // u32 words per bucket
 #define OGB_WARPS 8             // warps per block in the scan / mark kernels
-#ifndef OGB_SCAN_BLOCKS
-#define OGB_SCAN_BLOCKS 4       // resident blocks per SM the scan kernel is compiled for (register cap)
-#endif
-#define OGB_HQ 288              // per-warp candidate queue (<= 31 left over + 32 lanes x 8 slots)
-#define OGB_STAGE_WORDS 32      // query reads up to 1024 bp are staged in shared memory (longer: slow path)
-#define OGB_EC 256              // per-warp edge buffer (reads with more edges take the slow path)
+#define OGB_EC 256              // largest node sorted in shared memory by one warp
 #define OGB_SETCAP 512          // per-warp neighbour set slots in shared memory (degree <= 256)
 #define OGB_DEG_BITS 24
 #define OGB_DEG_MASK 0xFFFFFFull
-#define OGB_NODE_OVERFLOW OGB_DEG_MASK   // degree field value marking "take the slow path"
 
 enum { MODE_OVERLAP = 0, MODE_CONTAIN = 1 };
 
@@ -52,7 +51,7 @@ enum { MODE_OVERLAP = 0, MODE_CONTAIN = 1 };
 enum {
 	CTR_EDGE_CURSOR = 0, CTR_OVERFLOW, CTR_PROBES, CTR_SECTORS, CTR_CANDIDATES, CTR_CONTAIN_HITS,
 	CTR_PIVOT_ENTRIES, CTR_ACTIVE_PIVOTS, CTR_MAX_DEGREE, CTR_N_CONTAINED, CTR_NODES_FINAL,
-	CTR_ASYMMETRIC, CTR_SCRATCH_CURSOR, CTR_SCRATCH_FAIL, CTR_EDGES_DROPPED, CTR_PAD, CTR_COUNT
+	CTR_ASYMMETRIC, CTR_SCRATCH_CURSOR, CTR_SCRATCH_FAIL, CTR_CAND_MAX, CTR_BIG_NODES, CTR_COUNT
 };
 
 struct ReadStore {
@@ -64,7 +63,7 @@ struct ReadStore {
 };
 
 struct Table {
-	u64 *slots;
+	u32 *slots;          // nb * OGB_BWORDS words
 	u32 nb;              // buckets
 	u32 h;               // hashStringLength = minOverlap-1 (HashTable.cpp:54)
 };
@@ -89,7 +88,15 @@ struct LdShared { static __device__ __forceinline__ u64 ld(const u64 *p) { retur
 struct LdGlobal { static __device__ __forceinline__ u64 ld(const u64 *p) { return __ldg(p); } };
 struct LdStream { static __device__ __forceinline__ u64 ld(const u64 *p) { return ld_na(p); } };
 
-__device__ __forceinline__ u64 funnel(u64 a, u64 b, u32 sh) { return sh ? ((a << sh) | (b >> (64 - sh))) : a; }
+// Upper 64 bits of (a:b) << sh for sh in [0,63]: two 32-bit funnel shifts (SHF) after picking the
+// three source words, instead of the 64-bit shift / or / select sequence the compiler emits.
+__device__ __forceinline__ u64 funnel(u64 a, u64 b, u32 sh)
+{
+	const u32 a1 = (u32)(a >> 32), a0 = (u32)a, b1 = (u32)(b >> 32), b0 = (u32)b;
+	const bool hi = sh >= 32;
+	const u32 x2 = hi ? a0 : a1, x1 = hi ? b1 : a0, x0 = hi ? b0 : b1;
+	return ((u64)__funnelshift_l(x1, x2, sh) << 32) | __funnelshift_l(x0, x1, sh);
+}
 
 // 32 bases starting at base p of a packed strand (high bits first). The words after a strand are
 // always allocated, so loads past its end are safe; callers mask what they do not need.
@@ -138,26 +145,57 @@ template <class LD> __device__ __forceinline__ u64 key_hash(const u64 *__restric
 	return mix64(acc, extract32<LD>(w, p) & (~0ULL << (64 - 2 * rem)));
 }
 
-__device__ __forceinline__ u32 hash_fp(u64 hash) { u32 f = (u32)hash; return f ? f : 1u; }   // 0 is reserved for "empty"
+__device__ __forceinline__ u32 hash_fp(u64 hash) { u32 f = (u32)hash & 0xFFFFu; return f ? f : 1u; }   // 16 bits; 0 is reserved for "empty"
 __device__ __forceinline__ u32 bucket_of(u64 hash, u32 nb) { return __umulhi((u32)(hash >> 32), nb); }
 
 // s[a..a+len) == t[b..b+len) on packed strands, streaming one new word per side and 32 bases. No
 // early exit: (almost) every candidate verifies, and independent iterations keep the sector
-// requests of the partner read in flight together.
+// requests of the partner read in flight together. Words past the last base of a region are never
+// loaded: for a 100 bp partner that would cost a second 64-byte HBM burst per candidate.
 template <class LDS, class LDT>
 __device__ __forceinline__ bool region_equal(const u64 *__restrict__ s, u32 a, const u64 *__restrict__ t, u32 b, u32 len)
 {
 	const u32 sa = (a & 31) << 1, sb = (b & 31) << 1;
 	const u64 *ws = s + (a >> 5), *wt = t + (b >> 5);
+	const u64 *es = s + ((a + len - 1) >> 5), *et = t + ((b + len - 1) >> 5);   // last words that hold compared bases
 	u64 s0 = LDS::ld(ws), t0 = LDT::ld(wt), diff = 0;
 	u32 k = 0;
 	for (; k + 32 <= len; k += 32) {
-		u64 s1 = LDS::ld(++ws), t1 = LDT::ld(++wt);
+		++ws; ++wt;
+		const u64 s1 = ws <= es ? LDS::ld(ws) : 0, t1 = wt <= et ? LDT::ld(wt) : 0;
 		diff |= funnel(s0, s1, sa) ^ funnel(t0, t1, sb);
 		s0 = s1; t0 = t1;
 	}
-	u32 rem = len - k;
-	if (rem) diff |= (funnel(s0, LDS::ld(ws + 1), sa) ^ funnel(t0, LDT::ld(wt + 1), sb)) & (~0ULL << (64 - 2 * rem));
+	const u32 rem = len - k;
+	if (rem) {
+		++ws; ++wt;
+		const u64 s1 = ws <= es ? LDS::ld(ws) : 0, t1 = wt <= et ? LDT::ld(wt) : 0;
+		diff |= (funnel(s0, s1, sa) ^ funnel(t0, t1, sb)) & (~0ULL << (64 - 2 * rem));
+	}
+	return diff == 0;
+}
+
+// p[pa..pa+len) == q[0..len): the common shape of both overlap checks (one side always starts at a
+// strand boundary), one funnel shift per 32 bases.
+template <class LDP, class LDQ>
+__device__ __forceinline__ bool region_equal_aligned(const u64 *__restrict__ p, u32 pa, const u64 *__restrict__ q, u32 len)
+{
+	const u32 sh = (pa & 31) << 1;
+	const u64 *wp = p + (pa >> 5), *ep = p + ((pa + len - 1) >> 5);
+	u64 p0 = LDP::ld(wp), diff = 0;
+	u32 k = 0;
+	for (; k + 32 <= len; k += 32) {
+		++wp;
+		const u64 p1 = wp <= ep ? LDP::ld(wp) : 0;
+		diff |= funnel(p0, p1, sh) ^ LDQ::ld(q + (k >> 5));
+		p0 = p1;
+	}
+	const u32 rem = len - k;
+	if (rem) {
+		++wp;
+		const u64 p1 = wp <= ep ? LDP::ld(wp) : 0;
+		diff |= (funnel(p0, p1, sh) ^ LDQ::ld(q + (k >> 5))) & (~0ULL << (64 - 2 * rem));
+	}
 	return diff == 0;
 }
 
@@ -257,105 +295,328 @@ __global__ void k_hash_insert(ReadStore R, Table T)
 	const u64 *w = R.words + off + (o >> 1) * padded_words(L);
 	u32 p = (o & 1) ? L - T.h : 0;
 	u64 hash = key_hash<LdGlobal>(w, p, T.h);
-	u64 val = ((u64)hash_fp(hash) << 32) | ((u64)(idx + 1) << 2) | o;
+	const u32 fp = hash_fp(hash), val = ((idx + 1) << 2) | o;
 	u32 b = bucket_of(hash, T.nb);
 	for (;;) {
-		u64 *slot = T.slots + (u64)b * OGB_SLOTS;
-		// one L2-coherent look at the whole bucket, then a CAS on its first empty slot; buckets fill
-		// front to back, so a lost race just moves on to the next slot
-		u64 cur[OGB_SLOTS];
+		u32 *w = T.slots + (u64)b * OGB_BWORDS;
+		// one L2-coherent look at the ten values, then a CAS on the first empty one; buckets fill front
+		// to back, so a lost race just moves on to the next slot. The fingerprint half-word is ORed in
+		// after the value is claimed (readers run in later kernels).
+		u32 cur[12];
 		#pragma unroll
-		for (int q = 0; q < OGB_SLOTS; q += 2)
-			asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(cur[q]), "=l"(cur[q + 1]) : "l"(slot + q) : "memory");
-		int s = 0;
+		for (int q = 0; q < 12; q += 4)
+			asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(cur[q]), "=r"(cur[q + 1]), "=r"(cur[q + 2]), "=r"(cur[q + 3]) : "l"(w + 4 + q) : "memory");
+		int s = OGB_SLOTS;                                                    // cur[1 + i] = value of slot i
 		#pragma unroll
-		for (int q = OGB_SLOTS - 1; q >= 0; q--) s = cur[q] == 0 ? q : s;
+		for (int q = OGB_SLOTS - 1; q >= 0; q--) s = cur[1 + q] == 0 ? q : s;
 		bool done = false;
-		if (cur[OGB_SLOTS - 1] == 0)
-			for (; s < OGB_SLOTS && !done; s++) done = atomicCAS(slot + s, 0ull, val) == 0;
-		if (done) break;
+		for (; s < OGB_SLOTS && !done; s++) done = atomicCAS(w + 5 + s, 0u, val) == 0;
+		if (done) { atomicOr(w + ((s - 1) >> 1), fp << (16 * ((s - 1) & 1))); break; }
 		b = (b + 1 == T.nb) ? 0 : b + 1;
 	}
 }
 
-// One bucket = 64 bytes = two 256-bit non-allocating loads.
-__device__ __forceinline__ void load_bucket(const u64 *__restrict__ slots, u32 b, u64 (&s)[OGB_SLOTS])
+// One bucket = 64 bytes = two 256-bit non-allocating loads. w[0..4] fingerprint pairs, w[5..14] values.
+__device__ __forceinline__ void load_bucket(const u32 *__restrict__ slots, u32 b, u32 (&w)[OGB_BWORDS])
 {
-	const u64 *p = slots + (u64)b * OGB_SLOTS;
-	asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(s[0]), "=l"(s[1]), "=l"(s[2]), "=l"(s[3]) : "l"(p));
-	asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(s[4]), "=l"(s[5]), "=l"(s[6]), "=l"(s[7]) : "l"(p + 4));
+	const u32 *p = slots + (u64)b * OGB_BWORDS;
+	u64 x[8];
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x[0]), "=l"(x[1]), "=l"(x[2]), "=l"(x[3]) : "l"(p));
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x[4]), "=l"(x[5]), "=l"(x[6]), "=l"(x[7]) : "l"(p + 8));
+	#pragma unroll
+	for (int i = 0; i < 8; i++) { w[2 * i] = (u32)x[i]; w[2 * i + 1] = (u32)(x[i] >> 32); }
+}
+
+// Ten-bit mask of the slots whose 16-bit fingerprint equals fp (fp != 0, so empty slots never match).
+// Fast reject with the zero-halfword trick on w ^ splat (3 ALU ops per word pair); the exact mask is
+// only built when some halfword may match.
+__device__ __forceinline__ u32 match_bucket(const u32 (&w)[OGB_BWORDS], u32 fp)
+{
+	const u32 splat = fp | (fp << 16);
+	u32 any = 0;
+	#pragma unroll
+	for (int i = 0; i < 5; i++) { const u32 x = w[i] ^ splat; any |= (x - 0x00010001u) & ~x & 0x80008000u; }
+	if (any == 0) return 0;
+	u32 mm = 0;
+	#pragma unroll
+	for (int i = 0; i < 5; i++) {
+		const u32 x = w[i] ^ splat;
+		mm |= (((x & 0xFFFFu) == 0) | (((x >> 16) == 0) << 1)) << (2 * i);
+	}
+	return mm;
+}
+// value of slot k (0..9)
+__device__ __forceinline__ u32 bucket_value(const u32 (&w)[OGB_BWORDS], int k)
+{
+	u32 v = w[5];
+	#pragma unroll
+	for (int q = 1; q < OGB_SLOTS; q++) v = (k == q) ? w[5 + q] : v;
+	return v;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 / K3: sliding-window scan, one warp per query read.
+// K2 / K3: sliding-window scan, decomposed into thin data-parallel kernels (a fused warp-per-read
+// kernel measured latency-bound at 31-50 % occupancy, profiles/r1_notes.md):
 //
-// Phase A  lane l probes windows j = 1+l, 33+l, ... (j = 1 .. L-h-1, OverlapGraph.cpp:534): key hash
-//          -> bucket sector -> fingerprint compare; matches go to a per-warp candidate queue in
-//          shared memory (ballot + popc compaction, warp-synchronous).
-// Phase B  whenever >= 32 candidates are queued (and at the end) each lane verifies one candidate
-//          against the partner's packed strand (one random sector for 100 bp) -- checkOverlap /
-//          checkOverlapForContainedRead restated on packed words.
-// Phase C  (overlap mode) verified edges are sorted by (offset,dst,orient) in shared memory
-//          (bitonic), a contiguous range of the global edge array is claimed with one atomicAdd and
-//          the node record start<<24|deg is written: the adjacency comes out sorted (:563) with no
-//          global sort. Reads with more than OGB_EC edges are queued for k_scan_big.
+//   k_probe   warp per query read, lanes over its windows j = 1 .. L-h-1 (OverlapGraph.cpp:534):
+//             key -> hash -> one 64-byte bucket (non-allocating 256-bit loads) -> fingerprint compare.
+//             Matches are appended as candidates (read, j, slot value) to a global queue; a warp
+//             reserves queue space in chunks of OGB_QCHUNK entries, so the queue cursor sees one
+//             atomic per ~100 candidates, and pads its last chunk with sentinels.
+//   k_verify  one THREAD per candidate: fetch the partner strand (one 64-byte burst for 100 bp) and
+//             compare the whole overlap on packed words -- checkOverlap / checkOverlapForContainedRead.
+//             Overlap mode appends the edge to the source read's slot region (deg[] atomics, spread
+//             over N addresses); containment mode does the atomicMax on superRead.
+//   k_nodes / k_place_overflow / k_sort_nodes   node records, heavy nodes, per-node sort (:563).
+//
+// The host runs k_probe + k_verify over chunks of reads sized so that the candidate queue of a chunk
+// stays L2-resident.
+//
+// Adjacency layout: read idx owns edges[idx*cap .. idx*cap+cap) ("slots"); a node with more than cap
+// edges is moved, complete, to an extension area behind the slot region. nodes[idx] = start<<24|deg
+// describes either case, so the later kernels do not care.
 // ------------------------------------------------------------------------------------------------
+#define OGB_QCHUNK 128          // candidate-queue entries a warp reserves at a time
+#define OGB_NOCAND 0xFFFFFFFFu  // sentinel read index of a padding entry
 
 struct ScanArgs {
 	ReadStore R;
 	Table T;
-	u32 lo, hi;                 // query read indices [lo, hi) (this rank's shard)
+	u32 lo, hi;                 // query read indices [lo, hi) of this launch
 	const u32 *contained;       // bitmap by read index (null when no read is contained)
+	// candidate queue
+	u32 *cand_q;                // read index (OGB_NOCAND = padding)
+	u64 *cand_v;                // j<<32 | slot value (id<<2|o)
+	u64 cand_cap;
+	u64 *cand_cursor;           // entries reserved so far (may exceed cand_cap: entries beyond are dropped and counted)
+	// outputs
 	u64 *sup;                   // MODE_CONTAIN: per read idx, max over hits of (L_super<<32 | ~super_idx)
-	u64 *edges;                 // MODE_OVERLAP outputs
-	u64 edge_cap;
-	u64 *nodes;
-	u32 *overflow_list;
-	u32 overflow_cap;
+	u64 *slots_e;               // MODE_OVERLAP: slot regions, read idx owns [(idx-slot_lo)*cap, +cap)
+	u32 slot_lo;
+	u32 cap;                    // slots per read
+	u32 *deg;                   // edges found per read, by read idx (keeps counting past cap)
+	u32 *ov_q;                  // overflow edges of heavy nodes: read idx / edge
+	u64 *ov_e;
+	u64 ov_cap;
 	u64 *ctr;
 };
 
-// Verifies candidate (j, val) of query read qi (strand words s, length L1). Returns the number of
-// edges produced (0, 1, or 2 for a self-overlap) in e0/e1; in MODE_CONTAIN performs the atomicMax.
-template <int MODE, class LDS>
-__device__ __forceinline__ int verify_candidate(const ScanArgs &A, const u64 *__restrict__ s, u32 qi, u32 L1, u32 j, u32 val, u64 &e0, u64 &e1)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_probe(ScanArgs A)
 {
-	const u32 h = A.T.h;
-	u32 ri = (val >> 2) - 1, o = val & 3;
-	u64 roff; u32 L2;
-	read_geom(A.R, ri, roff, L2);
-	const u64 *t = A.R.words + roff + (o >> 1) * padded_words(L2);
-	if (MODE == MODE_CONTAIN) {
-		// OverlapGraph.cpp:256: read1 must be longer; :302-340 restated on the whole of read2.
-		if (L1 <= L2) return 0;
-		u32 a;
-		if ((o & 1) == 0) { if (L1 - j < L2) return 0; a = j; }              // :316-321
-		else { if (j < L2 - h) return 0; a = j - (L2 - h); }                // :331-336
-		if (!region_equal<LDS, LdStream>(s, a, t, 0, L2)) return 0;
-		atomicMax(A.sup + ri, ((u64)L1 << 32) | (u64)(0xFFFFFFFFu - qi));   // :259-268
-		return 1;
-	} else {
-		if (A.contained && ((__ldg(A.contained + (ri >> 5)) >> (ri & 31)) & 1)) return 0;   // :548 superReadID == 0
-		u32 a, b, len, orient, offset;
-		if ((o & 1) == 0) {               // key = prefix of t: s[j..L1) must equal t[0..L1-j)      (:359-370)
-			if (L1 - j >= L2) return 0;
-			a = j; b = 0; len = L1 - j;
-			orient = o == 0 ? 3 : 2;      // :552,:554
-			offset = j;                   // L1 - overlap, overlap = L1 - j
-		} else {                          // key = suffix of t: s[0..j+h) must equal t[L2-h-j..L2)  (:371-382)
-			if (L2 - h < j) return 0;
-			a = 0; b = L2 - h - j; len = h + j;
-			orient = o == 1 ? 0 : 1;      // :553,:555
-			offset = L1 - h - j;          // L1 - overlap, overlap = h + j
+	const u32 lane = threadIdx.x & 31;
+	const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	const u32 h = A.T.h, lt = (1u << lane) - 1;
+	u64 c_probes = 0, c_sectors = 0;
+	u64 qbase = 0; u32 qused = OGB_QCHUNK;                                   // this warp's reserved queue chunk (warp-uniform)
+
+	// appends one candidate per lane of `bal` (warp-synchronous)
+	auto append = [&](u32 bal, bool has, u32 qi, u64 v) {
+		const u32 n = __popc(bal);
+		if (qused + n > OGB_QCHUNK) {                                        // pad the rest of the chunk, reserve a new one
+			for (u32 i = qused + lane; i < OGB_QCHUNK; i += 32) if (qbase + i < A.cand_cap) A.cand_q[qbase + i] = OGB_NOCAND;
+			if (lane == 0) qbase = atomicAdd(A.cand_cursor, (u64)OGB_QCHUNK);
+			qbase = __shfl_sync(0xFFFFFFFFu, qbase, 0);
+			qused = 0;
 		}
-		if (!region_equal<LDS, LdStream>(s, a, t, b, len)) return 0;
-		e0 = make_edge(offset & 0xFFFF, ri + 1, orient);
-		if (ri != qi) return 1;
-		// Self-overlap: the reference inserts the edge and its twin object into the same list
-		// (OverlapGraph.cpp:409-417); twin offset = (UINT16)(L2 + offset - L1) = offset.
-		e1 = make_edge(offset & 0xFFFF, ri + 1, twin_orient(orient));
-		return 2;
+		if (has) {
+			const u64 at = qbase + qused + __popc(bal & lt);
+			if (at < A.cand_cap) { A.cand_q[at] = qi; A.cand_v[at] = v; }
+		}
+		qused += n;
+	};
+
+	for (u32 qi = A.lo + gw; qi < A.hi; qi += nwarps) {
+		if (MODE == MODE_OVERLAP && A.contained && ((__ldg(A.contained + (qi >> 5)) >> (qi & 31)) & 1)) continue;   // (:548)
+		u64 off; u32 L1;
+		read_geom(A.R, qi, off, L1);
+		const u64 *s = A.R.words + off;
+		const u32 nwin = L1 - h - 1;
+		c_probes += nwin;
+		for (u32 jb = 1; jb <= nwin; jb += 32) {
+			const u32 j = jb + lane;
+			bool active = j <= nwin;
+			u32 b = 0, fp = 0;
+			if (active) { const u64 hash = key_hash<LdGlobal>(s, j, h); b = bucket_of(hash, A.T.nb); fp = hash_fp(hash); }
+			const u64 tag = (u64)j << 32;
+			while (__any_sync(0xFFFFFFFFu, active)) {
+				u32 w[OGB_BWORDS];
+				u32 mm = 0;                                                  // slots of this lane's bucket whose fingerprint matches
+				if (active) {
+					load_bucket(A.T.slots, b, w);
+					c_sectors++;
+					mm = match_bucket(w, fp);
+					// K1 fills a bucket front to back, so "last slot taken" = full = the key may continue in the next bucket
+					active = w[5 + OGB_SLOTS - 1] != 0;
+					if (active) b = (b + 1 == A.T.nb) ? 0 : b + 1;
+				}
+				u32 bal;
+				while ((bal = __ballot_sync(0xFFFFFFFFu, mm != 0)) != 0) {   // one round per match rank; a 2nd match in a bucket is rare
+					u64 v = 0;
+					if (mm) v = tag | bucket_value(w, __ffs(mm) - 1);
+					append(bal, mm != 0, qi, v);
+					mm &= mm - 1;
+				}
+			}
+		}
 	}
+	for (u32 i = qused + lane; i < OGB_QCHUNK; i += 32) if (qbase + i < A.cand_cap) A.cand_q[qbase + i] = OGB_NOCAND;
+	for (int d = 16; d > 0; d >>= 1) c_sectors += __shfl_down_sync(0xFFFFFFFFu, c_sectors, d);
+	if (lane == 0) { atomicAdd(A.ctr + CTR_PROBES, c_probes); atomicAdd(A.ctr + CTR_SECTORS, c_sectors); }
+}
+
+// k_probe for data sets with one read length (no contained reads, no per-read geometry): the windows
+// of all reads of the launch are flattened over the threads, x -> (read, j) by an exact multiply-
+// shift division, so every lane of every warp owns a window.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_probe_uniform(ScanArgs A, u32 nwin, u64 div_magic)
+{
+	const u32 lane = threadIdx.x & 31;
+	const u32 h = A.T.h, lt = (1u << lane) - 1;
+	const u32 total = (A.hi - A.lo) * nwin;                                  // < 2^32: a launch covers at most 2^16 reads
+	const u32 rounds = (total + 31) >> 5;
+	const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	const u32 stride = 2 * A.R.uniform_pw;
+	u64 c_sectors = 0;
+	u64 qbase = 0; u32 qused = OGB_QCHUNK;
+
+	for (u32 rd = gw; rd < rounds; rd += nwarps) {
+		const u32 x = rd * 32 + lane;
+		bool active = x < total;
+		const u32 qr = nwin == 1 ? x : (u32)__umul64hi(div_magic, (u64)x);  // x / nwin (Lemire: exact for 32-bit x, nwin > 1)
+		const u32 j = x - qr * nwin + 1, qi = A.lo + qr;
+		u32 b = 0, fp = 0;
+		if (active) {
+			const u64 hash = key_hash<LdGlobal>(A.R.words + (u64)qi * stride, j, h);
+			b = bucket_of(hash, A.T.nb); fp = hash_fp(hash);
+		}
+		const u64 tag = (u64)j << 32;
+		while (__any_sync(0xFFFFFFFFu, active)) {
+			u32 w[OGB_BWORDS];
+			u32 mm = 0;
+			if (active) {
+				load_bucket(A.T.slots, b, w);
+				c_sectors++;
+				mm = match_bucket(w, fp);
+				active = w[5 + OGB_SLOTS - 1] != 0;                          // full bucket: the key may continue in the next one
+				if (active) b = (b + 1 == A.T.nb) ? 0 : b + 1;
+			}
+			u32 bal;
+			while ((bal = __ballot_sync(0xFFFFFFFFu, mm != 0)) != 0) {
+				const u32 n = __popc(bal);
+				if (qused + n > OGB_QCHUNK) {                                    // pad the rest of the chunk, reserve a new one
+					for (u32 i = qused + lane; i < OGB_QCHUNK; i += 32) if (qbase + i < A.cand_cap) A.cand_q[qbase + i] = OGB_NOCAND;
+					if (lane == 0) qbase = atomicAdd(A.cand_cursor, (u64)OGB_QCHUNK);
+					qbase = __shfl_sync(0xFFFFFFFFu, qbase, 0);
+					qused = 0;
+				}
+				if (mm) {
+					const u64 at = qbase + qused + __popc(bal & lt);
+					if (at < A.cand_cap) { A.cand_q[at] = qi; A.cand_v[at] = tag | bucket_value(w, __ffs(mm) - 1); }
+					mm &= mm - 1;
+				}
+				qused += n;
+			}
+		}
+	}
+	for (u32 i = qused + lane; i < OGB_QCHUNK; i += 32) if (qbase + i < A.cand_cap) A.cand_q[qbase + i] = OGB_NOCAND;
+	for (int d = 16; d > 0; d >>= 1) c_sectors += __shfl_down_sync(0xFFFFFFFFu, c_sectors, d);
+	if (lane == 0) atomicAdd(A.ctr + CTR_SECTORS, c_sectors);
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.ctr + CTR_PROBES, (u64)total);
+}
+
+// One thread per candidate.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_verify(ScanArgs A)
+{
+	const u64 total = min(*A.cand_cursor, A.cand_cap);
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(A.ctr + CTR_CAND_MAX, *A.cand_cursor);
+	const u32 h = A.T.h;
+	u32 c_cand = 0, c_hits = 0;
+	for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (u64)gridDim.x * blockDim.x) {
+		const u32 qi = A.cand_q[c];
+		if (qi == OGB_NOCAND) continue;
+		const u64 cv = A.cand_v[c];
+		const u32 j = (u32)(cv >> 32), val = (u32)cv;
+		c_cand++;
+		u64 off; u32 L1;
+		read_geom(A.R, qi, off, L1);
+		const u64 *s = A.R.words + off;
+		const u32 ri = (val >> 2) - 1, o = val & 3;
+		u64 roff; u32 L2;
+		read_geom(A.R, ri, roff, L2);
+		const u64 *t = A.R.words + roff + (o >> 1) * padded_words(L2);
+		if (MODE == MODE_CONTAIN) {
+			// OverlapGraph.cpp:256: read1 must be longer; :302-340 restated on the whole of read2.
+			if (L1 <= L2) continue;
+			u32 a;
+			if ((o & 1) == 0) { if (L1 - j < L2) continue; a = j; }          // :316-321
+			else { if (j < L2 - h) continue; a = j - (L2 - h); }            // :331-336
+			if (!region_equal_aligned<LdGlobal, LdGlobal>(s, a, t, L2)) continue;
+			atomicMax(A.sup + ri, ((u64)L1 << 32) | (u64)(0xFFFFFFFFu - qi));   // :259-268
+			c_hits++;
+		} else {
+			if (A.contained && ((__ldg(A.contained + (ri >> 5)) >> (ri & 31)) & 1)) continue;   // :548 superReadID == 0
+			u32 pa, len, orient, offset;
+			const u64 *pp, *qq;               // compare pp[pa..pa+len) with qq[0..len)
+			if ((o & 1) == 0) {               // key = prefix of t: s[j..L1) must equal t[0..L1-j)      (:359-370)
+				if (L1 - j >= L2) continue;
+				pp = s; pa = j; qq = t; len = L1 - j;
+				orient = o == 0 ? 3 : 2;      // :552,:554
+				offset = j;                   // L1 - overlap, overlap = L1 - j
+			} else {                          // key = suffix of t: s[0..j+h) must equal t[L2-h-j..L2)  (:371-382)
+				if (L2 - h < j) continue;
+				pp = t; pa = L2 - h - j; qq = s; len = h + j;
+				orient = o == 1 ? 0 : 1;      // :553,:555
+				offset = L1 - h - j;          // L1 - overlap, overlap = h + j
+			}
+			if (!region_equal_aligned<LdGlobal, LdGlobal>(pp, pa, qq, len)) continue;
+			// Self-overlap: the reference inserts the edge and its twin object into the same list
+			// (OverlapGraph.cpp:409-417); twin offset = (UINT16)(L2 + offset - L1) = offset.
+			const u32 ne = ri == qi ? 2 : 1;
+			const u64 e0 = make_edge(offset & 0xFFFF, ri + 1, orient), e1 = make_edge(offset & 0xFFFF, ri + 1, twin_orient(orient));
+			const u32 pos = atomicAdd(A.deg + qi, ne);
+			for (u32 q = 0; q < ne; q++) {
+				const u64 e = q ? e1 : e0;
+				if (pos + q < A.cap) A.slots_e[(u64)(qi - A.slot_lo) * A.cap + pos + q] = e;
+				else {                                                       // heavy node: spill, placed by k_place_overflow
+					const u64 ov = atomicAdd(A.ctr + CTR_OVERFLOW, 1ull);
+					if (ov < A.ov_cap) { A.ov_q[ov] = qi; A.ov_e[ov] = e; }
+				}
+			}
+		}
+	}
+	for (int d = 16; d > 0; d >>= 1) { c_cand += __shfl_down_sync(0xFFFFFFFFu, c_cand, d); c_hits += __shfl_down_sync(0xFFFFFFFFu, c_hits, d); }
+	if ((threadIdx.x & 31) == 0) {
+		if (c_cand) atomicAdd(A.ctr + CTR_CANDIDATES, (u64)c_cand);
+		if (MODE == MODE_CONTAIN && c_hits) atomicAdd(A.ctr + CTR_CONTAIN_HITS, (u64)c_hits);
+	}
+}
+
+// Node records start<<24|deg from the scanned degrees (pos = exclusive scan over the shard), plus the
+// statistics E_pre / largest degree.
+__global__ void __launch_bounds__(256) k_nodes(const u32 *__restrict__ deg, const u64 *__restrict__ pos, u64 *__restrict__ nodes,
+                                               u32 *__restrict__ fill, u32 lo, u32 hi, u32 cap, u64 *ctr)
+{
+	const u32 u = lo + blockIdx.x * blockDim.x + threadIdx.x;
+	const u32 d = u < hi ? deg[u] : 0;
+	if (u < hi) { nodes[u] = d ? ((pos[u - lo] << OGB_DEG_BITS) | d) : 0; fill[u - lo] = cap; }
+	u32 mx = d;
+	for (int k = 16; k > 0; k >>= 1) mx = max(mx, __shfl_down_sync(0xFFFFFFFFu, mx, k));
+	if ((threadIdx.x & 31) == 0 && mx) atomicMax(ctr + CTR_MAX_DEGREE, (u64)mx);
+}
+
+// Spilled edges of heavy nodes (degree > cap) go straight to their final range, behind the first
+// `cap` edges that k_sort_nodes copies from the slot region.
+__global__ void __launch_bounds__(256) k_place_overflow(const u32 *__restrict__ ov_q, const u64 *__restrict__ ov_e, u64 n_over,
+                                                        const u64 *__restrict__ nodes, u64 *__restrict__ edges, u32 *__restrict__ fill, u32 lo)
+{
+	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_over) return;
+	const u32 u = ov_q[i];
+	const u64 nd = nodes[u];
+	const u32 p = atomicAdd(fill + (u - lo), 1u);
+	if (p < (u32)(nd & OGB_DEG_MASK)) edges[(nd >> OGB_DEG_BITS) + p] = ov_e[i];
 }
 
 // In-place ascending bitonic sort of n u64 keys in shared memory by one warp (n <= cap, cap a power
@@ -395,223 +656,74 @@ __device__ __forceinline__ u64 warp_sort32(u64 v, u32 lane)
 	return v;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(OGB_WARPS * 32, OGB_SCAN_BLOCKS) k_scan(ScanArgs A)
+// Per-node sort by (offset, dst, orient) = integer order of the edge word (OverlapGraph.cpp:563 plus
+// the deterministic tie-break of SURVEY.md App. B.1), fused with the move from the slot staging
+// area to the dense adjacency array. One warp per node: shuffles up to 32 edges, shared memory up to
+// OGB_EC; larger nodes are copied unsorted and listed for k_sort_big.
+__global__ void __launch_bounds__(OGB_WARPS * 32) k_sort_nodes(const u64 *__restrict__ nodes, const u64 *__restrict__ slots_e, u64 *__restrict__ edges,
+                                                               u32 lo, u32 hi, u32 cap, u32 *__restrict__ big_list, u32 big_cap, u64 *ctr)
 {
-	__shared__ u64 s_hq[OGB_WARPS][OGB_HQ];
-	__shared__ u64 s_edges[MODE == MODE_OVERLAP ? OGB_WARPS : 1][MODE == MODE_OVERLAP ? OGB_EC : 1];
-	__shared__ u64 s_read[OGB_WARPS][OGB_STAGE_WORDS + 4];
+	__shared__ u64 s_buf[OGB_WARPS][OGB_EC];
 	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const u32 gw = blockIdx.x * OGB_WARPS + wib, nwarps = gridDim.x * OGB_WARPS;
-	u64 *hq = s_hq[wib];
-	u64 *eb = s_edges[MODE == MODE_OVERLAP ? wib : 0];
-	const u32 h = A.T.h;
-	u64 c_probes = 0, c_sectors = 0, c_cand = 0, c_hits = 0;
-	u32 c_maxdeg = 0;
-
-	for (u32 qi = A.lo + gw; qi < A.hi; qi += nwarps) {
-		if (MODE == MODE_OVERLAP && A.contained && ((__ldg(A.contained + (qi >> 5)) >> (qi & 31)) & 1)) {
-			if (lane == 0) A.nodes[qi] = 0;                                  // contained reads have no edges (:548)
-			continue;
-		}
-		u64 off; u32 L1;
-		read_geom(A.R, qi, off, L1);
-		if (L1 > OGB_STAGE_WORDS * 32) {                                     // very long read: slow path
+	for (u32 u = lo + gw; u < hi; u += nwarps) {
+		const u64 nd = __ldg(nodes + u);
+		const u32 n = (u32)(nd & OGB_DEG_MASK);
+		if (n == 0) continue;
+		const u64 *src = slots_e + (u64)(u - lo) * cap;
+		u64 *dst = edges + (nd >> OGB_DEG_BITS);
+		const u32 ns = n < cap ? n : cap;                                    // edges still in the slot region
+		if (n <= 32 && n <= cap) {
+			u64 v = lane < n ? src[lane] : ~0ull;
+			v = warp_sort32(v, lane);
+			if (lane < n) dst[lane] = v;
+		} else if (n <= OGB_EC) {
+			u64 *buf = s_buf[wib];
+			for (u32 i = lane; i < ns; i += 32) buf[i] = src[i];
+			for (u32 i = ns + lane; i < n; i += 32) buf[i] = dst[i];         // spilled part, already placed
+			warp_sort(buf, n, lane);
+			for (u32 i = lane; i < n; i += 32) dst[i] = buf[i];
+			__syncwarp();
+		} else {
+			for (u32 i = lane; i < ns; i += 32) dst[i] = src[i];
 			if (lane == 0) {
-				u64 pos = atomicAdd(A.ctr + CTR_OVERFLOW, 1ull);
-				if (pos < A.overflow_cap) A.overflow_list[pos] = qi;
-				if (MODE == MODE_OVERLAP) A.nodes[qi] = OGB_NODE_OVERFLOW;
-			}
-			continue;
-		}
-		// stage the query strand (+2 words of slack for the window extraction) in shared memory
-		u64 *s = s_read[wib];
-		{
-			const u32 nw = (L1 + 31) >> 5;
-			__syncwarp();
-			for (u32 i = lane; i < nw + 3; i += 32) s[i] = i < nw ? __ldg(A.R.words + off + i) : 0;
-			__syncwarp();
-		}
-		const u32 nwin = L1 - h - 1;                                         // j = 1 .. L1-h-1 (:534)
-		u32 qn = 0;        // queued candidates (warp-uniform)
-		u32 en = 0;        // buffered edges (warp-uniform); keeps counting past OGB_EC
-		c_probes += nwin;
-
-		// ---- phase B: each lane verifies one queued candidate (taken from the tail of the queue)
-		auto verify_batch = [&]() {
-			u32 take = qn < 32 ? qn : 32;
-			u32 base = qn - take;
-			u64 e0 = 0, e1 = 0; int ne = 0;
-			if (lane < take) {
-				u64 c = hq[base + lane];
-				ne = verify_candidate<MODE, LdShared>(A, s, qi, L1, (u32)(c >> 32), (u32)c, e0, e1);
-				c_cand++;
-			}
-			qn = base;
-			if (MODE == MODE_OVERLAP) {
-				u32 b0 = __ballot_sync(0xFFFFFFFFu, ne >= 1), b1 = __ballot_sync(0xFFFFFFFFu, ne >= 2);
-				u32 p0 = en + __popc(b0 & ((1u << lane) - 1));
-				if (ne >= 1 && p0 < OGB_EC) eb[p0] = e0;
-				en += __popc(b0);
-				u32 p1 = en + __popc(b1 & ((1u << lane) - 1));
-				if (ne >= 2 && p1 < OGB_EC) eb[p1] = e1;
-				en += __popc(b1);
-			} else {
-				c_hits += ne;
-			}
-			__syncwarp();
-		};
-
-		for (u32 jb = 1; jb <= nwin; jb += 32) {
-			// ---- phase A: one window per lane
-			u32 j = jb + lane;
-			bool active = j <= nwin;
-			u64 hash = 0; u32 b = 0;
-			if (active) { hash = key_hash<LdShared>(s, j, h); b = bucket_of(hash, A.T.nb); }
-			const u32 fp = hash_fp(hash);
-			while (__any_sync(0xFFFFFFFFu, active)) {
-				u64 sl[OGB_SLOTS];
-				u32 mm = 0;                                                  // slots of this lane's bucket whose fingerprint matches
-				if (active) {
-					load_bucket(A.T.slots, b, sl);
-					c_sectors++;
-					#pragma unroll
-					for (int k = 0; k < OGB_SLOTS; k++) mm |= ((u32)(sl[k] >> 32) == fp) << k;
-					// K1 fills a bucket front to back, so "last slot taken" = full = the key may continue in the next bucket
-					active = sl[OGB_SLOTS - 1] != 0;
-					if (active) b = (b + 1 == A.T.nb) ? 0 : b + 1;
-				}
-				// queue the matches: one ballot per round; a second match in the same bucket is rare
-				u32 bal;
-				while ((bal = __ballot_sync(0xFFFFFFFFu, mm != 0)) != 0) {
-					if (mm) {
-						int k = __ffs(mm) - 1;
-						u64 v = sl[0];
-						#pragma unroll
-						for (int q = 1; q < OGB_SLOTS; q++) v = (k == q) ? sl[q] : v;
-						hq[qn + __popc(bal & ((1u << lane) - 1))] = ((u64)j << 32) | (u32)v;
-						mm &= mm - 1;
-					}
-					qn += __popc(bal);
-				}
-				__syncwarp();
-				while (qn >= 32) verify_batch();                             // keeps room for 32 lanes x 8 slots
+				const u64 p = atomicAdd(ctr + CTR_BIG_NODES, 1ull);
+				if (p < big_cap) big_list[p] = u;
 			}
 		}
-		while (qn > 0) verify_batch();
-
-		if (MODE == MODE_OVERLAP) {
-			// ---- phase C
-			if (en > c_maxdeg) c_maxdeg = en;
-			if (en == 0) { if (lane == 0) A.nodes[qi] = 0; }
-			else if (en <= OGB_EC) {
-				u64 mine = ~0ull;
-				if (en <= 32) { if (lane < en) mine = eb[lane]; mine = warp_sort32(mine, lane); }
-				else warp_sort(eb, en, lane);
-				u64 start = 0;
-				if (lane == 0) start = atomicAdd(A.ctr + CTR_EDGE_CURSOR, (u64)en);
-				start = __shfl_sync(0xFFFFFFFFu, start, 0);
-				if (start + en <= A.edge_cap) {
-					if (en <= 32) { if (lane < en) A.edges[start + lane] = mine; }
-					else for (u32 t = lane; t < en; t += 32) A.edges[start + t] = eb[t];
-				} else if (lane == 0) atomicAdd(A.ctr + CTR_EDGES_DROPPED, (u64)en);
-				if (lane == 0) A.nodes[qi] = (start << OGB_DEG_BITS) | en;
-				__syncwarp();
-			} else if (lane == 0) {
-				u64 pos = atomicAdd(A.ctr + CTR_OVERFLOW, 1ull);
-				if (pos < A.overflow_cap) A.overflow_list[pos] = qi;
-				A.nodes[qi] = OGB_NODE_OVERFLOW;
-			}
-		}
-	}
-	// per-warp counters -> global (one atomic per warp per counter)
-	for (int d = 16; d > 0; d >>= 1) {
-		c_sectors += __shfl_down_sync(0xFFFFFFFFu, c_sectors, d);
-		c_cand += __shfl_down_sync(0xFFFFFFFFu, c_cand, d);
-		c_hits += __shfl_down_sync(0xFFFFFFFFu, c_hits, d);
-	}
-	if (lane == 0) {
-		atomicAdd(A.ctr + CTR_PROBES, c_probes);
-		atomicAdd(A.ctr + CTR_SECTORS, c_sectors);
-		atomicAdd(A.ctr + CTR_CANDIDATES, c_cand);
-		if (MODE == MODE_CONTAIN) atomicAdd(A.ctr + CTR_CONTAIN_HITS, c_hits);
-		else atomicMax(A.ctr + CTR_MAX_DEGREE, (u64)c_maxdeg);
 	}
 }
 
-// Slow path for reads with more than OGB_EC edges (repeats): one block per queued read, two
-// passes over its windows. Pass 0 counts, then a global range is claimed, pass 1 stores, and the
-// block sorts the range in global memory (bitonic). Simple on purpose: it only ever sees a handful
-// of reads.
-__global__ void __launch_bounds__(256) k_scan_big(ScanArgs A, u32 n_over)
+// Nodes with more than OGB_EC edges (repeats): one block per node, bitonic sort in global memory
+// through a power-of-two scratch range.
+__global__ void __launch_bounds__(256) k_sort_big(const u64 *__restrict__ nodes, u64 *__restrict__ edges, const u32 *__restrict__ big_list, u32 n_big,
+                                                  u64 *__restrict__ scratch, u64 scratch_cap, u64 *ctr)
 {
-	__shared__ u32 s_count;
-	__shared__ u64 s_start;
-	const u32 h = A.T.h;
-	for (u32 it = blockIdx.x; it < n_over; it += gridDim.x) {
-		u32 qi = A.overflow_list[it];
-		u64 off; u32 L1;
-		read_geom(A.R, qi, off, L1);
-		const u64 *s = A.R.words + off;
-		const u32 nwin = L1 - h - 1;
-		for (int pass = 0; pass < 2; pass++) {
-			if (threadIdx.x == 0) s_count = 0;
-			__syncthreads();
-			for (u32 j = 1 + threadIdx.x; j <= nwin; j += blockDim.x) {
-				u64 hash = key_hash<LdGlobal>(s, j, h);
-				u32 fp = hash_fp(hash), b = bucket_of(hash, A.T.nb);
-				for (;;) {
-					u64 sl[OGB_SLOTS];
-					load_bucket(A.T.slots, b, sl);
-					bool full = true;
-					for (int k = 0; k < OGB_SLOTS; k++) {
-						if (sl[k] == 0) { full = false; continue; }
-						if ((u32)(sl[k] >> 32) != fp) continue;
-						u64 e0 = 0, e1 = 0;
-						int ne = verify_candidate<MODE_OVERLAP, LdGlobal>(A, s, qi, L1, j, (u32)sl[k], e0, e1);
-						if (ne) {
-							u32 pos = atomicAdd(&s_count, (u32)ne);
-							if (pass == 1 && s_start + pos + ne <= A.edge_cap) {
-								A.edges[s_start + pos] = e0;
-								if (ne == 2) A.edges[s_start + pos + 1] = e1;
-							}
-						}
-					}
-					if (!full) break;
-					b = (b + 1 == A.T.nb) ? 0 : b + 1;
-				}
-			}
-			__syncthreads();
-			if (pass == 0) {
-				if (threadIdx.x == 0) {
-					u32 m = 1; while (m < s_count) m <<= 1;                  // padded to a power of two for the sort
-					s_start = atomicAdd(A.ctr + CTR_EDGE_CURSOR, (u64)m);
-					atomicAdd(A.ctr + CTR_PAD, (u64)(m - s_count));          // padding is not an edge
-					atomicMax(A.ctr + CTR_MAX_DEGREE, (u64)s_count);
+	__shared__ u64 s_base;
+	for (u32 it = blockIdx.x; it < n_big; it += gridDim.x) {
+		const u64 nd = nodes[big_list[it]];
+		const u32 n = (u32)(nd & OGB_DEG_MASK);
+		u64 *a = edges + (nd >> OGB_DEG_BITS);
+		u32 m = 1;
+		while (m < n) m <<= 1;
+		__syncthreads();
+		if (threadIdx.x == 0) s_base = atomicAdd(ctr + CTR_SCRATCH_CURSOR, (u64)m);
+		__syncthreads();
+		if (s_base + m > scratch_cap) { if (threadIdx.x == 0) atomicAdd(ctr + CTR_SCRATCH_FAIL, 1ull); continue; }
+		u64 *buf = scratch + s_base;
+		for (u32 i = threadIdx.x; i < m; i += blockDim.x) buf[i] = i < n ? a[i] : ~0ull;
+		__syncthreads();
+		for (u32 k = 2; k <= m; k <<= 1)
+			for (u32 jj = k >> 1; jj > 0; jj >>= 1) {
+				for (u32 t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+					u32 i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1)), l = i | jj;
+					bool up = (i & k) == 0;
+					u64 x = buf[i], y = buf[l];
+					if ((x > y) == up) { buf[i] = y; buf[l] = x; }
 				}
 				__syncthreads();
 			}
-		}
-		u32 n = s_count, m = 1;
-		while (m < n) m <<= 1;
-		u64 start = s_start;
-		if (start + m <= A.edge_cap) {
-			u64 *buf = A.edges + start;
-			for (u32 i = n + threadIdx.x; i < m; i += blockDim.x) buf[i] = ~0ull;
-			__syncthreads();
-			for (u32 k = 2; k <= m; k <<= 1)
-				for (u32 jj = k >> 1; jj > 0; jj >>= 1) {
-					for (u32 t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
-						u32 i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1)), l = i | jj;
-						bool up = (i & k) == 0;
-						u64 x = buf[i], y = buf[l];
-						if ((x > y) == up) { buf[i] = y; buf[l] = x; }
-					}
-					__syncthreads();
-				}
-		} else if (threadIdx.x == 0) atomicAdd(A.ctr + CTR_EDGES_DROPPED, (u64)n);
-		if (threadIdx.x == 0) A.nodes[qi] = (start << OGB_DEG_BITS) | n;
-		__syncthreads();
+		for (u32 i = threadIdx.x; i < n; i += blockDim.x) a[i] = buf[i];
 	}
 }
 
@@ -744,10 +856,10 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 // ------------------------------------------------------------------------------------------------
 // K6: an edge (u,w) survives iff it was not flagged by u's marking and its twin was not flagged by
 // w's marking (:605-606, :623-661). Marks are per destination NODE, so w's verdict on u is read off
-// any (w,u) entry of w's adjacency -- no twin pointers are needed. One warp per node: the few edges
-// that u itself kept (~2) are checked one after another, each by a warp-wide scan of w's adjacency;
-// survivors are written compacted to surv[start .. start+cnt) as final records, so that the copy
-// kernel after the scan touches survivors only.
+// any (w,u) entry of w's adjacency -- no twin pointers are needed. One warp per node, one lane per
+// edge: the few edges that u itself kept (~2) look up w's verdict concurrently; survivors are
+// written compacted to surv[start .. start+cnt) as final records, so that the copy kernel after
+// the scan touches survivors only.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(OGB_WARPS * 32) k_twin_keep(const u64 *__restrict__ nodes, const u64 *__restrict__ edges,
                                                               const unsigned char *__restrict__ eflag, ogb_edge *__restrict__ surv,
@@ -762,44 +874,40 @@ __global__ void __launch_bounds__(OGB_WARPS * 32) k_twin_keep(const u64 *__restr
 		u64 start = nd >> OGB_DEG_BITS;
 		u32 total = 0;
 		for (u32 kb = 0; kb < deg; kb += 32) {
-			u32 k = kb + lane;
-			u64 e = 0, ndw = 0;
-			bool mine = k < deg && !eflag[start + k];
-			if (mine) { e = __ldg(edges + start + k); ndw = __ldg(nodes + (edge_dst(e) - 1)); }   // all twin nodes fetched together
-			u32 todo = __ballot_sync(0xFFFFFFFFu, mine);
-			while (todo) {
-				int src = __ffs(todo) - 1;
-				todo &= todo - 1;
-				u64 ee = __shfl_sync(0xFFFFFFFFu, e, src), nw = __shfl_sync(0xFFFFFFFFu, ndw, src);
-				u32 degw = (u32)(nw & OGB_DEG_MASK);
-				u64 startw = nw >> OGB_DEG_BITS;
-				int verdict = -1;                                            // -1 not found, 0 keep, 1 twin flagged
-				for (u32 xb = 0; xb < degw && verdict < 0; xb += 32) {
-					u32 x = xb + lane;
-					bool hit = x < degw && edge_dst(__ldg(edges + startw + x)) == u + 1;
-					u32 hm = __ballot_sync(0xFFFFFFFFu, hit);
-					if (hm) {
-						int hl = __ffs(hm) - 1;
-						int f = 0;
-						if ((int)lane == hl) f = eflag[startw + x];
-						verdict = __shfl_sync(0xFFFFFFFFu, f, hl);
-					}
+			const u32 k = kb + lane;
+			bool keep = k < deg && !eflag[start + k];
+			u64 e = 0;
+			if (keep) {
+				// every lane that still holds an edge looks its twin up on its own: the (few) lookups of a
+				// node run concurrently, each as batches of four independent loads
+				e = __ldg(edges + start + k);
+				const u64 ndw = __ldg(nodes + (edge_dst(e) - 1));
+				const u32 degw = (u32)(ndw & OGB_DEG_MASK);
+				const u64 *aw = edges + (ndw >> OGB_DEG_BITS);
+				const unsigned char *fw = eflag + (ndw >> OGB_DEG_BITS);
+				int at = -1;
+				for (u32 x = 0; x < degw && at < 0; x += 4) {
+					u64 f[4];
+					#pragma unroll
+					for (int q = 0; q < 4; q++) f[q] = x + q < degw ? __ldg(aw + x + q) : 0;
+					#pragma unroll
+					for (int q = 3; q >= 0; q--) if (edge_dst(f[q]) == u + 1) at = (int)x + q;
 				}
-				if (verdict < 0) { c_asym++; verdict = 0; }
-				if (verdict == 0) {
-					if (lane == 0) {
-						ogb_edge r;
-						r.src = u + 1; r.dst = edge_dst(ee); r.offset = (uint16_t)edge_offset(ee); r.orient = (uint8_t)edge_orient(ee); r.reserved = 0;
-						surv[start + total] = r;
-					}
-					total++;
-				}
+				if (at < 0) c_asym++;
+				else keep = fw[at] == 0;
 			}
+			const u32 bal = __ballot_sync(0xFFFFFFFFu, keep);
+			if (keep) {
+				ogb_edge r;
+				r.src = u + 1; r.dst = edge_dst(e); r.offset = (uint16_t)edge_offset(e); r.orient = (uint8_t)edge_orient(e); r.reserved = 0;
+				surv[start + total + __popc(bal & ((1u << lane) - 1))] = r;
+			}
+			total += __popc(bal);
 		}
 		if (lane == 0) { cnt[u] = total; c_nodes += total > 0; }
 	}
 	if (lane == 0 && c_nodes) atomicAdd(ctr + CTR_NODES_FINAL, (u64)c_nodes);
-	if (lane == 0 && c_asym) atomicAdd(ctr + CTR_ASYMMETRIC, (u64)c_asym);
+	if (c_asym) atomicAdd(ctr + CTR_ASYMMETRIC, (u64)c_asym);
 }
 
 // Exclusive scan of u32 counts into u64 offsets: (1) per-block sums, (2) one block scans the sums,
@@ -908,13 +1016,10 @@ __global__ void k_lookup(ReadStore R, Table T, const u64 *__restrict__ keys, u32
 	u64 hash = key_hash<LdGlobal>(key, 0, T.h);
 	u32 fp = hash_fp(hash), b = bucket_of(hash, T.nb), c = 0;
 	for (;;) {
-		u64 sl[OGB_SLOTS];
-		load_bucket(T.slots, b, sl);
-		bool full = true;
-		for (int s = 0; s < OGB_SLOTS; s++) {
-			if (sl[s] == 0) { full = false; continue; }
-			if ((u32)(sl[s] >> 32) != fp) continue;
-			u32 val = (u32)sl[s], ri = (val >> 2) - 1, o = val & 3;
+		u32 w[OGB_BWORDS];
+		load_bucket(T.slots, b, w);
+		for (u32 mm = match_bucket(w, fp); mm; mm &= mm - 1) {
+			u32 val = bucket_value(w, __ffs(mm) - 1), ri = (val >> 2) - 1, o = val & 3;
 			u64 off; u32 L;
 			read_geom(R, ri, off, L);
 			const u64 *t = R.words + off + (o >> 1) * padded_words(L);
@@ -922,7 +1027,7 @@ __global__ void k_lookup(ReadStore R, Table T, const u64 *__restrict__ keys, u32
 			if (pass == 1) out[pos[k] + c] = (u64)(ri + 1) | ((u64)o << 62);
 			c++;
 		}
-		if (!full) break;
+		if (w[5 + OGB_SLOTS - 1] == 0) break;
 		b = (b + 1 == T.nb) ? 0 : b + 1;
 	}
 	if (pass == 0) cnt[k] = c;

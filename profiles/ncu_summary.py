@@ -38,12 +38,12 @@ def source(rep, kernel, top, path):
             continue
         hdr = rows[a + 2]
         ci, si = hdr.index('Instructions Executed'), hdr.index('# Samples')
-        agg = collections.OrderedDict()
+        agg = collections.OrderedDict(); text = {}
         for r in rows[a + 3:b]:
             if r[0] == '':
                 continue
             try:
-                agg[int(r[0])] = (int(r[ci]), int(r[si]))
+                agg[int(r[0])] = (int(r[ci]), int(r[si])); text[int(r[0])] = r[1]
             except ValueError:
                 pass
         tot = sum(v[0] for v in agg.values()); tots = sum(v[1] for v in agg.values())
@@ -51,7 +51,7 @@ def source(rep, kernel, top, path):
             continue
         print(rows[a + 1][1][:60], 'instructions', tot, 'samples', tots)
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-            print(f"{v[0] / tot * 100:5.1f}% inst {v[1] / max(tots, 1) * 100:5.1f}% smp  L{k:>4} {src[k - 1].strip()[:110]}")
+            print(f"{v[0] / tot * 100:5.1f}% inst {v[1] / max(tots, 1) * 100:5.1f}% smp  L{k:>4} {text.get(k, '').strip()[:110]}")
 
 
 if __name__ == '__main__':

@@ -6,3 +6,4 @@ for l in sys.stdin:
         d=json.loads(l); print('ms/step',round(d['ms_per_step'],3),'e2e',round(d['e2e']['ms_per_step'],3),'phases',{k:round(v,3) for k,v in d['phases_ms'].items()},'k3',round(d['roofline']['kernel_ms'],3),'frac',round(d['roofline']['frac'],3),'sectors/probe',round(d['stats']['probe_sectors']/d['stats']['overlap_probes'],3))
     else: print(l.strip()[:300])
 "
+bash profiles/launches.sh 2>&1 | tail -16
