@@ -88,6 +88,8 @@ enum { EV_BEGIN = 0, EV_PACK0, EV_PACK1, EV_HASH0, EV_HASH1, EV_CONT0, EV_CONT1,
 struct ogb_context {
 	int device = 0, rank = 0, nranks = 1, sm_count = 148;
 	cudaStream_t stream = nullptr;
+	cudaStream_t stream2 = nullptr;   // verify kernels run here, overlapping the next chunk's probe
+	cudaEvent_t ev_probe[2] = {}, ev_verify[2] = {};
 	ncclComm_t comm = nullptr;
 	cudaEvent_t ev[EV_COUNT] = {};
 	// packed reads
@@ -111,9 +113,10 @@ struct ogb_context {
 	Pool<u32> cnt, scratch_keys;
 	Pool<ogb_edge> fin, pre, surv;
 	// scan staging: candidate queue of one chunk, per-read slot regions, spill list of heavy nodes
-	Pool<u32> cand_q, deg, fill, ov_q, big_list;
+	Pool<u32> cand_q, deg, fill, ov_q, big_list;   // cand_q / cand_v hold two ping-pong queues of cand_cap entries
 	Pool<u64> cand_v, slots_e, ov_e, sort_scratch;
-	u64 *d_cursor = nullptr;         // candidate-queue cursor
+	u64 cand_cap = 0;
+	u64 *d_cursor = nullptr;         // the two candidate-queue cursors
 	u32 slot_cap = 64;               // slots per read (adapted to the largest degree seen)
 	u32 chunk_reads = 1u << 16;      // query reads per probe/verify launch pair
 	Pool<char> flush;
@@ -178,7 +181,9 @@ static int context_create_common(ogb_context **out, int device)
 	for (int i = 0; i < EV_COUNT; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
 	CUDA_TRY(cudaMalloc((void **)&c->d_ctr, CTR_COUNT * sizeof(u64)));
 	CUDA_TRY(cudaMalloc((void **)&c->d_tot, 2 * sizeof(u64)));
-	CUDA_TRY(cudaMalloc((void **)&c->d_cursor, sizeof(u64)));
+	CUDA_TRY(cudaMalloc((void **)&c->d_cursor, 2 * sizeof(u64)));
+	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; i++) { CUDA_TRY(cudaEventCreateWithFlags(&c->ev_probe[i], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&c->ev_verify[i], cudaEventDisableTiming)); }
 	CUDA_TRY(cudaMemset(c->d_tot, 0, 2 * sizeof(u64)));
 	CUDA_TRY(cudaMallocHost((void **)&c->h_ctr, CTR_COUNT * sizeof(u64)));
 	CUDA_TRY(cudaMemset(c->d_ctr, 0, CTR_COUNT * sizeof(u64)));
@@ -219,6 +224,7 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
+	if (c->stream2) cudaStreamSynchronize(c->stream2);
 	if (c->comm) g_nccl.CommDestroy(c->comm);
 	c->words.release(); c->meta.release(); c->stage_bytes.release(); c->stage_offs.release(); c->stage_lens.release();
 	c->slots.release(); c->sup.release(); c->contained.release(); c->nodes.release(); c->edges.release(); c->pos.release();
@@ -231,6 +237,8 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	c->cand_v.release(); c->slots_e.release(); c->ov_e.release(); c->sort_scratch.release();
 	if (c->h_ctr) cudaFreeHost(c->h_ctr);
 	for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	for (int i = 0; i < 2; i++) { if (c->ev_probe[i]) cudaEventDestroy(c->ev_probe[i]); if (c->ev_verify[i]) cudaEventDestroy(c->ev_verify[i]); }
+	if (c->stream2) cudaStreamDestroy(c->stream2);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -483,29 +491,38 @@ static ScanArgs scan_args(ogb_context *c, u32 lo, u32 hi)
 	ScanArgs a;
 	a.R = c->rs(); a.T = c->tb(); a.lo = lo; a.hi = hi;
 	a.contained = c->any_contained ? c->contained.p : nullptr;
-	a.cand_q = c->cand_q.p; a.cand_v = c->cand_v.p; a.cand_cap = c->cand_q.cap; a.cand_cursor = c->d_cursor;
+	a.cand_q = c->cand_q.p; a.cand_v = c->cand_v.p; a.cand_cap = c->cand_cap; a.cand_cursor = c->d_cursor;
 	a.sup = c->sup.p; a.slots_e = c->slots_e.p; a.slot_lo = lo; a.cap = c->slot_cap; a.deg = c->deg.p;
 	a.ov_q = c->ov_q.p; a.ov_e = c->ov_e.p; a.ov_cap = c->ov_q.cap; a.ctr = c->d_ctr;
 	return a;
 }
 
 // k_probe + k_verify over [lo,hi) in chunks of c->chunk_reads reads, so that the candidate queue of a
-// chunk stays L2-resident. Nothing here synchronises with the host.
+// chunk (and the partner strands its probe prefetched) stay L2-resident. The probe of chunk i+1 runs
+// on the main stream while the verify of chunk i runs on stream2 (ping-pong queues): the former is
+// issue-bound, the latter latency-bound, so they share the SMs well and the launch tails overlap.
+// Nothing here synchronises with the host.
 template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 {
 	{
 		const char *e = getenv("OGB_CHUNK_READS");                           // experiment knob
-		if (e && atoll(e) >= 256) c->chunk_reads = (u32)std::min<long long>(atoll(e), 1ll << 30);
-		u64 want = e && atoll(e) > (1 << 16) ? 64ull << 20 : 8ull << 20;
-		if (c->cand_q.cap < want) { OGB_TRY(c->cand_q.ensure(want)); OGB_TRY(c->cand_v.ensure(want)); }
+		if (e && atoll(e) >= 256) c->chunk_reads = (u32)std::min<long long>(atoll(e), 1ll << 16);
+		const u64 want = 8ull << 20;
+		if (c->cand_cap < want) { OGB_TRY(c->cand_q.ensure(2 * want)); OGB_TRY(c->cand_v.ensure(2 * want)); c->cand_cap = want; }
 	}
+	if (c->chunk_reads > (1u << 16)) c->chunk_reads = 1u << 16;             // k_probe_uniform indexes windows with 32 bits
 	const int gp = grid_for(c, (const void *)k_probe<MODE>, 256), gv = grid_for(c, (const void *)k_verify<MODE>, 256);
 	const int gu = grid_for(c, (const void *)k_probe_uniform<MODE>, 256);
-	if (c->chunk_reads > (1u << 16)) c->chunk_reads = 1u << 16;             // k_probe_uniform indexes windows with 32 bits
+	const bool overlap_streams = getenv("OGB_ONE_STREAM") == nullptr;
+	cudaStream_t sv = overlap_streams ? c->stream2 : c->stream;
 	ScanArgs a = scan_args(c, lo, hi);
-	for (u32 b0 = lo; b0 < hi; b0 += c->chunk_reads) {
-		a.lo = b0; a.hi = std::min<u64>(hi, (u64)b0 + c->chunk_reads);
-		CUDA_TRY(cudaMemsetAsync(c->d_cursor, 0, sizeof(u64), c->stream));
+	u32 i = 0;
+	for (u32 b0 = lo; b0 < hi; b0 += c->chunk_reads, i++) {
+		const int q = i & 1;
+		a.lo = b0; a.hi = (u32)std::min<u64>(hi, (u64)b0 + c->chunk_reads);
+		a.cand_q = c->cand_q.p + q * c->cand_cap; a.cand_v = c->cand_v.p + q * c->cand_cap; a.cand_cursor = c->d_cursor + q;
+		if (overlap_streams && i >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_verify[q], 0));   // queue q is free again
+		CUDA_TRY(cudaMemsetAsync(a.cand_cursor, 0, sizeof(u64), c->stream));
 		const u32 warps = a.hi - a.lo;
 		if (c->uniform_len && !a.contained) {
 			const u32 nwin = c->uniform_len - c->h - 1;
@@ -513,9 +530,16 @@ template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 			k_probe_uniform<MODE><<<(unsigned)std::min<u64>(gu, (rounds * 32 + 255) / 256), 256, 0, c->stream>>>(a, nwin, ~0ull / nwin + 1);
 		} else
 			k_probe<MODE><<<(unsigned)std::min<u64>(gp, ((u64)warps * 32 + 255) / 256), 256, 0, c->stream>>>(a);
-		k_verify<MODE><<<gv, 256, 0, c->stream>>>(a);
+		if (overlap_streams) {
+			CUDA_TRY(cudaEventRecord(c->ev_probe[q], c->stream));
+			CUDA_TRY(cudaStreamWaitEvent(sv, c->ev_probe[q], 0));
+		}
+		k_verify<MODE><<<gv, 256, 0, sv>>>(a);
+		if (overlap_streams) CUDA_TRY(cudaEventRecord(c->ev_verify[q], sv));
 		c->launches += 2;
 	}
+	if (overlap_streams)                                                     // the main stream continues after every verify
+		for (int q = 0; q < 2 && q < (int)i; q++) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_verify[q], 0));
 	CUDA_TRY(cudaGetLastError());
 	return OGB_OK;
 }
@@ -544,7 +568,7 @@ extern "C" int ogb_mark_contained(ogb_context *c)
 		c->any_contained = saved;
 		OGB_TRY(rc);
 		OGB_TRY(ctr_fetch(c));
-		if (c->h_ctr[CTR_CAND_MAX] > c->cand_q.cap) { c->chunk_reads = std::max<u32>(256, c->chunk_reads / 2); continue; }
+		if (c->h_ctr[CTR_CAND_MAX] > c->cand_cap) { c->chunk_reads = std::max<u32>(256, c->chunk_reads / 2); continue; }
 		break;
 	}
 	c->st.contain_probes = c->h_ctr[CTR_PROBES];
@@ -650,7 +674,7 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		if (nloc) { k_nodes<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->deg.p, c->pos.p, c->nodes.p, c->fill.p, lo, hi, c->slot_cap, c->d_ctr); c->launches++; }
 		CUDA_TRY(cudaMemcpyAsync(&local_edges, c->d_tot, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 		OGB_TRY(ctr_fetch(c));
-		if (c->h_ctr[CTR_CAND_MAX] > c->cand_q.cap) { c->chunk_reads = std::max<u32>(256, c->chunk_reads / 2); continue; }
+		if (c->h_ctr[CTR_CAND_MAX] > c->cand_cap) { c->chunk_reads = std::max<u32>(256, c->chunk_reads / 2); continue; }
 		const u64 n_over = c->h_ctr[CTR_OVERFLOW];
 		if (n_over > c->ov_q.cap) {                                          // many heavy nodes: more slots per read, bigger spill list
 			if (c->slot_cap < 256) c->slot_cap *= 2;

@@ -327,22 +327,21 @@ __device__ __forceinline__ void load_bucket(const u32 *__restrict__ slots, u32 b
 	for (int i = 0; i < 8; i++) { w[2 * i] = (u32)x[i]; w[2 * i + 1] = (u32)(x[i] >> 32); }
 }
 
-// Ten-bit mask of the slots whose 16-bit fingerprint equals fp (fp != 0, so empty slots never match).
-// Fast reject with the zero-halfword trick on w ^ splat (3 ALU ops per word pair); the exact mask is
-// only built when some halfword may match.
+// Ten-bit mask of the slots whose 16-bit fingerprint equals fp, by the zero-halfword trick on
+// w ^ splat: z has bit 15 / 31 set where the low / high halfword is zero. The high bit can also come
+// out set when the low half matched and the high half differs only in its lowest bit -- a spurious
+// candidate (about 1 in 10^5 matches) that verification rejects like any fingerprint collision;
+// consumers skip a spurious hit on an empty slot (value 0).
 __device__ __forceinline__ u32 match_bucket(const u32 (&w)[OGB_BWORDS], u32 fp)
 {
 	const u32 splat = fp | (fp << 16);
-	u32 any = 0;
+	u32 z[5], any = 0;
 	#pragma unroll
-	for (int i = 0; i < 5; i++) { const u32 x = w[i] ^ splat; any |= (x - 0x00010001u) & ~x & 0x80008000u; }
+	for (int i = 0; i < 5; i++) { const u32 x = w[i] ^ splat; z[i] = (x - 0x00010001u) & ~x & 0x80008000u; any |= z[i]; }
 	if (any == 0) return 0;
 	u32 mm = 0;
 	#pragma unroll
-	for (int i = 0; i < 5; i++) {
-		const u32 x = w[i] ^ splat;
-		mm |= (((x & 0xFFFFu) == 0) | (((x >> 16) == 0) << 1)) << (2 * i);
-	}
+	for (int i = 0; i < 5; i++) mm |= (((z[i] >> 15) & 1) | ((z[i] >> 30) & 2)) << (2 * i);
 	return mm;
 }
 // value of slot k (0..9)
@@ -401,30 +400,53 @@ struct ScanArgs {
 	u64 *ctr;
 };
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// A warp's position in the candidate queue: it owns [qbase, qbase+qsize) and has used qused of it.
+struct QueueCursor { u64 qbase; u32 qused, qsize; };
+
+__device__ __forceinline__ void queue_pad(const ScanArgs &A, const QueueCursor &Q, u32 lane)
+{
+	for (u32 i = Q.qused + lane; i < Q.qsize; i += 32) if (Q.qbase + i < A.cand_cap) A.cand_q[Q.qbase + i] = OGB_NOCAND;
+}
+
+// Appends the matches of all lanes (mm = this lane's 10-bit slot mask, w = its bucket) as candidates.
+// Warp-synchronous: one shuffle scan of the per-lane counts, then every lane writes its own matches.
+// Each candidate's partner strand (or, for mixed lengths, its geometry word) is prefetched to L2: the
+// verify kernel that follows is bound by exactly that fetch.
+__device__ __forceinline__ void append_matches(const ScanArgs &A, QueueCursor &Q, u32 lane, u32 mm, const u32 (&w)[OGB_BWORDS], u32 qi, u64 tag)
+{
+	const u32 cnt = __popc(mm);
+	u32 inc = cnt;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= (u32)d) inc += t; }
+	const u32 total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+	if (Q.qused + total > Q.qsize) {                                         // pad what is left, reserve a new piece
+		queue_pad(A, Q, lane);
+		Q.qsize = total > OGB_QCHUNK ? (total + 31) & ~31u : OGB_QCHUNK;
+		if (lane == 0) Q.qbase = atomicAdd(A.cand_cursor, (u64)Q.qsize);
+		Q.qbase = __shfl_sync(0xFFFFFFFFu, Q.qbase, 0);
+		Q.qused = 0;
+	}
+	u64 at = Q.qbase + Q.qused + (inc - cnt);
+	for (; mm; mm &= mm - 1, at++) {
+		const u32 v = bucket_value(w, __ffs(mm) - 1);
+		if (at < A.cand_cap) { A.cand_q[at] = qi; A.cand_v[at] = tag | v; }
+		const u32 ri = (v >> 2) - 1;
+		if (A.R.uniform_len) prefetch_l2(A.R.words + (u64)ri * (2 * A.R.uniform_pw) + ((v >> 1) & 1) * A.R.uniform_pw);
+		else prefetch_l2(A.R.meta + ri);
+	}
+	Q.qused += total;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) k_probe(ScanArgs A)
 {
 	const u32 lane = threadIdx.x & 31;
 	const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-	const u32 h = A.T.h, lt = (1u << lane) - 1;
+	const u32 h = A.T.h;
 	u64 c_probes = 0, c_sectors = 0;
-	u64 qbase = 0; u32 qused = OGB_QCHUNK;                                   // this warp's reserved queue chunk (warp-uniform)
-
-	// appends one candidate per lane of `bal` (warp-synchronous)
-	auto append = [&](u32 bal, bool has, u32 qi, u64 v) {
-		const u32 n = __popc(bal);
-		if (qused + n > OGB_QCHUNK) {                                        // pad the rest of the chunk, reserve a new one
-			for (u32 i = qused + lane; i < OGB_QCHUNK; i += 32) if (qbase + i < A.cand_cap) A.cand_q[qbase + i] = OGB_NOCAND;
-			if (lane == 0) qbase = atomicAdd(A.cand_cursor, (u64)OGB_QCHUNK);
-			qbase = __shfl_sync(0xFFFFFFFFu, qbase, 0);
-			qused = 0;
-		}
-		if (has) {
-			const u64 at = qbase + qused + __popc(bal & lt);
-			if (at < A.cand_cap) { A.cand_q[at] = qi; A.cand_v[at] = v; }
-		}
-		qused += n;
-	};
+	QueueCursor Q = {0, 0, 0};                                               // this warp's piece of the candidate queue (warp-uniform)
 
 	for (u32 qi = A.lo + gw; qi < A.hi; qi += nwarps) {
 		if (MODE == MODE_OVERLAP && A.contained && ((__ldg(A.contained + (qi >> 5)) >> (qi & 31)) & 1)) continue;   // (:548)
@@ -450,17 +472,11 @@ __global__ void __launch_bounds__(256) k_probe(ScanArgs A)
 					active = w[5 + OGB_SLOTS - 1] != 0;
 					if (active) b = (b + 1 == A.T.nb) ? 0 : b + 1;
 				}
-				u32 bal;
-				while ((bal = __ballot_sync(0xFFFFFFFFu, mm != 0)) != 0) {   // one round per match rank; a 2nd match in a bucket is rare
-					u64 v = 0;
-					if (mm) v = tag | bucket_value(w, __ffs(mm) - 1);
-					append(bal, mm != 0, qi, v);
-					mm &= mm - 1;
-				}
+				if (__any_sync(0xFFFFFFFFu, mm != 0)) append_matches(A, Q, lane, mm, w, qi, tag);
 			}
 		}
 	}
-	for (u32 i = qused + lane; i < OGB_QCHUNK; i += 32) if (qbase + i < A.cand_cap) A.cand_q[qbase + i] = OGB_NOCAND;
+	queue_pad(A, Q, lane);
 	for (int d = 16; d > 0; d >>= 1) c_sectors += __shfl_down_sync(0xFFFFFFFFu, c_sectors, d);
 	if (lane == 0) { atomicAdd(A.ctr + CTR_PROBES, c_probes); atomicAdd(A.ctr + CTR_SECTORS, c_sectors); }
 }
@@ -472,13 +488,13 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_probe_uniform(ScanArgs A, u32 nwin, u64 div_magic)
 {
 	const u32 lane = threadIdx.x & 31;
-	const u32 h = A.T.h, lt = (1u << lane) - 1;
+	const u32 h = A.T.h;
 	const u32 total = (A.hi - A.lo) * nwin;                                  // < 2^32: a launch covers at most 2^16 reads
 	const u32 rounds = (total + 31) >> 5;
 	const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 	const u32 stride = 2 * A.R.uniform_pw;
 	u64 c_sectors = 0;
-	u64 qbase = 0; u32 qused = OGB_QCHUNK;
+	QueueCursor Q = {0, 0, 0};
 
 	for (u32 rd = gw; rd < rounds; rd += nwarps) {
 		const u32 x = rd * 32 + lane;
@@ -501,25 +517,10 @@ __global__ void __launch_bounds__(256) k_probe_uniform(ScanArgs A, u32 nwin, u64
 				active = w[5 + OGB_SLOTS - 1] != 0;                          // full bucket: the key may continue in the next one
 				if (active) b = (b + 1 == A.T.nb) ? 0 : b + 1;
 			}
-			u32 bal;
-			while ((bal = __ballot_sync(0xFFFFFFFFu, mm != 0)) != 0) {
-				const u32 n = __popc(bal);
-				if (qused + n > OGB_QCHUNK) {                                    // pad the rest of the chunk, reserve a new one
-					for (u32 i = qused + lane; i < OGB_QCHUNK; i += 32) if (qbase + i < A.cand_cap) A.cand_q[qbase + i] = OGB_NOCAND;
-					if (lane == 0) qbase = atomicAdd(A.cand_cursor, (u64)OGB_QCHUNK);
-					qbase = __shfl_sync(0xFFFFFFFFu, qbase, 0);
-					qused = 0;
-				}
-				if (mm) {
-					const u64 at = qbase + qused + __popc(bal & lt);
-					if (at < A.cand_cap) { A.cand_q[at] = qi; A.cand_v[at] = tag | bucket_value(w, __ffs(mm) - 1); }
-					mm &= mm - 1;
-				}
-				qused += n;
-			}
+			if (__any_sync(0xFFFFFFFFu, mm != 0)) append_matches(A, Q, lane, mm, w, qi, tag);
 		}
 	}
-	for (u32 i = qused + lane; i < OGB_QCHUNK; i += 32) if (qbase + i < A.cand_cap) A.cand_q[qbase + i] = OGB_NOCAND;
+	queue_pad(A, Q, lane);
 	for (int d = 16; d > 0; d >>= 1) c_sectors += __shfl_down_sync(0xFFFFFFFFu, c_sectors, d);
 	if (lane == 0) atomicAdd(A.ctr + CTR_SECTORS, c_sectors);
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.ctr + CTR_PROBES, (u64)total);
@@ -538,6 +539,7 @@ __global__ void __launch_bounds__(256) k_verify(ScanArgs A)
 		if (qi == OGB_NOCAND) continue;
 		const u64 cv = A.cand_v[c];
 		const u32 j = (u32)(cv >> 32), val = (u32)cv;
+		if (val == 0) continue;                                              // spurious fingerprint hit on an empty slot
 		c_cand++;
 		u64 off; u32 L1;
 		read_geom(A.R, qi, off, L1);
@@ -1020,6 +1022,7 @@ __global__ void k_lookup(ReadStore R, Table T, const u64 *__restrict__ keys, u32
 		load_bucket(T.slots, b, w);
 		for (u32 mm = match_bucket(w, fp); mm; mm &= mm - 1) {
 			u32 val = bucket_value(w, __ffs(mm) - 1), ri = (val >> 2) - 1, o = val & 3;
+			if (val == 0) continue;
 			u64 off; u32 L;
 			read_geom(R, ri, off, L);
 			const u64 *t = R.words + off + (o >> 1) * padded_words(L);
