@@ -117,6 +117,7 @@ struct ogb_context {
 	Pool<u64> cand_v, slots_e, ov_e, sort_scratch;
 	u64 cand_cap = 0;
 	u64 *d_cursor = nullptr;         // the two candidate-queue cursors
+	u64 *d_xchg = nullptr;           // 2 * 64 u64: small per-rank values exchanged with NCCL
 	u32 slot_cap = 64;               // slots per read (adapted to the largest degree seen)
 	u32 chunk_reads = 1u << 16;      // query reads per probe/verify launch pair
 	Pool<char> flush;
@@ -182,6 +183,7 @@ static int context_create_common(ogb_context **out, int device)
 	CUDA_TRY(cudaMalloc((void **)&c->d_ctr, CTR_COUNT * sizeof(u64)));
 	CUDA_TRY(cudaMalloc((void **)&c->d_tot, 2 * sizeof(u64)));
 	CUDA_TRY(cudaMalloc((void **)&c->d_cursor, 2 * sizeof(u64)));
+	CUDA_TRY(cudaMalloc((void **)&c->d_xchg, 128 * sizeof(u64)));
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
 	for (int i = 0; i < 2; i++) { CUDA_TRY(cudaEventCreateWithFlags(&c->ev_probe[i], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&c->ev_verify[i], cudaEventDisableTiming)); }
 	CUDA_TRY(cudaMemset(c->d_tot, 0, 2 * sizeof(u64)));
@@ -233,6 +235,7 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	if (c->d_ctr) cudaFree(c->d_ctr);
 	if (c->d_tot) cudaFree(c->d_tot);
 	if (c->d_cursor) cudaFree(c->d_cursor);
+	if (c->d_xchg) cudaFree(c->d_xchg);
 	c->cand_q.release(); c->deg.release(); c->fill.release(); c->ov_q.release(); c->big_list.release();
 	c->cand_v.release(); c->slots_e.release(); c->ov_e.release(); c->sort_scratch.release();
 	if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -602,12 +605,12 @@ extern "C" int ogb_super_read_ids(ogb_context *c, uint64_t *out, uint64_t cap)
 // ------------------------------------------------------------------------------------------------
 // K3..K6
 // ------------------------------------------------------------------------------------------------
-static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *d_total)
+static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *d_total, u64 *d_max = nullptr)
 {
 	u32 nblocks = (n + OGB_SCAN_ITEMS - 1) / OGB_SCAN_ITEMS;
 	if (nblocks == 0) nblocks = 1;
 	OGB_TRY(c->sums.ensure(nblocks + 1));
-	k_scan_sums<<<nblocks, 256, 0, c->stream>>>(cnt, n, c->sums.p);
+	k_scan_sums<<<nblocks, 256, 0, c->stream>>>(cnt, n, c->sums.p, d_max);
 	k_scan_top<<<1, 1024, 0, c->stream>>>(c->sums.p, nblocks, d_total);
 	k_scan_apply<<<nblocks, 256, 0, c->stream>>>(cnt, n, c->sums.p, out);
 	CUDA_TRY(cudaGetLastError());
@@ -629,12 +632,6 @@ static int allgatherv(ogb_context *c, void *buf, size_t elem, const std::vector<
 	return OGB_OK;
 }
 
-__global__ void k_shift_nodes(u64 *nodes, u32 lo, u32 hi, u64 delta)
-{
-	u32 i = lo + blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < hi) { u64 nd = nodes[i]; if (nd & OGB_DEG_MASK) nodes[i] = nd + (delta << OGB_DEG_BITS); }
-}
-
 extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 {
 	if (!c) { ogb_set_error("NULL context"); return OGB_E_ARG; }
@@ -644,7 +641,7 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	if (!c->contain_done) OGB_TRY(ogb_mark_contained(c));
 	c->have_graph = false; c->have_pre = false; c->n_final = 0; c->n_pre = 0;
 	const u32 n = c->n;
-	if (n == 0) { c->have_graph = true; c->have_pre = keep_pre != 0; c->st.edges_pre = c->st.edges_final = c->st.nodes_final = 0; return OGB_OK; }
+	if (n == 0) { c->have_graph = true; c->have_pre = keep_pre != 0; c->st.edges_pre = c->st.edges_pre_local = c->st.edges_final = c->st.nodes_final = 0; return OGB_OK; }
 	u32 lo, hi;
 	c->shard(lo, hi);
 	const int G = c->nranks;
@@ -661,7 +658,8 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	// ---- K3 (probe + verify in chunks) and K4 (node records, heavy nodes, per-node sort into the dense
 	// adjacency array); retried with larger pools when a capacity was exceeded
 	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL0], c->stream));
-	u64 local_edges = 0;
+	u64 local_edges = 0, total_edges = 0;
+	std::vector<u64> seg_cnt(G, 0), seg_off(G, 0);
 	for (int attempt = 0;; attempt++) {
 		if (attempt == 16) { ogb_set_error("ogb_build_graph: staging pools kept overflowing"); return OGB_E_CAPACITY; }
 		OGB_TRY(c->slots_e.ensure(std::max<u64>((u64)nloc * c->slot_cap, 1)));
@@ -670,43 +668,66 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		CUDA_TRY(cudaEventRecord(c->ev[EV_K3A], c->stream));
 		OGB_TRY(scan_chunks<MODE_OVERLAP>(c, lo, hi));
 		CUDA_TRY(cudaEventRecord(c->ev[EV_K3B], c->stream));
-		OGB_TRY(exclusive_scan(c, c->deg.p + lo, nloc, c->pos.p, c->d_tot));
-		if (nloc) { k_nodes<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->deg.p, c->pos.p, c->nodes.p, c->fill.p, lo, hi, c->slot_cap, c->d_ctr); c->launches++; }
+		OGB_TRY(exclusive_scan(c, c->deg.p + lo, nloc, c->pos.p, c->d_tot, c->d_ctr + CTR_MAX_DEGREE));
 		CUDA_TRY(cudaMemcpyAsync(&local_edges, c->d_tot, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 		OGB_TRY(ctr_fetch(c));
-		if (c->h_ctr[CTR_CAND_MAX] > c->cand_cap) { c->chunk_reads = std::max<u32>(256, c->chunk_reads / 2); continue; }
+		// every rank sees the same verdicts below only for its own shard, so a retry decision is made
+		// collectively (max over ranks) before anything rank-specific happens
+		u64 verdict[4] = {c->h_ctr[CTR_CAND_MAX] > c->cand_cap, c->h_ctr[CTR_OVERFLOW], c->h_ctr[CTR_MAX_DEGREE], local_edges};
+		if (G > 1) {
+			// one small allgather carries the retry verdicts and the per-rank edge counts (C1 segment sizes)
+			CUDA_TRY(cudaMemcpyAsync(c->d_xchg + 4 * c->rank, verdict, sizeof verdict, cudaMemcpyHostToDevice, c->stream));
+			NCCL_TRY(g_nccl.AllGather(c->d_xchg + 4 * c->rank, c->d_xchg, 4, NCCL_UINT64, c->comm, c->stream));
+			std::vector<u64> all(4 * G);
+			CUDA_TRY(cudaMemcpyAsync(all.data(), c->d_xchg, 4 * G * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+			CUDA_TRY(cudaStreamSynchronize(c->stream));
+			total_edges = 0;
+			for (int r = 0; r < G; r++) {
+				verdict[0] = std::max(verdict[0], all[4 * r]); verdict[1] = std::max(verdict[1], all[4 * r + 1]); verdict[2] = std::max(verdict[2], all[4 * r + 2]);
+				seg_cnt[r] = all[4 * r + 3]; seg_off[r] = total_edges; total_edges += seg_cnt[r];
+			}
+		} else total_edges = local_edges;
+		if (verdict[0]) { c->chunk_reads = std::max<u32>(256, c->chunk_reads / 2); continue; }
 		const u64 n_over = c->h_ctr[CTR_OVERFLOW];
-		if (n_over > c->ov_q.cap) {                                          // many heavy nodes: more slots per read, bigger spill list
+		if (verdict[1] > c->ov_q.cap) {                                      // many heavy nodes: more slots per read, bigger spill list
 			if (c->slot_cap < 256) c->slot_cap *= 2;
-			else { OGB_TRY(c->ov_q.ensure(n_over + n_over / 8 + 1024)); OGB_TRY(c->ov_e.ensure(n_over + n_over / 8 + 1024)); }
+			else { OGB_TRY(c->ov_q.ensure(verdict[1] + verdict[1] / 8 + 1024)); OGB_TRY(c->ov_e.ensure(verdict[1] + verdict[1] / 8 + 1024)); }
 			continue;
 		}
-		OGB_TRY(c->edges.ensure(std::max<u64>(local_edges + local_edges / 8 + 1024, 1 << 20)));
+		c->st.max_degree = verdict[2];
+		OGB_TRY(c->edges.ensure(std::max<u64>(total_edges + total_edges / 8 + 1024, 1 << 20)));
+		if (nloc) { k_nodes<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->deg.p, c->pos.p, c->nodes.p, c->fill.p, lo, hi, c->slot_cap, seg_off[c->rank]); c->launches++; }
 		if (n_over) { k_place_overflow<<<(unsigned)((n_over + 255) / 256), 256, 0, c->stream>>>(c->ov_q.p, c->ov_e.p, n_over, c->nodes.p, c->edges.p, c->fill.p, lo); c->launches++; }
 		k_sort_nodes<<<grid_for(c, (const void *)k_sort_nodes, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->slots_e.p, c->edges.p, lo, hi, c->slot_cap,
 		                                                                                                       c->big_list.p, (u32)c->big_list.cap, c->d_ctr);
 		CUDA_TRY(cudaGetLastError());
 		c->launches++;
-		c->st.max_degree = c->h_ctr[CTR_MAX_DEGREE];
 		c->st.overflow_reads = 0;
-		if (c->st.max_degree > OGB_EC) {                                     // repeats: a few very large nodes
+		if (c->st.max_degree > OGB_EC) {                                     // repeats: a few very large nodes (may be none on this rank)
 			OGB_TRY(ctr_fetch(c));
 			u64 n_big = c->h_ctr[CTR_BIG_NODES];
-			if (n_big > c->big_list.cap) { OGB_TRY(c->big_list.ensure(n_big + 1024)); continue; }
-			u64 need = 0, m = 1;
-			while (m < c->st.max_degree) m <<= 1;
-			need = n_big * m;
-			OGB_TRY(c->sort_scratch.ensure(std::max<u64>(need, 1)));
-			k_sort_big<<<(unsigned)std::min<u64>(n_big, 2048), 256, 0, c->stream>>>(c->nodes.p, c->edges.p, c->big_list.p, (u32)n_big, c->sort_scratch.p, c->sort_scratch.cap, c->d_ctr);
-			CUDA_TRY(cudaGetLastError());
-			c->launches++;
+			if (n_big > c->big_list.cap) {                                   // only this rank's list was too short: redo its sort pass
+				OGB_TRY(c->big_list.ensure(n_big + 1024));
+				CUDA_TRY(cudaMemsetAsync(c->d_ctr + CTR_BIG_NODES, 0, sizeof(u64), c->stream));
+				k_sort_nodes<<<grid_for(c, (const void *)k_sort_nodes, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->slots_e.p, c->edges.p, lo, hi, c->slot_cap,
+				                                                                                                       c->big_list.p, (u32)c->big_list.cap, c->d_ctr);
+				c->launches++;
+			}
+			if (n_big) {
+				u64 m = 1;
+				while (m < c->st.max_degree) m <<= 1;
+				OGB_TRY(c->sort_scratch.ensure(std::max<u64>(n_big * m, 1)));
+				k_sort_big<<<(unsigned)std::min<u64>(n_big, 2048), 256, 0, c->stream>>>(c->nodes.p, c->edges.p, c->big_list.p, (u32)n_big, c->sort_scratch.p, c->sort_scratch.cap, c->d_ctr);
+				CUDA_TRY(cudaGetLastError());
+				c->launches++;
+			}
 			c->st.overflow_reads = n_big;
 		}
-		// next build on these reads: slots sized to the degrees actually seen
+		// next build on these reads: slots sized to the degrees actually seen (same decision on every rank)
 		{
 			u32 want = (u32)std::min<u64>(256, std::max<u64>(16, (c->st.max_degree * 5 / 4 + 7) / 8 * 8));
-			if (n_over == 0 && want < c->slot_cap) c->slot_cap = want;
-			else if (n_over > 0 && c->slot_cap < 256 && n_over > local_edges / 64) c->slot_cap = std::min<u32>(256, c->slot_cap * 2);
+			if (verdict[1] == 0 && want < c->slot_cap) c->slot_cap = want;
+			else if (verdict[1] > 0 && c->slot_cap < 256 && verdict[1] > total_edges / 64) c->slot_cap = std::min<u32>(256, c->slot_cap * 2);
 		}
 		break;
 	}
@@ -717,52 +738,13 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	c->st.edges_pre_local = local_exact;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL1], c->stream));
 
-	// ---- C1: every rank needs the whole pre-reduction adjacency (a pivot can live anywhere)
-	std::vector<u64> seg_cnt(G, 0), seg_off(G, 0);
-	u64 total_edges = local_edges;
+	// ---- C1: every rank needs the whole pre-reduction adjacency (a pivot can live anywhere). The sort
+	// already wrote this rank's segment at its global position.
 	if (G > 1) {
-		Pool<u64> d_counts;
-		OGB_TRY(d_counts.ensure(G));
-		std::vector<u64> counts(G, 0);
-		CUDA_TRY(cudaMemcpyAsync(d_counts.p + c->rank, &local_edges, sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-		NCCL_TRY(g_nccl.AllGather(d_counts.p + c->rank, d_counts.p, 1, NCCL_UINT64, c->comm, c->stream));
-		CUDA_TRY(cudaMemcpyAsync(counts.data(), d_counts.p, G * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		d_counts.release();
-		total_edges = 0;
-		for (int r = 0; r < G; r++) { seg_cnt[r] = counts[r]; seg_off[r] = total_edges; total_edges += counts[r]; }
-		if (total_edges > c->edges.cap) {
-			// grow, keeping this rank's segment
-			Pool<u64> bigger;
-			OGB_TRY(bigger.ensure(total_edges + total_edges / 16 + 1024));
-			CUDA_TRY(cudaMemcpyAsync(bigger.p, c->edges.p, local_edges * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
-			CUDA_TRY(cudaStreamSynchronize(c->stream));
-			c->edges.release();
-			c->edges = bigger;
-		}
-		if (seg_off[c->rank] != 0) {
-			// move the local segment to its global position (ranges may overlap: go through pos-sized temp only if needed)
-			Pool<u64> tmp;
-			OGB_TRY(tmp.ensure(std::max<u64>(local_edges, 1)));
-			CUDA_TRY(cudaMemcpyAsync(tmp.p, c->edges.p, local_edges * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
-			CUDA_TRY(cudaMemcpyAsync(c->edges.p + seg_off[c->rank], tmp.p, local_edges * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
-			if (hi > lo) { k_shift_nodes<<<(hi - lo + 255) / 256, 256, 0, c->stream>>>(c->nodes.p, lo, hi, seg_off[c->rank]); c->launches++; }
-			CUDA_TRY(cudaStreamSynchronize(c->stream));
-			tmp.release();
-		}
 		OGB_TRY(allgatherv(c, c->edges.p, sizeof(u64), seg_off, seg_cnt));
 		NCCL_TRY(g_nccl.AllGather(c->nodes.p + per * c->rank, c->nodes.p, per, NCCL_UINT64, c->comm, c->stream));
 	}
-	u64 exact_total = local_exact;
-	if (G > 1) {
-		Pool<u64> d_x;
-		OGB_TRY(d_x.ensure(2));
-		CUDA_TRY(cudaMemcpyAsync(d_x.p, &local_exact, sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-		NCCL_TRY(g_nccl.AllReduce(d_x.p, d_x.p + 1, 1, NCCL_UINT64, 0 /*ncclSum*/, c->comm, c->stream));
-		CUDA_TRY(cudaMemcpyAsync(&exact_total, d_x.p + 1, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		d_x.release();
-	}
+	const u64 exact_total = total_edges;
 	c->st.edges_pre = exact_total;
 	c->n_pre = exact_total;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_XPRE1], c->stream));
@@ -830,12 +812,9 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		std::vector<u64> foff(G), fcnt(G);
 		for (int r = 0; r < G; r++) { foff[r] = bounds[r]; fcnt[r] = bounds[r + 1] - bounds[r]; }
 		OGB_TRY(allgatherv(c, c->fin.p, sizeof(ogb_edge), foff, fcnt));
-		Pool<u64> d_nodes_final;
-		OGB_TRY(d_nodes_final.ensure(1));
-		NCCL_TRY(g_nccl.AllReduce(c->d_ctr + CTR_NODES_FINAL, d_nodes_final.p, 1, NCCL_UINT64, 0 /*ncclSum*/, c->comm, c->stream));
-		CUDA_TRY(cudaMemcpyAsync(&c->h_ctr[CTR_NODES_FINAL], d_nodes_final.p, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		NCCL_TRY(g_nccl.AllReduce(c->d_ctr + CTR_NODES_FINAL, c->d_xchg + 64, 1, NCCL_UINT64, 0 /*ncclSum*/, c->comm, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(&c->h_ctr[CTR_NODES_FINAL], c->d_xchg + 64, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		d_nodes_final.release();
 	}
 	CUDA_TRY(cudaEventRecord(c->ev[EV_RED1], c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));

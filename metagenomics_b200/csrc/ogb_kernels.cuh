@@ -595,17 +595,16 @@ __global__ void __launch_bounds__(256) k_verify(ScanArgs A)
 	}
 }
 
-// Node records start<<24|deg from the scanned degrees (pos = exclusive scan over the shard), plus the
-// statistics E_pre / largest degree.
+// Node records start<<24|deg from the scanned degrees: pos = exclusive scan over the shard, base =
+// where this rank's segment starts in the (global) dense adjacency array.
 __global__ void __launch_bounds__(256) k_nodes(const u32 *__restrict__ deg, const u64 *__restrict__ pos, u64 *__restrict__ nodes,
-                                               u32 *__restrict__ fill, u32 lo, u32 hi, u32 cap, u64 *ctr)
+                                               u32 *__restrict__ fill, u32 lo, u32 hi, u32 cap, u64 base)
 {
 	const u32 u = lo + blockIdx.x * blockDim.x + threadIdx.x;
-	const u32 d = u < hi ? deg[u] : 0;
-	if (u < hi) { nodes[u] = d ? ((pos[u - lo] << OGB_DEG_BITS) | d) : 0; fill[u - lo] = cap; }
-	u32 mx = d;
-	for (int k = 16; k > 0; k >>= 1) mx = max(mx, __shfl_down_sync(0xFFFFFFFFu, mx, k));
-	if ((threadIdx.x & 31) == 0 && mx) atomicMax(ctr + CTR_MAX_DEGREE, (u64)mx);
+	if (u >= hi) return;
+	const u32 d = deg[u];
+	nodes[u] = d ? (((base + pos[u - lo]) << OGB_DEG_BITS) | d) : 0;
+	fill[u - lo] = cap;
 }
 
 // Spilled edges of heavy nodes (degree > cap) go straight to their final range, behind the first
@@ -915,11 +914,16 @@ __global__ void __launch_bounds__(OGB_WARPS * 32) k_twin_keep(const u64 *__restr
 // Exclusive scan of u32 counts into u64 offsets: (1) per-block sums, (2) one block scans the sums,
 // (3) per-block scan + base.
 #define OGB_SCAN_ITEMS 2048     // per block of 256 threads (8 per thread)
-__global__ void __launch_bounds__(256) k_scan_sums(const u32 *__restrict__ cnt, u32 n, u64 *__restrict__ sums)
+__global__ void __launch_bounds__(256) k_scan_sums(const u32 *__restrict__ cnt, u32 n, u64 *__restrict__ sums, u64 *max_out)
 {
 	__shared__ u64 sh[8];
 	u64 base = (u64)blockIdx.x * OGB_SCAN_ITEMS, acc = 0;
-	for (u32 i = threadIdx.x; i < OGB_SCAN_ITEMS; i += 256) if (base + i < n) acc += cnt[base + i];
+	u32 mx = 0;
+	for (u32 i = threadIdx.x; i < OGB_SCAN_ITEMS; i += 256) if (base + i < n) { const u32 v = cnt[base + i]; acc += v; mx = max(mx, v); }
+	if (max_out) {
+		for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_down_sync(0xFFFFFFFFu, mx, d));
+		if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_out, (u64)mx);
+	}
 	for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d);
 	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
 	__syncthreads();

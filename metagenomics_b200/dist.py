@@ -40,6 +40,8 @@ def make_context(backend="nccl"):
     from .api import Context, nccl_unique_id
     rank, world, local = env_rank()
     uid = None
+    if backend == "nccl" and torch.cuda.is_available():
+        torch.cuda.set_device(local)      # object collectives stage through the current device
     if world > 1:
         if not dist.is_initialized():
             kw = {"device_id": torch.device("cuda", local)} if backend == "nccl" else {}
