@@ -197,7 +197,9 @@ def main():
         C.memmove(p, arr.ctypes.data, arr.nbytes)
         return p
     p_words, p_offs, p_lens = pinned(words), pinned(woffs), pinned(lens)
-    h2d = words.nbytes + woffs.nbytes + lens.nbytes
+    # a uniform-length, tightly packed input travels as words only (ogb_reads_upload_packed derives the rest)
+    uniform = n_unique > 0 and int(lens.min()) == int(lens.max())
+    h2d = words.nbytes + (0 if uniform else woffs.nbytes + lens.nbytes)
 
     def barrier():
         if world > 1:
@@ -269,21 +271,25 @@ def main():
         orc = Oracle(cfg["bases"], cfg["offsets"], m).run_all(Oracle.THREE_PHASE, threads=os.cpu_count() or 1)
         assert np.array_equal(sort_tuples(edges_as_tuples(got)), orc.edges()), "bench result differs from the oracle"
 
-    # gather per-rank stats for the roofline (local counters differ per rank)
+    # Roofline of the dominant kernel = the probe kernel (k_probe_uniform / k_probe), one launch per
+    # chunk of query reads. Algorithmic bytes of one launch (DESIGN.md "Roofline", SURVEY.md 8(d) K3
+    # terms): one 32-byte sector per probed window + the 12-byte candidate record per fingerprint match
+    # + the query strand of every read of the chunk streamed once.
     read_bytes = int(np.mean([(int(l) + 63) // 64 * 16 for l in lens[:: max(1, len(lens) // 4096)]])) if n_unique else 32
-    lo_hi = (n_unique + world - 1) // world
-    n_local = max(0, min(n_unique, lo_hi * (rank + 1)) - min(n_unique, lo_hi * rank))
-    scan_bytes = SECTOR * st["overlap_probes"] + (read_bytes + EDGE_BYTES) * st["edges_pre_local"] + read_bytes * n_local
+    launches = max(1, st["probe_launches"])
+    from metagenomics_b200.dist import shard_bounds
+    s_lo, s_hi = shard_bounds(n_unique, rank, world)
+    scan_bytes = (SECTOR * st["overlap_probes"] + 12 * st["candidates"] + read_bytes * (s_hi - s_lo)) / launches
     peak, peak_src = measured_peaks()
 
     if rank == 0:
-        achieved = scan_bytes / (st["ms_scan_kernel"] * 1e-3) / 1e9 if st["ms_scan_kernel"] > 0 else 0.0
+        achieved = scan_bytes / (st["ms_probe_launch"] * 1e-3) / 1e9 if st["ms_probe_launch"] > 0 else 0.0
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "scan_kernel_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "probe_kernel_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
                 tj = json.load(f)
-            if tj.get("workload") == f"config{args.config}@{args.scale}":
+            if tj.get("workload") == f"config{args.config}@{args.scale}x{world}":
                 traffic = tj.get("dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -299,11 +305,12 @@ def main():
             "per_step_ms": [round(float(x), 3) for x in per_step],
             "gpu_launches": int(st["kernel_launches"]) * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": "k_scan<MODE_OVERLAP> (K3: window scan + verification + per-node sort)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": scan_bytes, "kernel_ms": st["ms_scan_kernel"],
-                         "share_of_step": st["ms_scan_kernel"] / ms_step if ms_step else None},
-            "phases_ms": {k: st[k] for k in ("ms_hash_build", "ms_contain", "ms_overlap", "ms_exchange_pre", "ms_mark", "ms_reduce", "ms_total")},
+            "roofline": {"kernel": "k_probe_uniform (K3 probe: window hash + 64-byte bucket gather + fingerprint match), one launch per chunk of 65536 reads",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": scan_bytes, "kernel_ms": st["ms_probe_launch"],
+                         "launches_per_step": launches, "share_of_step": st["ms_probe_launch"] * launches / ms_step if ms_step else None,
+                         "note": "the index (64 B per read) is L2-resident at this size, so DRAM traffic is below the algorithmic bytes; the kernel is issue-bound (profiles/r1_notes.md)"},
+            "phases_ms": {k: st[k] for k in ("ms_hash_build", "ms_contain", "ms_overlap", "ms_scan_kernel", "ms_exchange_pre", "ms_mark", "ms_reduce", "ms_total")},
             "stats": {k: st[k] for k in ("table_bytes", "overlap_probes", "probe_sectors", "candidates", "pivot_entries", "active_pivots",
                                          "max_degree", "overflow_reads", "n_contained", "nodes_final")},
             "setup_s": {"dataset_sort_dedupe": t_dataset}, "wall_s_timed_region": wall,

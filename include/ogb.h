@@ -75,17 +75,17 @@ typedef struct ogb_stats {
 	uint64_t max_degree;       /* largest pre-reduction out-degree (this rank) */
 	uint64_t overflow_reads;   /* reads that took the large-degree slow path */
 	uint32_t kernel_launches;  /* kernels of this library launched by the last hash_build+build_graph */
-	uint32_t reserved;
+	uint32_t probe_launches;   /* launches of the probe kernel (one per chunk of query reads) */
 	float ms_pack;             /* K0 */
 	float ms_hash_build;       /* K1 */
 	float ms_contain;          /* K2 (+ allreduce) */
-	float ms_overlap;          /* K3 (+K4: per-node sort fused) */
+	float ms_overlap;          /* K3 probe + verify (all chunks) and K4 node records + per-node sort */
 	float ms_exchange_pre;     /* C1 allgatherv of pre-reduction edges (0 on one GPU) */
 	float ms_mark;             /* K5 */
 	float ms_reduce;           /* K6 (+C2/C3) */
 	float ms_total;            /* hash_build + mark_contained + build_graph, device time */
-	float ms_scan_kernel;      /* the K3 kernel launch alone (the roofline kernel) */
-	float reserved2;
+	float ms_scan_kernel;      /* K3 alone: all probe + verify launches */
+	float ms_probe_launch;     /* average duration of one probe launch (the roofline kernel), measured in place */
 } ogb_stats;
 
 int ogb_version(void);

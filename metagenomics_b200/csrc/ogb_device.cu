@@ -90,6 +90,8 @@ struct ogb_context {
 	cudaStream_t stream = nullptr;
 	cudaStream_t stream2 = nullptr;   // verify kernels run here, overlapping the next chunk's probe
 	cudaEvent_t ev_probe[2] = {}, ev_verify[2] = {};
+	cudaEvent_t ev_pk[2 * 64] = {};   // timing pairs around the first 64 probe launches of a build
+	u32 n_pk = 0;
 	ncclComm_t comm = nullptr;
 	cudaEvent_t ev[EV_COUNT] = {};
 	// packed reads
@@ -120,6 +122,7 @@ struct ogb_context {
 	u64 *d_xchg = nullptr;           // 2 * 64 u64: small per-rank values exchanged with NCCL
 	u32 slot_cap = 64;               // slots per read (adapted to the largest degree seen)
 	u32 chunk_reads = 1u << 16;      // query reads per probe/verify launch pair
+	int probe_blocks_per_sm = 0, verify_blocks_per_sm = 0;   // 0 = as many as fit
 	Pool<char> flush;
 	u64 n_final = 0, n_pre = 0;
 	bool have_graph = false, have_pre = false;
@@ -180,6 +183,7 @@ static int context_create_common(ogb_context **out, int device)
 	}
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (int i = 0; i < EV_COUNT; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
+	for (int i = 0; i < 128; i++) CUDA_TRY(cudaEventCreate(&c->ev_pk[i]));
 	CUDA_TRY(cudaMalloc((void **)&c->d_ctr, CTR_COUNT * sizeof(u64)));
 	CUDA_TRY(cudaMalloc((void **)&c->d_tot, 2 * sizeof(u64)));
 	CUDA_TRY(cudaMalloc((void **)&c->d_cursor, 2 * sizeof(u64)));
@@ -240,6 +244,7 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	c->cand_v.release(); c->slots_e.release(); c->ov_e.release(); c->sort_scratch.release();
 	if (c->h_ctr) cudaFreeHost(c->h_ctr);
 	for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	for (int i = 0; i < 128; i++) if (c->ev_pk[i]) cudaEventDestroy(c->ev_pk[i]);
 	for (int i = 0; i < 2; i++) { if (c->ev_probe[i]) cudaEventDestroy(c->ev_probe[i]); if (c->ev_verify[i]) cudaEventDestroy(c->ev_verify[i]); }
 	if (c->stream2) cudaStreamDestroy(c->stream2);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -347,30 +352,42 @@ extern "C" int ogb_reads_upload_packed(ogb_context *c, const uint64_t *words, co
 	if (!c || (n && (!words || !word_offsets || !lengths))) { ogb_set_error("ogb_reads_upload_packed: NULL argument"); return OGB_E_ARG; }
 	if (n >= (1ull << 30)) { ogb_set_error("ogb_reads_upload_packed: at most 2^30-1 reads per context"); return OGB_E_CAPACITY; }
 	CUDA_TRY(cudaSetDevice(c->device));
-	std::vector<u32> lens(n);
-	for (u64 i = 0; i < n; i++) {
-		if (lengths[i] < 2) { ogb_set_error("ogb_reads_upload_packed: read %llu shorter than 2", (unsigned long long)(i + 1)); return OGB_E_ARG; }
-		lens[i] = lengths[i];
-	}
+	uint16_t mn = 0xFFFF, mx = 0;
+	for (u64 i = 0; i < n; i++) { mn = std::min(mn, lengths[i]); mx = std::max(mx, lengths[i]); }
+	if (n && mn < 2) { ogb_set_error("ogb_reads_upload_packed: a read is shorter than 2"); return OGB_E_ARG; }
 	u64 total_words = 0;
 	std::vector<u64> meta_host;
-	OGB_TRY(layout_reads(c, lens, total_words, meta_host));
+	const u64 in_words = n ? word_offsets[n] - word_offsets[0] : 0;
+	// one read length and a tight input: only the words travel, the kernel derives offsets and lengths
+	const bool regular = n && mn == mx && in_words == n * (u64)((mx + 31) / 32);
+	if (regular) {
+		c->n = (u32)n; c->min_len = c->max_len = mx; c->uniform_len = mx; c->uniform_pw = ((mx + 63) >> 6) << 1;
+		total_words = n * 2 * c->uniform_pw;
+	} else {
+		std::vector<u32> lens(n);
+		for (u64 i = 0; i < n; i++) lens[i] = lengths[i];
+		OGB_TRY(layout_reads(c, lens, total_words, meta_host));
+	}
 	OGB_TRY(upload_common(c, total_words, meta_host));
 	if (n == 0) return OGB_OK;
-	u64 in_words = word_offsets[n] - word_offsets[0];
 	OGB_TRY(c->stage_bytes.ensure(in_words * sizeof(u64)));
-	OGB_TRY(c->stage_offs.ensure(n + 1));
-	OGB_TRY(c->stage_lens.ensure(n));
 	std::vector<u64> rel;
 	const u64 *offs_src = (const u64 *)word_offsets;
-	if (word_offsets[0] != 0) { rel.resize(n + 1); for (u64 i = 0; i <= n; i++) rel[i] = word_offsets[i] - word_offsets[0]; offs_src = rel.data(); }
+	if (!regular) {
+		OGB_TRY(c->stage_offs.ensure(n + 1));
+		OGB_TRY(c->stage_lens.ensure(n));
+		if (word_offsets[0] != 0) { rel.resize(n + 1); for (u64 i = 0; i <= n; i++) rel[i] = word_offsets[i] - word_offsets[0]; offs_src = rel.data(); }
+	}
 	CUDA_TRY(cudaEventRecord(c->ev[EV_PACK0], c->stream));
 	CUDA_TRY(cudaMemcpyAsync(c->stage_bytes.p, words + word_offsets[0], in_words * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-	CUDA_TRY(cudaMemcpyAsync(c->stage_offs.p, offs_src, (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-	CUDA_TRY(cudaMemcpyAsync(c->stage_lens.p, lengths, n * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+	if (!regular) {
+		CUDA_TRY(cudaMemcpyAsync(c->stage_offs.p, offs_src, (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(c->stage_lens.p, lengths, n * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+	}
 	u32 max_pw = ((c->max_len + 63) >> 6) << 1;
 	u64 threads = (u64)n * max_pw;
-	k_pack_words<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>((const u64 *)c->stage_bytes.p, c->stage_offs.p, c->stage_lens.p, c->words.p,
+	k_pack_words<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>((const u64 *)c->stage_bytes.p, regular ? nullptr : c->stage_offs.p,
+	                                                                      regular ? nullptr : c->stage_lens.p, c->words.p,
 	                                                                      c->uniform_len ? nullptr : c->meta.p, (u32)n, c->uniform_len, c->uniform_pw, max_pw);
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(c->ev[EV_PACK1], c->stream));
@@ -514,8 +531,16 @@ template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 		if (c->cand_cap < want) { OGB_TRY(c->cand_q.ensure(2 * want)); OGB_TRY(c->cand_v.ensure(2 * want)); c->cand_cap = want; }
 	}
 	if (c->chunk_reads > (1u << 16)) c->chunk_reads = 1u << 16;             // k_probe_uniform indexes windows with 32 bits
-	const int gp = grid_for(c, (const void *)k_probe<MODE>, 256), gv = grid_for(c, (const void *)k_verify<MODE>, 256);
-	const int gu = grid_for(c, (const void *)k_probe_uniform<MODE>, 256);
+	int gp = grid_for(c, (const void *)k_probe<MODE>, 256), gv = grid_for(c, (const void *)k_verify<MODE>, 256);
+	int gu = grid_for(c, (const void *)k_probe_uniform<MODE>, 256);
+	{
+		// probe (issue-bound) and verify (latency-bound) of neighbouring chunks are meant to be co-resident:
+		// cap the resident blocks per SM of each so that neither grid fills the machine alone
+		const char *ep = getenv("OGB_PROBE_BLOCKS_PER_SM"), *ev = getenv("OGB_VERIFY_BLOCKS_PER_SM");
+		const int bp = ep ? atoi(ep) : c->probe_blocks_per_sm, bv = ev ? atoi(ev) : c->verify_blocks_per_sm;
+		if (bp > 0) { gp = std::min(gp, c->sm_count * bp); gu = std::min(gu, c->sm_count * bp); }
+		if (bv > 0) gv = std::min(gv, c->sm_count * bv);
+	}
 	const bool overlap_streams = getenv("OGB_ONE_STREAM") == nullptr;
 	cudaStream_t sv = overlap_streams ? c->stream2 : c->stream;
 	ScanArgs a = scan_args(c, lo, hi);
@@ -527,12 +552,15 @@ template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 		if (overlap_streams && i >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_verify[q], 0));   // queue q is free again
 		CUDA_TRY(cudaMemsetAsync(a.cand_cursor, 0, sizeof(u64), c->stream));
 		const u32 warps = a.hi - a.lo;
+		const bool timed = MODE == MODE_OVERLAP && i < 64;
+		if (timed) CUDA_TRY(cudaEventRecord(c->ev_pk[2 * i], c->stream));
 		if (c->uniform_len && !a.contained) {
 			const u32 nwin = c->uniform_len - c->h - 1;
 			const u64 rounds = ((u64)warps * nwin + 31) / 32;
 			k_probe_uniform<MODE><<<(unsigned)std::min<u64>(gu, (rounds * 32 + 255) / 256), 256, 0, c->stream>>>(a, nwin, ~0ull / nwin + 1);
 		} else
 			k_probe<MODE><<<(unsigned)std::min<u64>(gp, ((u64)warps * 32 + 255) / 256), 256, 0, c->stream>>>(a);
+		if (timed) { CUDA_TRY(cudaEventRecord(c->ev_pk[2 * i + 1], c->stream)); c->n_pk = i + 1; }
 		if (overlap_streams) {
 			CUDA_TRY(cudaEventRecord(c->ev_probe[q], c->stream));
 			CUDA_TRY(cudaStreamWaitEvent(sv, c->ev_probe[q], 0));
@@ -825,6 +853,12 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	c->st.nodes_final = c->h_ctr[CTR_NODES_FINAL];
 	c->st.ms_overlap = ev_ms(c, EV_OVL0, EV_OVL1);
 	c->st.ms_scan_kernel = ev_ms(c, EV_K3A, EV_K3B);
+	{
+		float sum = 0;
+		for (u32 i = 0; i < c->n_pk; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev_pk[2 * i], c->ev_pk[2 * i + 1]) == cudaSuccess) sum += ms; else cudaGetLastError(); }
+		c->st.ms_probe_launch = c->n_pk ? sum / c->n_pk : 0;
+		c->st.probe_launches = (nloc + c->chunk_reads - 1) / c->chunk_reads;
+	}
 	c->st.ms_exchange_pre = ev_ms(c, EV_OVL1, EV_XPRE1);
 	c->st.ms_mark = ev_ms(c, EV_XPRE1, EV_MARK1);
 	c->st.ms_reduce = ev_ms(c, EV_MARK1, EV_RED1);

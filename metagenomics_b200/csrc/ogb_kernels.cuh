@@ -254,12 +254,13 @@ __global__ void k_pack_words(const u64 *__restrict__ in_words, const u64 *__rest
 	u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	u32 idx = (u32)(tid / max_pw), k = (u32)(tid % max_pw);
 	if (idx >= n) return;
-	u32 L = lens[idx];
+	// lens / in_offsets are null for a uniform-length, tightly packed input (nothing but the words is uploaded)
+	u32 L = lens ? lens[idx] : uniform_len;
 	u64 off;
 	if (uniform_len) off = (u64)idx * (2 * uniform_pw); else off = meta[idx] >> 16;
 	u32 pw = padded_words(L), nw = (L + 31) >> 5;
 	if (k >= pw) return;
-	const u64 *src = in_words + in_offsets[idx];
+	const u64 *src = in_words + (in_offsets ? in_offsets[idx] : (u64)idx * nw);
 	u64 fw = k < nw ? src[k] : 0;
 	// rc bases [32k, 32k+32) = complement of forward bases (L-32k-32 .. L-32k], reversed
 	u64 rc = 0;
