@@ -527,70 +527,89 @@ __global__ void __launch_bounds__(256) k_probe_uniform(ScanArgs A, u32 nwin, u64
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.ctr + CTR_PROBES, (u64)total);
 }
 
-// One thread per candidate.
+// One thread per candidate. The loop is warp-uniform (32 consecutive candidates per warp and
+// iteration): a read's candidates are adjacent in the queue, so the lanes of a warp mostly append to
+// the same one or two nodes -- their deg[] increments are aggregated with __match_any_sync into one
+// atomic per distinct node instead of ~26 serialised same-address atomics.
 template <int MODE>
 __global__ void __launch_bounds__(256) k_verify(ScanArgs A)
 {
 	const u64 total = min(*A.cand_cursor, A.cand_cap);
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(A.ctr + CTR_CAND_MAX, *A.cand_cursor);
-	const u32 h = A.T.h;
+	const u32 h = A.T.h, lane = threadIdx.x & 31, lt = (1u << lane) - 1;
 	u32 c_cand = 0, c_hits = 0;
-	for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (u64)gridDim.x * blockDim.x) {
-		const u32 qi = A.cand_q[c];
-		if (qi == OGB_NOCAND) continue;
-		const u64 cv = A.cand_v[c];
-		const u32 j = (u32)(cv >> 32), val = (u32)cv;
-		if (val == 0) continue;                                              // spurious fingerprint hit on an empty slot
-		c_cand++;
-		u64 off; u32 L1;
-		read_geom(A.R, qi, off, L1);
-		const u64 *s = A.R.words + off;
-		const u32 ri = (val >> 2) - 1, o = val & 3;
-		u64 roff; u32 L2;
-		read_geom(A.R, ri, roff, L2);
-		const u64 *t = A.R.words + roff + (o >> 1) * padded_words(L2);
-		if (MODE == MODE_CONTAIN) {
-			// OverlapGraph.cpp:256: read1 must be longer; :302-340 restated on the whole of read2.
-			if (L1 <= L2) continue;
-			u32 a;
-			if ((o & 1) == 0) { if (L1 - j < L2) continue; a = j; }          // :316-321
-			else { if (j < L2 - h) continue; a = j - (L2 - h); }            // :331-336
-			if (!region_equal_aligned<LdGlobal, LdGlobal>(s, a, t, L2)) continue;
-			atomicMax(A.sup + ri, ((u64)L1 << 32) | (u64)(0xFFFFFFFFu - qi));   // :259-268
-			c_hits++;
-		} else {
-			if (A.contained && ((__ldg(A.contained + (ri >> 5)) >> (ri & 31)) & 1)) continue;   // :548 superReadID == 0
-			u32 pa, len, orient, offset;
-			const u64 *pp, *qq;               // compare pp[pa..pa+len) with qq[0..len)
-			if ((o & 1) == 0) {               // key = prefix of t: s[j..L1) must equal t[0..L1-j)      (:359-370)
-				if (L1 - j >= L2) continue;
-				pp = s; pa = j; qq = t; len = L1 - j;
-				orient = o == 0 ? 3 : 2;      // :552,:554
-				offset = j;                   // L1 - overlap, overlap = L1 - j
-			} else {                          // key = suffix of t: s[0..j+h) must equal t[L2-h-j..L2)  (:371-382)
-				if (L2 - h < j) continue;
-				pp = t; pa = L2 - h - j; qq = s; len = h + j;
-				orient = o == 1 ? 0 : 1;      // :553,:555
-				offset = L1 - h - j;          // L1 - overlap, overlap = h + j
+	for (u64 c0 = (u64)blockIdx.x * blockDim.x + (threadIdx.x - lane); c0 < total; c0 += (u64)gridDim.x * blockDim.x) {
+		const u64 c = c0 + lane;
+		bool ok = false;
+		u32 qi = c < total ? A.cand_q[c] : OGB_NOCAND, ri = 0, o = 0, L1 = 0, L2 = 0, orient = 0, offset = 0;
+		if (qi != OGB_NOCAND) {
+			const u64 cv = A.cand_v[c];
+			const u32 j = (u32)(cv >> 32), val = (u32)cv;
+			if (val != 0) {                                                  // 0: spurious fingerprint hit on an empty slot
+				c_cand++;
+				u64 off, roff;
+				read_geom(A.R, qi, off, L1);
+				const u64 *s = A.R.words + off;
+				ri = (val >> 2) - 1; o = val & 3;
+				read_geom(A.R, ri, roff, L2);
+				const u64 *t = A.R.words + roff + (o >> 1) * padded_words(L2);
+				if (MODE == MODE_CONTAIN) {
+					// OverlapGraph.cpp:256: read1 must be longer; :302-340 restated on the whole of read2.
+					if (L1 > L2) {
+						u32 a = 0; bool fits;
+						if ((o & 1) == 0) { fits = L1 - j >= L2; a = j; }            // :316-321
+						else { fits = j >= L2 - h; a = j - (L2 - h); }             // :331-336
+						if (fits && region_equal_aligned<LdGlobal, LdGlobal>(s, a, t, L2)) {
+							atomicMax(A.sup + ri, ((u64)L1 << 32) | (u64)(0xFFFFFFFFu - qi));   // :259-268
+							c_hits++;
+						}
+					}
+				} else if (!(A.contained && ((__ldg(A.contained + (ri >> 5)) >> (ri & 31)) & 1))) {   // :548 superReadID == 0
+					u32 pa, len; bool fits;
+					const u64 *pp, *qq;           // compare pp[pa..pa+len) with qq[0..len)
+					if ((o & 1) == 0) {           // key = prefix of t: s[j..L1) must equal t[0..L1-j)      (:359-370)
+						fits = L1 - j < L2;
+						pp = s; pa = j; qq = t; len = L1 - j;
+						orient = o == 0 ? 3 : 2;  // :552,:554
+						offset = j;               // L1 - overlap, overlap = L1 - j
+					} else {                      // key = suffix of t: s[0..j+h) must equal t[L2-h-j..L2)  (:371-382)
+						fits = L2 - h >= j;
+						pp = t; pa = L2 - h - j; qq = s; len = h + j;
+						orient = o == 1 ? 0 : 1;  // :553,:555
+						offset = L1 - h - j;      // L1 - overlap, overlap = h + j
+					}
+					ok = fits && region_equal_aligned<LdGlobal, LdGlobal>(pp, pa, qq, len);
+				}
 			}
-			if (!region_equal_aligned<LdGlobal, LdGlobal>(pp, pa, qq, len)) continue;
+		}
+		if (MODE == MODE_OVERLAP) {
 			// Self-overlap: the reference inserts the edge and its twin object into the same list
-			// (OverlapGraph.cpp:409-417); twin offset = (UINT16)(L2 + offset - L1) = offset.
-			const u32 ne = ri == qi ? 2 : 1;
-			const u64 e0 = make_edge(offset & 0xFFFF, ri + 1, orient), e1 = make_edge(offset & 0xFFFF, ri + 1, twin_orient(orient));
-			const u32 pos = atomicAdd(A.deg + qi, ne);
-			for (u32 q = 0; q < ne; q++) {
-				const u64 e = q ? e1 : e0;
-				if (pos + q < A.cap) A.slots_e[(u64)(qi - A.slot_lo) * A.cap + pos + q] = e;
-				else {                                                       // heavy node: spill, placed by k_place_overflow
-					const u64 ov = atomicAdd(A.ctr + CTR_OVERFLOW, 1ull);
-					if (ov < A.ov_cap) { A.ov_q[ov] = qi; A.ov_e[ov] = e; }
+			// (OverlapGraph.cpp:409-417); twin offset = (UINT16)(L2 + offset - L1) = offset -> two entries.
+			const u32 ne = ok ? (ri == qi ? 2u : 1u) : 0u;
+			const u32 grp = __match_any_sync(0xFFFFFFFFu, ok ? qi : (0x80000000u | lane));   // lanes appending to the same node
+			const int leader = __ffs(grp) - 1;
+			const u32 b1 = __ballot_sync(0xFFFFFFFFu, ne >= 1), b2 = __ballot_sync(0xFFFFFFFFu, ne == 2);
+			const u32 all = __popc(grp & b1) + __popc(grp & b2);             // entries my group appends / those of lanes before me
+			const u32 before = __popc(grp & b1 & lt) + __popc(grp & b2 & lt);
+			u32 base = 0;
+			if (ok && (int)lane == leader) base = atomicAdd(A.deg + qi, all);
+			base = __shfl_sync(0xFFFFFFFFu, base, leader);
+			if (ok) {
+				const u64 e0 = make_edge(offset & 0xFFFF, ri + 1, orient), e1 = make_edge(offset & 0xFFFF, ri + 1, twin_orient(orient));
+				for (u32 q = 0; q < ne; q++) {
+					const u64 e = q ? e1 : e0;
+					const u32 pos = base + before + q;
+					if (pos < A.cap) A.slots_e[(u64)(qi - A.slot_lo) * A.cap + pos] = e;
+					else {                                                   // heavy node: spill, placed by k_place_overflow
+						const u64 ov = atomicAdd(A.ctr + CTR_OVERFLOW, 1ull);
+						if (ov < A.ov_cap) { A.ov_q[ov] = qi; A.ov_e[ov] = e; }
+					}
 				}
 			}
 		}
 	}
 	for (int d = 16; d > 0; d >>= 1) { c_cand += __shfl_down_sync(0xFFFFFFFFu, c_cand, d); c_hits += __shfl_down_sync(0xFFFFFFFFu, c_hits, d); }
-	if ((threadIdx.x & 31) == 0) {
+	if (lane == 0) {
 		if (c_cand) atomicAdd(A.ctr + CTR_CANDIDATES, (u64)c_cand);
 		if (MODE == MODE_CONTAIN && c_hits) atomicAdd(A.ctr + CTR_CONTAIN_HITS, (u64)c_hits);
 	}

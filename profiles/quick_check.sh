@@ -7,4 +7,3 @@ for l in sys.stdin:
     else: print(l.strip()[:300])
 "; }
 run
-OGB_NO_SYM=1 run
