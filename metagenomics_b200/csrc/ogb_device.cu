@@ -102,8 +102,9 @@ struct ogb_context {
 	u32 n = 0, uniform_len = 0, uniform_pw = 0, min_len = 0, max_len = 0;
 	bool have_reads = false;
 	// index
-	Pool<u32> slots;
+	Pool<u32> slots, summary;
 	u32 nb = 0, h = 0;
+	bool use_summary = false;       // the per-bucket summary pays off once the index no longer fits L2
 	bool have_table = false;
 	// containment
 	Pool<u64> sup;
@@ -132,7 +133,7 @@ struct ogb_context {
 	u32 launches = 0;
 
 	ReadStore rs() const { ReadStore r; r.words = words.p; r.meta = uniform_len ? nullptr : meta.p; r.n = n; r.uniform_len = uniform_len; r.uniform_pw = uniform_pw; return r; }
-	Table tb() const { Table t; t.slots = slots.p; t.nb = nb; t.h = h; return t; }
+	Table tb() const { Table t; t.slots = slots.p; t.summary = use_summary ? summary.p : nullptr; t.nb = nb; t.h = h; return t; }
 	void shard(u32 &lo, u32 &hi) const
 	{
 		u64 per = ((u64)n + nranks - 1) / nranks;
@@ -233,7 +234,7 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	if (c->stream2) cudaStreamSynchronize(c->stream2);
 	if (c->comm) g_nccl.CommDestroy(c->comm);
 	c->words.release(); c->meta.release(); c->stage_bytes.release(); c->stage_offs.release(); c->stage_lens.release();
-	c->slots.release(); c->sup.release(); c->contained.release(); c->nodes.release(); c->edges.release(); c->pos.release();
+	c->slots.release(); c->summary.release(); c->sup.release(); c->contained.release(); c->nodes.release(); c->edges.release(); c->pos.release();
 	c->sums.release(); c->eflag.release(); c->surv.release(); c->scratch_state.release(); c->cnt.release();
 	c->scratch_keys.release(); c->fin.release(); c->pre.release(); c->flush.release();
 	if (c->d_ctr) cudaFree(c->d_ctr);
@@ -424,9 +425,17 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 	if (nb >= (1ull << 32)) { ogb_set_error("index too large"); return OGB_E_CAPACITY; }
 	c->nb = (u32)nb;
 	OGB_TRY(c->slots.ensure(nb * OGB_BWORDS));
+	{
+		// measured on B200 (profiles/r1_notes.md): with the index L2-resident (83 MB at 1.3 M reads) the summary
+		// costs 4 % of a step; once the index outgrows the 126 MB L2 it removes most HBM bucket fetches
+		const char *e = getenv("OGB_SUMMARY");
+		c->use_summary = e ? atoi(e) != 0 : nb * OGB_BWORDS * sizeof(u32) > (96ull << 20);
+	}
+	if (c->use_summary) OGB_TRY(c->summary.ensure(nb));
 	c->launches = 0;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_HASH0], c->stream));
 	CUDA_TRY(cudaMemsetAsync(c->slots.p, 0, nb * OGB_BWORDS * sizeof(u32), c->stream));
+	if (c->use_summary) CUDA_TRY(cudaMemsetAsync(c->summary.p, 0, nb * sizeof(u32), c->stream));
 	if (c->n) {
 		u64 threads = (u64)c->n * 4;
 		k_hash_insert<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->rs(), c->tb());
@@ -686,10 +695,11 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	// ---- K3 (probe + verify in chunks) and K4 (node records, heavy nodes, per-node sort into the dense
 	// adjacency array); retried with larger pools when a capacity was exceeded
 	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL0], c->stream));
-	u64 local_edges = 0, total_edges = 0;
+	u64 local_edges = 0, total_edges = 0, exact_edges = 0, seg_stride = 0;   // total_edges = extent of the dense array (with padding)
 	std::vector<u64> seg_cnt(G, 0), seg_off(G, 0);
 	for (int attempt = 0;; attempt++) {
 		if (attempt == 16) { ogb_set_error("ogb_build_graph: staging pools kept overflowing"); return OGB_E_CAPACITY; }
+		seg_stride = 0;
 		OGB_TRY(c->slots_e.ensure(std::max<u64>((u64)nloc * c->slot_cap, 1)));
 		OGB_TRY(ctr_zero(c));
 		CUDA_TRY(cudaMemsetAsync(c->deg.p + lo, 0, (size_t)nloc * sizeof(u32), c->stream));
@@ -709,12 +719,17 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 			std::vector<u64> all(4 * G);
 			CUDA_TRY(cudaMemcpyAsync(all.data(), c->d_xchg, 4 * G * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 			CUDA_TRY(cudaStreamSynchronize(c->stream));
-			total_edges = 0;
+			// Segments sit at a common stride (the largest segment, rounded up) so that C1 and C2 are single
+			// in-place ncclAllGather calls; shards are balanced, so the padding is < 1 % of the transfer.
+			exact_edges = 0;
 			for (int r = 0; r < G; r++) {
 				verdict[0] = std::max(verdict[0], all[4 * r]); verdict[1] = std::max(verdict[1], all[4 * r + 1]); verdict[2] = std::max(verdict[2], all[4 * r + 2]);
-				seg_cnt[r] = all[4 * r + 3]; seg_off[r] = total_edges; total_edges += seg_cnt[r];
+				seg_cnt[r] = all[4 * r + 3]; seg_stride = std::max(seg_stride, seg_cnt[r]); exact_edges += seg_cnt[r];
 			}
-		} else total_edges = local_edges;
+			seg_stride = (seg_stride + 255) & ~255ull;
+			for (int r = 0; r < G; r++) seg_off[r] = seg_stride * r;
+			total_edges = seg_stride * G;
+		} else total_edges = exact_edges = local_edges;
 		if (verdict[0]) { c->chunk_reads = std::max<u32>(256, c->chunk_reads / 2); continue; }
 		const u64 n_over = c->h_ctr[CTR_OVERFLOW];
 		if (verdict[1] > c->ov_q.cap) {                                      // many heavy nodes: more slots per read, bigger spill list
@@ -769,10 +784,10 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	// ---- C1: every rank needs the whole pre-reduction adjacency (a pivot can live anywhere). The sort
 	// already wrote this rank's segment at its global position.
 	if (G > 1) {
-		OGB_TRY(allgatherv(c, c->edges.p, sizeof(u64), seg_off, seg_cnt));
+		NCCL_TRY(g_nccl.AllGather(c->edges.p + seg_off[c->rank], c->edges.p, seg_stride, NCCL_UINT64, c->comm, c->stream));
 		NCCL_TRY(g_nccl.AllGather(c->nodes.p + per * c->rank, c->nodes.p, per, NCCL_UINT64, c->comm, c->stream));
 	}
-	const u64 exact_total = total_edges;
+	const u64 exact_total = exact_edges;
 	c->st.edges_pre = exact_total;
 	c->n_pre = exact_total;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_XPRE1], c->stream));
@@ -807,7 +822,7 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		OGB_TRY(c->scratch_keys.ensure(need)); OGB_TRY(c->scratch_state.ensure(need));
 	}
 	CUDA_TRY(cudaEventRecord(c->ev[EV_MARK1], c->stream));
-	if (G > 1) OGB_TRY(allgatherv(c, c->eflag.p, 1, seg_off, seg_cnt));   // C2
+	if (G > 1) NCCL_TRY(g_nccl.AllGather(c->eflag.p + seg_off[c->rank], c->eflag.p, seg_stride, NCCL_UINT8, c->comm, c->stream));   // C2
 
 	// ---- K6
 	k_twin_keep<<<grid_for(c, (const void *)k_twin_keep, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->edges.p, c->eflag.p, c->surv.p,
