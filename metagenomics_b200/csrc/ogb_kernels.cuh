@@ -65,7 +65,10 @@ struct ReadStore {
 struct Table {
 	u32 *slots;          // nb * OGB_BWORDS words
 	u32 *summary;        // nb words: Bloom bits of the fingerprints stored in the bucket | OGB_SPILLED; null = not used
-	u32 nb;              // buckets
+	u32 nb;              // buckets = nparts * part_buckets
+	u32 nparts;          // hash partitions (= ranks: every rank builds one partition, then the slices are allgathered)
+	u32 part_buckets;    // buckets per partition; linear probing wraps inside a partition
+	u32 my_part;         // K1: insert only keys of this partition (nparts > 1)
 	u32 h;               // hashStringLength = minOverlap-1 (HashTable.cpp:54)
 };
 
@@ -160,7 +163,16 @@ __device__ __forceinline__ u32 hash_fp(u64 hash) { u32 f = (u32)hash & 0xFFFFu; 
 #define OGB_SPILLED 0x80000000u
 __device__ __forceinline__ u32 summary_bits(u32 fp) { return (1u << min(fp & 31u, 30u)) | (1u << min((fp >> 5) & 31u, 30u)); }
 
-__device__ __forceinline__ u32 bucket_of(u64 hash, u32 nb) { return __umulhi((u32)(hash >> 32), nb); }
+// Two-level range reduction of the high hash half: partition = floor(x*P / 2^32), bucket inside the
+// partition from the fractional part. With one partition this is plain floor(x*nb / 2^32).
+__device__ __forceinline__ u32 bucket_of(u64 hash, const Table &T, u32 &part)
+{
+	const u64 t = (u64)(u32)(hash >> 32) * T.nparts;
+	part = (u32)(t >> 32);
+	return part * T.part_buckets + __umulhi((u32)t, T.part_buckets);
+}
+// next bucket of the probe sequence: wraps at the end of the partition (pend = one past its last bucket)
+__device__ __forceinline__ u32 next_bucket(u32 b, u32 pend, const Table &T) { return b + 1 == pend ? pend - T.part_buckets : b + 1; }
 
 // s[a..a+len) == t[b..b+len) on packed strands, streaming one new word per side and 32 bases. No
 // early exit: (almost) every candidate verifies, and independent iterations keep the sector
@@ -311,7 +323,10 @@ __global__ void k_hash_insert(ReadStore R, Table T)
 	u32 p = (o & 1) ? L - T.h : 0;
 	u64 hash = key_hash<LdGlobal>(w, p, T.h);
 	const u32 fp = hash_fp(hash), val = ((idx + 1) << 2) | o;
-	u32 b = bucket_of(hash, T.nb);
+	u32 part;
+	u32 b = bucket_of(hash, T, part);
+	if (T.nparts > 1 && part != T.my_part) return;                           // another rank builds that partition
+	const u32 pend = (part + 1) * T.part_buckets;
 	for (;;) {
 		u32 *w = T.slots + (u64)b * OGB_BWORDS;
 		// one L2-coherent look at the ten values, then a CAS on the first empty one; buckets fill front
@@ -328,7 +343,7 @@ __global__ void k_hash_insert(ReadStore R, Table T)
 		for (; s < OGB_SLOTS && !done; s++) done = atomicCAS(w + 5 + s, 0u, val) == 0;
 		if (done) { atomicOr(w + ((s - 1) >> 1), fp << (16 * ((s - 1) & 1))); if (T.summary) atomicOr(T.summary + b, summary_bits(fp)); break; }
 		if (T.summary) atomicOr(T.summary + b, OGB_SPILLED);
-		b = (b + 1 == T.nb) ? 0 : b + 1;
+		b = next_bucket(b, pend, T);
 	}
 }
 
@@ -474,9 +489,10 @@ __global__ void __launch_bounds__(256) k_probe(ScanArgs A)
 		for (u32 jb = 1; jb <= nwin; jb += 32) {
 			const u32 j = jb + lane;
 			bool active = j <= nwin;
-			u32 b = 0, fp = 0;
+			u32 b = 0, fp = 0, pend = 0;
 			if (active) {
-				const u64 hash = key_hash<LdGlobal>(s, j, h); b = bucket_of(hash, A.T.nb); fp = hash_fp(hash);
+				u32 part;
+				const u64 hash = key_hash<LdGlobal>(s, j, h); b = bucket_of(hash, A.T, part); fp = hash_fp(hash); pend = (part + 1) * A.T.part_buckets;
 				if (A.T.summary) {
 					const u32 sm = ld_na32(A.T.summary + b), need = summary_bits(fp);
 					active = (sm & need) == need || (sm & OGB_SPILLED);          // else: no entry with this fingerprint, no fetch
@@ -492,7 +508,7 @@ __global__ void __launch_bounds__(256) k_probe(ScanArgs A)
 					mm = match_bucket(w, fp);
 					// K1 fills a bucket front to back, so "last slot taken" = full = the key may continue in the next bucket
 					active = w[5 + OGB_SLOTS - 1] != 0;
-					if (active) b = (b + 1 == A.T.nb) ? 0 : b + 1;
+					if (active) b = next_bucket(b, pend, A.T);
 				}
 				if (__any_sync(0xFFFFFFFFu, mm != 0)) append_matches(A, Q, lane, mm, w, qi, tag);
 			}
@@ -523,10 +539,11 @@ __global__ void __launch_bounds__(256) k_probe_uniform(ScanArgs A, u32 nwin, u64
 		bool active = x < total;
 		const u32 qr = nwin == 1 ? x : (u32)__umul64hi(div_magic, (u64)x);  // x / nwin (Lemire: exact for 32-bit x, nwin > 1)
 		const u32 j = x - qr * nwin + 1, qi = A.lo + qr;
-		u32 b = 0, fp = 0;
+		u32 b = 0, fp = 0, pend = 0;
 		if (active) {
+			u32 part;
 			const u64 hash = key_hash<LdGlobal>(A.R.words + (u64)qi * stride, j, h);
-			b = bucket_of(hash, A.T.nb); fp = hash_fp(hash);
+			b = bucket_of(hash, A.T, part); fp = hash_fp(hash); pend = (part + 1) * A.T.part_buckets;
 			if (A.T.summary) {
 				if (A.T.summary) {
 					const u32 sm = ld_na32(A.T.summary + b), need = summary_bits(fp);
@@ -543,7 +560,7 @@ __global__ void __launch_bounds__(256) k_probe_uniform(ScanArgs A, u32 nwin, u64
 				c_sectors++;
 				mm = match_bucket(w, fp);
 				active = w[5 + OGB_SLOTS - 1] != 0;                          // full bucket: the key may continue in the next one
-				if (active) b = (b + 1 == A.T.nb) ? 0 : b + 1;
+				if (active) b = next_bucket(b, pend, A.T);
 			}
 			if (__any_sync(0xFFFFFFFFu, mm != 0)) append_matches(A, Q, lane, mm, w, qi, tag);
 		}
@@ -1021,13 +1038,13 @@ __global__ void __launch_bounds__(256) k_scan_apply(const u32 *__restrict__ cnt,
 // Final edge records, sorted by (src, offset, dst, orient) = node order x adjacency order: one
 // thread per node copies its cnt[u] survivors from surv[start..] to out[pos[u]..].
 __global__ void __launch_bounds__(256) k_compact(const u64 *__restrict__ nodes, const ogb_edge *__restrict__ surv, const u32 *__restrict__ cnt,
-                                                 const u64 *__restrict__ pos, ogb_edge *__restrict__ out, u32 lo, u32 hi)
+                                                 const u64 *__restrict__ pos, ogb_edge *__restrict__ out, u32 lo, u32 hi, u64 sub, u64 add)
 {
 	u32 u = lo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (u >= hi) return;
 	u32 c = cnt[u];
 	if (c == 0) return;
-	u64 start = __ldg(nodes + u) >> OGB_DEG_BITS, p = pos[u];
+	u64 start = __ldg(nodes + u) >> OGB_DEG_BITS, p = pos[u] - sub + add;     // multi-rank: position inside this rank's padded segment
 	for (u32 i = 0; i < c; i++) out[p + i] = surv[start + i];
 }
 
@@ -1067,7 +1084,9 @@ __global__ void k_lookup(ReadStore R, Table T, const u64 *__restrict__ keys, u32
 	if (k >= n_keys) return;
 	const u64 *key = keys + k * (kw + 2);
 	u64 hash = key_hash<LdGlobal>(key, 0, T.h);
-	u32 fp = hash_fp(hash), b = bucket_of(hash, T.nb), c = 0;
+	u32 part;
+	u32 fp = hash_fp(hash), b = bucket_of(hash, T, part), c = 0;
+	const u32 pend = (part + 1) * T.part_buckets;
 	for (;;) {
 		u32 w[OGB_BWORDS];
 		load_bucket(T.slots, b, w);
@@ -1082,7 +1101,7 @@ __global__ void k_lookup(ReadStore R, Table T, const u64 *__restrict__ keys, u32
 			c++;
 		}
 		if (w[5 + OGB_SLOTS - 1] == 0) break;
-		b = (b + 1 == T.nb) ? 0 : b + 1;
+		b = next_bucket(b, pend, T);
 	}
 	if (pass == 0) cnt[k] = c;
 }
