@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libogb.so")
+LIB_PATH = os.environ.get("OGB_LIB") or os.path.join(_HERE, "libogb.so")   # OGB_LIB: another build of the same library (experiments)
 
 OGB_OK, OGB_E_ARG, OGB_E_CUDA, OGB_E_NCCL, OGB_E_STATE, OGB_E_CAPACITY, OGB_E_IO, OGB_E_NOMEM = range(8)
 

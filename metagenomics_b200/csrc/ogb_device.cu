@@ -5,7 +5,7 @@
 //   ogb_reads_upload*   H2D + K0                         [Read::setRead, Read.cpp:75-82]
 //   ogb_hash_build      K1                               [HashTable::insertDataset, HashTable.cpp:50-80]
 //   ogb_mark_contained  K2 (+ allreduce-max)             [OverlapGraph::markContainedReads, OverlapGraph.cpp:225-290]
-//   ogb_build_graph     K3 (+big) -> C1 -> K5 -> C2 -> K6 -> C3   [buildOverlapGraphFromHashTable, OverlapGraph.cpp:107-210]
+//   ogb_build_graph     K3 -> barrier -> K5 (peer reads) -> barrier -> K6 (peer reads) -> C3   [buildOverlapGraphFromHashTable, OverlapGraph.cpp:107-210]
 // All buffers are grow-only pools owned by the context, so a repeated build allocates nothing.
 
 #include "ogb_internal.h"
@@ -83,6 +83,9 @@ template <class T> struct Pool {
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// d_xchg layout (u64 words): per-rank verdict vectors, the ranks' IPC handles (3 x 64 bytes each), scratch
+enum { XCHG_PER_RANK = 8, XCHG_HANDLES = XCHG_PER_RANK * OGB_MAX_RANKS, XCHG_SCRATCH = XCHG_HANDLES + 24 * OGB_MAX_RANKS, XCHG_WORDS = XCHG_SCRATCH + 8 };
+
 enum { EV_BEGIN = 0, EV_PACK0, EV_PACK1, EV_HASH0, EV_HASH1, EV_CONT0, EV_CONT1, EV_OVL0, EV_OVL1, EV_XPRE1, EV_MARK1, EV_RED1, EV_K3A, EV_K3B, EV_T0, EV_T1, EV_COUNT };
 
 struct ogb_context {
@@ -111,16 +114,21 @@ struct ogb_context {
 	Pool<u32> contained;
 	bool contain_done = false, any_contained = false;
 	// graph
-	Pool<u64> nodes, edges, pos, sums;
-	Pool<unsigned char> eflag, scratch_state;
+	Pool<u64> pos, sums, surv;       // surv: the first OGB_SURV surviving edge words of every own node
+	Pool<unsigned char> scratch_state;
 	Pool<u32> cnt, scratch_keys;
-	Pool<ogb_edge> fin, pre, surv, fin_stage;
-	// scan staging: candidate queue of one chunk, per-read slot regions, spill list of heavy nodes
-	Pool<u32> cand_q, deg, fill, ov_q, big_list;   // cand_q / cand_v hold two ping-pong queues of cand_cap entries
-	Pool<u64> cand_v, slots_e, ov_e, sort_scratch;
+	Pool<ogb_edge> fin, pre, fin_stage;
+	// the adjacency: per-read slot regions, degrees, heavy lists -- the three pools the other ranks map (GraphView)
+	Pool<u64> slots_e, ext;
+	Pool<u32> deg;
+	void *peer_ptr[3][OGB_MAX_RANKS] = {};   // [slots_e, deg, ext][rank]: CUDA IPC mappings of the peers' pools
+	bool shared_ready = false;
+	// scan staging: candidate queue of one chunk, spill list of heavy nodes
+	Pool<u32> cand_q, fill, ov_q;    // cand_q / cand_v hold two ping-pong queues of cand_cap entries
+	Pool<u64> cand_v, ov_e;
 	u64 cand_cap = 0;
 	u64 *d_cursor = nullptr;         // the two candidate-queue cursors
-	u64 *d_xchg = nullptr;           // 2 * 64 u64: small per-rank values exchanged with NCCL
+	u64 *d_xchg = nullptr;           // small per-rank values exchanged with NCCL (XCHG_* layout)
 	u32 slot_cap = 64;               // slots per read (adapted to the largest degree seen)
 	u32 chunk_reads = 1u << 16;      // query reads per probe/verify launch pair
 	int probe_blocks_per_sm = 0, verify_blocks_per_sm = 0;   // 0 = as many as fit
@@ -194,7 +202,8 @@ static int context_create_common(ogb_context **out, int device)
 	CUDA_TRY(cudaMalloc((void **)&c->d_ctr, CTR_COUNT * sizeof(u64)));
 	CUDA_TRY(cudaMalloc((void **)&c->d_tot, 2 * sizeof(u64)));
 	CUDA_TRY(cudaMalloc((void **)&c->d_cursor, 2 * sizeof(u64)));
-	CUDA_TRY(cudaMalloc((void **)&c->d_xchg, 128 * sizeof(u64)));
+	CUDA_TRY(cudaMalloc((void **)&c->d_xchg, XCHG_WORDS * sizeof(u64)));
+	CUDA_TRY(cudaMemset(c->d_xchg, 0, XCHG_WORDS * sizeof(u64)));
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
 	for (int i = 0; i < 2; i++) { CUDA_TRY(cudaEventCreateWithFlags(&c->ev_probe[i], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&c->ev_verify[i], cudaEventDisableTiming)); }
 	CUDA_TRY(cudaMemset(c->d_tot, 0, 2 * sizeof(u64)));
@@ -238,17 +247,20 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	if (c->stream2) cudaStreamSynchronize(c->stream2);
+	for (int r = 0; r < OGB_MAX_RANKS; r++)
+		for (int k = 0; k < 3; k++) if (c->peer_ptr[k][r]) cudaIpcCloseMemHandle(c->peer_ptr[k][r]);
+	cudaGetLastError();
 	if (c->comm) g_nccl.CommDestroy(c->comm);
 	c->words.release(); c->meta.release(); c->stage_bytes.release(); c->stage_offs.release(); c->stage_lens.release();
-	c->slots.release(); c->summary.release(); c->sup.release(); c->contained.release(); c->nodes.release(); c->edges.release(); c->pos.release();
-	c->sums.release(); c->eflag.release(); c->surv.release(); c->scratch_state.release(); c->cnt.release();
+	c->slots.release(); c->summary.release(); c->sup.release(); c->contained.release(); c->pos.release();
+	c->sums.release(); c->surv.release(); c->scratch_state.release(); c->cnt.release();
 	c->scratch_keys.release(); c->fin.release(); c->pre.release(); c->flush.release(); c->fin_stage.release();
 	if (c->d_ctr) cudaFree(c->d_ctr);
 	if (c->d_tot) cudaFree(c->d_tot);
 	if (c->d_cursor) cudaFree(c->d_cursor);
 	if (c->d_xchg) cudaFree(c->d_xchg);
-	c->cand_q.release(); c->deg.release(); c->fill.release(); c->ov_q.release(); c->big_list.release();
-	c->cand_v.release(); c->slots_e.release(); c->ov_e.release(); c->sort_scratch.release();
+	c->cand_q.release(); c->deg.release(); c->fill.release(); c->ov_q.release();
+	c->cand_v.release(); c->slots_e.release(); c->ext.release(); c->ov_e.release();
 	if (c->h_ctr) cudaFreeHost(c->h_ctr);
 	for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 128; i++) if (c->ev_pk[i]) cudaEventDestroy(c->ev_pk[i]);
@@ -671,6 +683,102 @@ static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *
 	return OGB_OK;
 }
 
+// Device-side barrier over all ranks: a one-word allreduce on the build stream. It completes on a rank
+// only after every rank has enqueued it behind its own earlier work, so whatever the peers wrote
+// before their barrier is in their HBM when the kernels behind ours read it over NVLink.
+static int rank_barrier(ogb_context *c)
+{
+	if (c->nranks > 1) NCCL_TRY(g_nccl.AllReduce(c->d_xchg + XCHG_SCRATCH, c->d_xchg + XCHG_SCRATCH + 1, 1, NCCL_UINT64, 0 /*ncclSum*/, c->comm, c->stream));
+	return OGB_OK;
+}
+
+static void close_peers(ogb_context *c)
+{
+	for (int r = 0; r < OGB_MAX_RANKS; r++)
+		for (int k = 0; k < 3; k++)
+			if (c->peer_ptr[k][r]) { cudaIpcCloseMemHandle(c->peer_ptr[k][r]); c->peer_ptr[k][r] = nullptr; }
+	cudaGetLastError();
+}
+
+// The three pools the other ranks read in K5 / K6 -- slot regions, degrees, heavy lists. Every rank
+// calls this with the same sizes (they derive from collective values only), so growing them is a
+// collective decision: peers unmap, everybody reallocates, the CUDA IPC handles are allgathered and
+// the peers' pools are mapped again. Steady state (sizes unchanged) costs nothing.
+static int ensure_shared(ogb_context *c, size_t need_slots, size_t need_deg, size_t need_ext)
+{
+	if (need_slots <= c->slots_e.cap && need_deg <= c->deg.cap && need_ext <= c->ext.cap && c->shared_ready) return OGB_OK;
+	const int G = c->nranks;
+	if (G > 1 && c->shared_ready) {
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		close_peers(c);
+		OGB_TRY(rank_barrier(c));                                            // nobody frees while a peer still has the pool mapped
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+	}
+	c->shared_ready = false;
+	OGB_TRY(c->slots_e.ensure(need_slots + need_slots / 4));
+	OGB_TRY(c->deg.ensure(need_deg));
+	OGB_TRY(c->ext.ensure(std::max<size_t>(need_ext + need_ext / 4, 1 << 16)));
+	if (G > 1) {
+		if (G > OGB_MAX_RANKS) { ogb_set_error("at most %d ranks", OGB_MAX_RANKS); return OGB_E_ARG; }
+		cudaIpcMemHandle_t mine[3], all[3 * OGB_MAX_RANKS];
+		void *ptrs[3] = {c->slots_e.p, c->deg.p, c->ext.p};
+		for (int k = 0; k < 3; k++) CUDA_TRY(cudaIpcGetMemHandle(&mine[k], ptrs[k]));
+		static_assert(sizeof(mine) == 3 * 64, "cudaIpcMemHandle_t is 64 bytes");
+		u64 *slot = c->d_xchg + XCHG_HANDLES + (size_t)c->rank * 24;
+		CUDA_TRY(cudaMemcpyAsync(slot, mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+		NCCL_TRY(g_nccl.AllGather(slot, c->d_xchg + XCHG_HANDLES, 24, NCCL_UINT64, c->comm, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(all, c->d_xchg + XCHG_HANDLES, (size_t)G * sizeof mine, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		for (int r = 0; r < G; r++) {
+			if (r == c->rank) continue;
+			for (int k = 0; k < 3; k++) {
+				cudaError_t e = cudaIpcOpenMemHandle(&c->peer_ptr[k][r], all[3 * r + k], cudaIpcMemLazyEnablePeerAccess);
+				if (e != cudaSuccess) {
+					ogb_set_error("cannot map rank %d's adjacency over NVLink (cudaIpcOpenMemHandle: %s); all ranks must be GPUs of one node with peer access",
+					              r, cudaGetErrorString(e));
+					cudaGetLastError();
+					return OGB_E_CUDA;
+				}
+			}
+		}
+	}
+	c->shared_ready = true;
+	return OGB_OK;
+}
+
+static GraphView graph_view(const ogb_context *c)
+{
+	GraphView g;
+	memset(&g, 0, sizeof g);
+	const u64 per = ((u64)c->n + c->nranks - 1) / c->nranks;
+	for (int r = 0; r < c->nranks; r++) {
+		const bool me = r == c->rank;
+		g.slots[r] = me ? c->slots_e.p : (const u64 *)c->peer_ptr[0][r];
+		g.deg[r] = me ? c->deg.p : (const u32 *)c->peer_ptr[1][r];
+		g.ext[r] = me ? c->ext.p : (const u64 *)c->peer_ptr[2][r];
+	}
+	g.per = (u32)std::max<u64>(per, 1);
+	g.per_magic = (u32)std::min<u64>(0xFFFFFFFFull, ((1ull << 32) + g.per - 1) / g.per);
+	g.cap = c->slot_cap;
+	g.nranks = (u32)c->nranks;
+	return g;
+}
+
+// Allgather of per-rank segments of `count[r]` records each: every rank has written its own segment at
+// stage + stride*rank; one in-place ncclAllGather at the common stride, then the segments are copied
+// down into the contiguous list `out`.
+template <class T> static int gather_segments(ogb_context *c, Pool<T> &stage, u64 stride, const std::vector<u64> &count, T *out)
+{
+	const int G = c->nranks;
+	if (stride) NCCL_TRY(g_nccl.AllGather(stage.p + stride * c->rank, stage.p, stride * sizeof(T), NCCL_UINT8, c->comm, c->stream));
+	u64 at = 0;
+	for (int r = 0; r < G; r++) {
+		if (count[r]) CUDA_TRY(cudaMemcpyAsync(out + at, stage.p + stride * r, count[r] * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
+		at += count[r];
+	}
+	return OGB_OK;
+}
+
 extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 {
 	if (!c) { ogb_set_error("NULL context"); return OGB_E_ARG; }
@@ -685,134 +793,110 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	c->shard(lo, hi);
 	const int G = c->nranks;
 	const u64 per = ((u64)n + G - 1) / G;
-	OGB_TRY(c->nodes.ensure(per * G + 1));
-	OGB_TRY(c->cnt.ensure(per * G + 1));
-	OGB_TRY(c->pos.ensure((size_t)n + 1));
-	OGB_TRY(c->deg.ensure((size_t)n + 1));
-	OGB_TRY(c->fill.ensure(per + 1));
-	if (c->ov_q.cap == 0) { OGB_TRY(c->ov_q.ensure(1 << 20)); OGB_TRY(c->ov_e.ensure(1 << 20)); }
-	if (c->big_list.cap == 0) OGB_TRY(c->big_list.ensure(1 << 16));
 	const u32 nloc = hi - lo;
+	{
+		const char *e = getenv("OGB_SLOT_CAP");                              // experiment knob: fixed slots per read
+		if (e && atoi(e) >= 8 && atoi(e) <= 256) c->slot_cap = (u32)atoi(e);
+	}
+	OGB_TRY(c->cnt.ensure(per + 1));
+	OGB_TRY(c->pos.ensure(per + 1));
+	OGB_TRY(c->fill.ensure(per + 1));
+	OGB_TRY(c->surv.ensure((per + 1) * OGB_SURV));
+	if (c->ov_q.cap == 0) { OGB_TRY(c->ov_q.ensure(1 << 20)); OGB_TRY(c->ov_e.ensure(1 << 20)); }
 
-	// ---- K3 (probe + verify in chunks) and K4 (node records, heavy nodes, per-node sort into the dense
-	// adjacency array); retried with larger pools when a capacity was exceeded
+	// ---- K3 (probe + verify in chunks) into the slot regions; retried with larger pools when a capacity
+	// was exceeded. Every decision below derives from values all ranks share.
 	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL0], c->stream));
-	u64 local_edges = 0, total_edges = 0, exact_edges = 0, seg_stride = 0;   // total_edges = extent of the dense array (with padding)
-	std::vector<u64> seg_cnt(G, 0), seg_off(G, 0);
+	u64 local_edges = 0, exact_edges = 0;
+	std::vector<u64> seg_cnt(G, 0);
 	for (int attempt = 0;; attempt++) {
 		if (attempt == 16) { ogb_set_error("ogb_build_graph: staging pools kept overflowing"); return OGB_E_CAPACITY; }
-		seg_stride = 0;
-		OGB_TRY(c->slots_e.ensure(std::max<u64>((u64)nloc * c->slot_cap, 1)));
+		OGB_TRY(ensure_shared(c, per * c->slot_cap + 64, (size_t)n + 1, 0));   // +64: K5 fetches 32 slots of a pivot before it knows its degree
 		OGB_TRY(ctr_zero(c));
-		CUDA_TRY(cudaMemsetAsync(c->deg.p + lo, 0, (size_t)nloc * sizeof(u32), c->stream));
+		if (nloc) CUDA_TRY(cudaMemsetAsync(c->deg.p + lo, 0, (size_t)nloc * sizeof(u32), c->stream));
 		CUDA_TRY(cudaEventRecord(c->ev[EV_K3A], c->stream));
 		OGB_TRY(scan_chunks<MODE_OVERLAP>(c, lo, hi));
 		CUDA_TRY(cudaEventRecord(c->ev[EV_K3B], c->stream));
-		OGB_TRY(exclusive_scan(c, c->deg.p + lo, nloc, c->pos.p, c->d_tot, c->d_ctr + CTR_MAX_DEGREE));
+		OGB_TRY(exclusive_scan(c, c->deg.p + lo, nloc, c->pos.p, c->d_tot, c->d_ctr + CTR_MAX_DEGREE));   // edge count, largest degree, positions for keep_pre
 		CUDA_TRY(cudaMemcpyAsync(&local_edges, c->d_tot, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 		OGB_TRY(ctr_fetch(c));
-		// every rank sees the same verdicts below only for its own shard, so a retry decision is made
-		// collectively (max over ranks) before anything rank-specific happens
-		u64 verdict[4] = {c->h_ctr[CTR_CAND_MAX] > c->cand_cap, c->h_ctr[CTR_OVERFLOW], c->h_ctr[CTR_MAX_DEGREE], local_edges};
+		const u64 n_over = c->h_ctr[CTR_OVERFLOW], n_heavy = c->h_ctr[CTR_BIG_NODES];
+		// [0] candidate queue overflowed, [1] spilled edges, [2] largest degree, [3] edges of this rank, [4] words its heavy lists need
+		u64 verdict[XCHG_PER_RANK] = {c->h_ctr[CTR_CAND_MAX] > c->cand_cap, n_over, c->h_ctr[CTR_MAX_DEGREE], local_edges, n_over + n_heavy * c->slot_cap, 0, 0, 0};
+		u64 need_ext = verdict[4];
+		seg_cnt[0] = local_edges; exact_edges = local_edges;
 		if (G > 1) {
-			// one small allgather carries the retry verdicts and the per-rank edge counts (C1 segment sizes)
-			CUDA_TRY(cudaMemcpyAsync(c->d_xchg + 4 * c->rank, verdict, sizeof verdict, cudaMemcpyHostToDevice, c->stream));
-			NCCL_TRY(g_nccl.AllGather(c->d_xchg + 4 * c->rank, c->d_xchg, 4, NCCL_UINT64, c->comm, c->stream));
-			std::vector<u64> all(4 * G);
-			CUDA_TRY(cudaMemcpyAsync(all.data(), c->d_xchg, 4 * G * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+			// one small allgather carries the retry verdicts and the per-rank edge counts
+			CUDA_TRY(cudaMemcpyAsync(c->d_xchg + XCHG_PER_RANK * c->rank, verdict, sizeof verdict, cudaMemcpyHostToDevice, c->stream));
+			NCCL_TRY(g_nccl.AllGather(c->d_xchg + XCHG_PER_RANK * c->rank, c->d_xchg, XCHG_PER_RANK, NCCL_UINT64, c->comm, c->stream));
+			std::vector<u64> all((size_t)XCHG_PER_RANK * G);
+			CUDA_TRY(cudaMemcpyAsync(all.data(), c->d_xchg, all.size() * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 			CUDA_TRY(cudaStreamSynchronize(c->stream));
-			// Segments sit at a common stride (the largest segment, rounded up) so that C1 and C2 are single
-			// in-place ncclAllGather calls; shards are balanced, so the padding is < 1 % of the transfer.
 			exact_edges = 0;
 			for (int r = 0; r < G; r++) {
-				verdict[0] = std::max(verdict[0], all[4 * r]); verdict[1] = std::max(verdict[1], all[4 * r + 1]); verdict[2] = std::max(verdict[2], all[4 * r + 2]);
-				seg_cnt[r] = all[4 * r + 3]; seg_stride = std::max(seg_stride, seg_cnt[r]); exact_edges += seg_cnt[r];
+				const u64 *v = &all[(size_t)XCHG_PER_RANK * r];
+				verdict[0] = std::max(verdict[0], v[0]); verdict[1] = std::max(verdict[1], v[1]); verdict[2] = std::max(verdict[2], v[2]);
+				need_ext = std::max(need_ext, v[4]);
+				seg_cnt[r] = v[3]; exact_edges += v[3];
 			}
-			seg_stride = (seg_stride + 255) & ~255ull;
-			for (int r = 0; r < G; r++) seg_off[r] = seg_stride * r;
-			total_edges = seg_stride * G;
-		} else total_edges = exact_edges = local_edges;
+		}
 		if (verdict[0]) { c->chunk_reads = std::max<u32>(256, c->chunk_reads / 2); continue; }
-		const u64 n_over = c->h_ctr[CTR_OVERFLOW];
 		if (verdict[1] > c->ov_q.cap) {                                      // many heavy nodes: more slots per read, bigger spill list
 			if (c->slot_cap < 256) c->slot_cap *= 2;
 			else { OGB_TRY(c->ov_q.ensure(verdict[1] + verdict[1] / 8 + 1024)); OGB_TRY(c->ov_e.ensure(verdict[1] + verdict[1] / 8 + 1024)); }
 			continue;
 		}
 		c->st.max_degree = verdict[2];
-		OGB_TRY(c->edges.ensure(std::max<u64>(total_edges + total_edges / 8 + 1024, 1 << 20)));
-		if (nloc) { k_nodes<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->deg.p, c->pos.p, c->nodes.p, c->fill.p, lo, hi, c->slot_cap, seg_off[c->rank]); c->launches++; }
-		if (n_over) { k_place_overflow<<<(unsigned)((n_over + 255) / 256), 256, 0, c->stream>>>(c->ov_q.p, c->ov_e.p, n_over, c->nodes.p, c->edges.p, c->fill.p, lo); c->launches++; }
-		k_sort_nodes<<<grid_for(c, (const void *)k_sort_nodes, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->slots_e.p, c->edges.p, lo, hi, c->slot_cap,
-		                                                                                                       c->big_list.p, (u32)c->big_list.cap, c->d_ctr);
-		CUDA_TRY(cudaGetLastError());
-		c->launches++;
-		c->st.overflow_reads = 0;
-		if (c->st.max_degree > OGB_EC) {                                     // repeats: a few very large nodes (may be none on this rank)
-			OGB_TRY(ctr_fetch(c));
-			u64 n_big = c->h_ctr[CTR_BIG_NODES];
-			if (n_big > c->big_list.cap) {                                   // only this rank's list was too short: redo its sort pass
-				OGB_TRY(c->big_list.ensure(n_big + 1024));
-				CUDA_TRY(cudaMemsetAsync(c->d_ctr + CTR_BIG_NODES, 0, sizeof(u64), c->stream));
-				k_sort_nodes<<<grid_for(c, (const void *)k_sort_nodes, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->slots_e.p, c->edges.p, lo, hi, c->slot_cap,
-				                                                                                                       c->big_list.p, (u32)c->big_list.cap, c->d_ctr);
-				c->launches++;
-			}
-			if (n_big) {
-				u64 m = 1;
-				while (m < c->st.max_degree) m <<= 1;
-				OGB_TRY(c->sort_scratch.ensure(std::max<u64>(n_big * m, 1)));
-				k_sort_big<<<(unsigned)std::min<u64>(n_big, 2048), 256, 0, c->stream>>>(c->nodes.p, c->edges.p, c->big_list.p, (u32)n_big, c->sort_scratch.p, c->sort_scratch.cap, c->d_ctr);
+		c->st.overflow_reads = n_heavy;
+		if (verdict[1]) {                                                    // repeats: some rank has nodes with more than slot_cap edges
+			OGB_TRY(ensure_shared(c, per * c->slot_cap + 64, (size_t)n + 1, need_ext));
+			if (n_over) {
+				k_heavy_move<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->slots_e.p, c->deg.p, lo, hi, c->slot_cap, c->ext.p, c->ext.cap, c->fill.p, c->d_ctr);
+				k_heavy_place<<<(unsigned)((n_over + 255) / 256), 256, 0, c->stream>>>(c->ov_q.p, c->ov_e.p, n_over, c->slots_e.p, lo, c->slot_cap, c->ext.p, c->fill.p);
 				CUDA_TRY(cudaGetLastError());
-				c->launches++;
+				c->launches += 2;
 			}
-			c->st.overflow_reads = n_big;
-		}
-		// next build on these reads: slots sized to the degrees actually seen (same decision on every rank)
-		{
-			u32 want = (u32)std::min<u64>(256, std::max<u64>(16, (c->st.max_degree * 5 / 4 + 7) / 8 * 8));
-			if (verdict[1] == 0 && want < c->slot_cap) c->slot_cap = want;
-			else if (verdict[1] > 0 && c->slot_cap < 256 && verdict[1] > total_edges / 64) c->slot_cap = std::min<u32>(256, c->slot_cap * 2);
 		}
 		break;
 	}
 	c->st.overlap_probes = c->h_ctr[CTR_PROBES];
 	c->st.probe_sectors = c->h_ctr[CTR_SECTORS];
 	c->st.candidates = c->h_ctr[CTR_CANDIDATES];
-	const u64 local_exact = local_edges;
-	c->st.edges_pre_local = local_exact;
+	c->st.edges_pre_local = local_edges;
+	c->st.edges_pre = exact_edges;
+	c->n_pre = exact_edges;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL1], c->stream));
-
-	// ---- C1: every rank needs the whole pre-reduction adjacency (a pivot can live anywhere). The sort
-	// already wrote this rank's segment at its global position.
-	if (G > 1) {
-		NCCL_TRY(g_nccl.AllGather(c->edges.p + seg_off[c->rank], c->edges.p, seg_stride, NCCL_UINT64, c->comm, c->stream));
-		NCCL_TRY(g_nccl.AllGather(c->nodes.p + per * c->rank, c->nodes.p, per, NCCL_UINT64, c->comm, c->stream));
-	}
-	const u64 exact_total = exact_edges;
-	c->st.edges_pre = exact_total;
-	c->n_pre = exact_total;
+	OGB_TRY(rank_barrier(c));                                                // every rank's slot regions are complete
 	CUDA_TRY(cudaEventRecord(c->ev[EV_XPRE1], c->stream));
 
+	const u32 cap_now = c->slot_cap;
+	const int g_emit = grid_for(c, (const void *)k_emit<false>, OGB_WARPS * 32);
 	if (keep_pre) {
-		// export the pre-reduction adjacency as records, in node order
-		OGB_TRY(c->pre.ensure(std::max<u64>(total_edges, 1)));
-		k_degrees<<<(n + 255) / 256, 256, 0, c->stream>>>(c->nodes.p, n, c->cnt.p);
-		OGB_TRY(exclusive_scan(c, c->cnt.p, n, c->pos.p, c->d_tot));
-		k_export_pre<<<grid_for(c, (const void *)k_export_pre, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->edges.p, c->pos.p, c->pre.p, n);
-		CUDA_TRY(cudaGetLastError());
+		// the pre-reduction list as records, in node order (positions = the degree scan above)
+		OGB_TRY(c->pre.ensure(std::max<u64>(exact_edges, 1)));
+		if (G == 1) {
+			k_emit<true><<<g_emit, OGB_WARPS * 32, 0, c->stream>>>(c->slots_e.p, c->ext.p, c->deg.p, nullptr, c->pos.p, c->pre.p, lo, hi, cap_now, 0, 0);
+			CUDA_TRY(cudaGetLastError());
+		} else {
+			u64 stride = 0;
+			for (int r = 0; r < G; r++) stride = std::max(stride, seg_cnt[r]);
+			stride = (stride + 63) & ~63ull;
+			OGB_TRY(c->fin_stage.ensure(std::max<u64>(stride * G, 1)));
+			k_emit<true><<<g_emit, OGB_WARPS * 32, 0, c->stream>>>(c->slots_e.p, c->ext.p, c->deg.p, nullptr, c->pos.p, c->fin_stage.p, lo, hi, cap_now, stride * c->rank, 0);
+			CUDA_TRY(cudaGetLastError());
+			OGB_TRY(gather_segments(c, c->fin_stage, stride, seg_cnt, c->pre.p));
+		}
 		c->have_pre = true;
 	}
 
 	// ---- K5
-	OGB_TRY(c->eflag.ensure(std::max<u64>(c->edges.cap, 1)));
-	OGB_TRY(c->surv.ensure(std::max<u64>(c->edges.cap, 1)));
+	MarkArgs m;
+	m.G = graph_view(c);
+	m.own_slots = c->slots_e.p; m.own_ext = c->ext.p; m.lo = lo; m.hi = hi; m.rank = (u32)c->rank; m.cnt = c->cnt.p;
 	if (c->scratch_keys.cap == 0) { OGB_TRY(c->scratch_keys.ensure(1 << 20)); OGB_TRY(c->scratch_state.ensure(1 << 20)); }
 	for (int attempt = 0;; attempt++) {
 		if (attempt == 4) { ogb_set_error("ogb_build_graph: neighbour-set scratch kept overflowing"); return OGB_E_CAPACITY; }
 		OGB_TRY(ctr_zero(c));
-		MarkArgs m;
-		m.nodes = c->nodes.p; m.edges = c->edges.p; m.eflag = c->eflag.p; m.lo = lo; m.hi = hi;
 		m.scratch_keys = c->scratch_keys.p; m.scratch_state = c->scratch_state.p; m.scratch_cap = c->scratch_keys.cap; m.ctr = c->d_ctr;
 		k_mark<<<grid_for(c, (const void *)k_mark, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
 		CUDA_TRY(cudaGetLastError());
@@ -820,62 +904,60 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		if (c->st.max_degree * 2 <= OGB_SETCAP) break;                      // no node can have used the scratch pool
 		OGB_TRY(ctr_fetch(c));
 		if (c->h_ctr[CTR_SCRATCH_FAIL] == 0) break;
-		u64 need = c->h_ctr[CTR_SCRATCH_CURSOR] + 1024;
+		u64 need = c->h_ctr[CTR_SCRATCH_CURSOR] + 1024;                     // a rerun repeats the same verdicts: the flag bits already set stay valid
 		OGB_TRY(c->scratch_keys.ensure(need)); OGB_TRY(c->scratch_state.ensure(need));
 	}
 	CUDA_TRY(cudaEventRecord(c->ev[EV_MARK1], c->stream));
-	if (G > 1) NCCL_TRY(g_nccl.AllGather(c->eflag.p + seg_off[c->rank], c->eflag.p, seg_stride, NCCL_UINT8, c->comm, c->stream));   // C2
+	OGB_TRY(rank_barrier(c));                                                // every rank's verdicts are in its edge words
 
 	// ---- K6
-	k_twin_keep<<<grid_for(c, (const void *)k_twin_keep, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(c->nodes.p, c->edges.p, c->eflag.p, c->surv.p,
-	                                                                                                     c->cnt.p, lo, hi, c->d_ctr);
+	k_keep<<<grid_for(c, (const void *)k_keep, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m, c->surv.p);
 	CUDA_TRY(cudaGetLastError());
 	c->launches++;
-	if (G > 1) NCCL_TRY(g_nccl.AllGather(c->cnt.p + per * c->rank, c->cnt.p, per, NCCL_UINT32, c->comm, c->stream));
-	OGB_TRY(exclusive_scan(c, c->cnt.p, n, c->pos.p, c->d_tot + 1));
-	OGB_TRY(c->fin.ensure(std::max<u64>(c->edges.cap, 1)));                // E_final <= E_pre: no sync needed to size it
+	OGB_TRY(exclusive_scan(c, c->cnt.p, nloc, c->pos.p, c->d_tot + 1));
 	if (G == 1) {
-		if (hi > lo) { k_compact<<<(hi - lo + 255) / 256, 256, 0, c->stream>>>(c->nodes.p, c->surv.p, c->cnt.p, c->pos.p, c->fin.p, lo, hi, 0, 0); c->launches++; }
+		OGB_TRY(c->fin.ensure(std::max<u64>(exact_edges, 1)));               // E_final <= E_pre: no sync needed to size it
+		if (nloc) k_emit_small<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->surv.p, c->cnt.p, c->pos.p, c->fin.p, lo, hi, 0);
+		k_emit<false><<<g_emit, OGB_WARPS * 32, 0, c->stream>>>(c->slots_e.p, c->ext.p, c->deg.p, c->cnt.p, c->pos.p, c->fin.p, lo, hi, cap_now, 0, OGB_SURV);
 		CUDA_TRY(cudaGetLastError());
+		c->launches += 2;
+		u64 tot = 0;
+		CUDA_TRY(cudaMemcpyAsync(&tot, c->d_tot + 1, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 		OGB_TRY(ctr_fetch(c));
-		u64 tot[2] = {0, 0};
-		CUDA_TRY(cudaMemcpyAsync(tot, c->d_tot, 2 * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		c->n_final = tot[1];
-		if (keep_pre) c->n_pre = tot[0];
+		c->n_final = tot;
 	} else {
-		// C3: final edges of every rank's node range. Segment sizes come from the scanned positions; the
-		// segments are compacted at a common stride so that the exchange is one ncclAllGather, then
-		// copied down into the contiguous, globally sorted list.
-		std::vector<u64> bounds(G + 1, 0);
-		u64 tot[2] = {0, 0};
-		CUDA_TRY(cudaMemcpyAsync(tot, c->d_tot, 2 * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-		for (int r = 0; r < G; r++) {
-			u64 node = std::min<u64>(n, per * r);
-			if (node < n) CUDA_TRY(cudaMemcpyAsync(&bounds[r], c->pos.p + node, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-		}
+		// C3: the final edges of every rank's node range (the exchange north_star names). Segment sizes
+		// travel first (one word per rank); the segments are emitted at a common stride so that the
+		// exchange is one ncclAllGather, then copied down into the contiguous, globally sorted list.
+		std::vector<u64> fin_cnt(G, 0), all(G, 0);
+		CUDA_TRY(cudaMemcpyAsync(c->d_xchg + c->rank, c->d_tot + 1, sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+		NCCL_TRY(g_nccl.AllGather(c->d_xchg + c->rank, c->d_xchg, 1, NCCL_UINT64, c->comm, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(fin_cnt.data(), c->d_xchg, (size_t)G * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		c->n_final = tot[1];
-		if (keep_pre) c->n_pre = tot[0];
-		for (int r = 0; r <= G; r++) if (std::min<u64>(n, per * r) >= n) bounds[r] = c->n_final;
-		u64 fstride = 0;
-		for (int r = 0; r < G; r++) fstride = std::max(fstride, bounds[r + 1] - bounds[r]);
-		fstride = (fstride + 63) & ~63ull;
-		OGB_TRY(c->fin_stage.ensure(std::max<u64>(fstride * G, 1)));
-		if (hi > lo) { k_compact<<<(hi - lo + 255) / 256, 256, 0, c->stream>>>(c->nodes.p, c->surv.p, c->cnt.p, c->pos.p, c->fin_stage.p, lo, hi, bounds[c->rank], fstride * c->rank); c->launches++; }
+		u64 stride = 0, total = 0;
+		for (int r = 0; r < G; r++) { stride = std::max(stride, fin_cnt[r]); total += fin_cnt[r]; }
+		stride = (stride + 63) & ~63ull;
+		c->n_final = total;
+		OGB_TRY(c->fin_stage.ensure(std::max<u64>(stride * G, 1)));
+		OGB_TRY(c->fin.ensure(std::max<u64>(total, 1)));
+		if (nloc) k_emit_small<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->surv.p, c->cnt.p, c->pos.p, c->fin_stage.p, lo, hi, stride * c->rank);
+		k_emit<false><<<g_emit, OGB_WARPS * 32, 0, c->stream>>>(c->slots_e.p, c->ext.p, c->deg.p, c->cnt.p, c->pos.p, c->fin_stage.p, lo, hi, cap_now, stride * c->rank, OGB_SURV);
 		CUDA_TRY(cudaGetLastError());
-		if (fstride) NCCL_TRY(g_nccl.AllGather(c->fin_stage.p + fstride * c->rank, c->fin_stage.p, fstride * sizeof(ogb_edge), NCCL_UINT8, c->comm, c->stream));
-		for (int r = 0; r < G; r++)
-			if (bounds[r + 1] > bounds[r])
-				CUDA_TRY(cudaMemcpyAsync(c->fin.p + bounds[r], c->fin_stage.p + fstride * r, (bounds[r + 1] - bounds[r]) * sizeof(ogb_edge), cudaMemcpyDeviceToDevice, c->stream));
-		NCCL_TRY(g_nccl.AllReduce(c->d_ctr + CTR_NODES_FINAL, c->d_xchg + 64, 1, NCCL_UINT64, 0 /*ncclSum*/, c->comm, c->stream));
+		c->launches += 2;
+		OGB_TRY(gather_segments(c, c->fin_stage, stride, fin_cnt, c->fin.p));
+		NCCL_TRY(g_nccl.AllReduce(c->d_ctr + CTR_NODES_FINAL, c->d_xchg + XCHG_SCRATCH + 2, 1, NCCL_UINT64, 0 /*ncclSum*/, c->comm, c->stream));
 		OGB_TRY(ctr_fetch(c));
-		CUDA_TRY(cudaMemcpyAsync(&c->h_ctr[CTR_NODES_FINAL], c->d_xchg + 64, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(&c->h_ctr[CTR_NODES_FINAL], c->d_xchg + XCHG_SCRATCH + 2, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
 	}
 	CUDA_TRY(cudaEventRecord(c->ev[EV_RED1], c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	if (c->h_ctr[CTR_ASYMMETRIC]) { ogb_set_error("ogb_build_graph: %llu edges without a twin (internal error)", (unsigned long long)c->h_ctr[CTR_ASYMMETRIC]); return OGB_E_STATE; }
+	// next build on these reads: slots sized to the largest degree seen (a collective value: same decision on every rank)
+	{
+		u32 want = (u32)std::min<u64>(256, std::max<u64>(32, (c->st.max_degree * 5 / 4 + 7) / 8 * 8));
+		if (want < c->slot_cap) c->slot_cap = want;
+	}
 	c->st.pivot_entries = c->h_ctr[CTR_PIVOT_ENTRIES];
 	c->st.active_pivots = c->h_ctr[CTR_ACTIVE_PIVOTS];
 	c->st.edges_final = c->n_final;

@@ -4,9 +4,9 @@
 //   K1  k_hash_insert                 HashTable::hashRead + insertIntoTable       (HashTable.cpp:88-195)
 //   K2  k_probe/k_verify<CONTAIN>     markContainedReads + checkOverlapForContainedRead (OverlapGraph.cpp:225-340)
 //   K3  k_probe/k_verify<OVERLAP>     insertAllEdgesOfRead + checkOverlap (OverlapGraph.cpp:354-383,529-565)
-//   K4  k_nodes/k_sort_nodes          per-node sort by offset (OverlapGraph.cpp:563) + CSR
+//   K4  (none)                        the per-node sort (OverlapGraph.cpp:563) is replaced by min-reductions in K5 / ranking in K6
 //   K5  k_mark                        markTransitiveEdges                         (OverlapGraph.cpp:574-615)
-//   K6  k_twin_keep / k_compact       removeTransitiveEdges                       (OverlapGraph.cpp:623-661)
+//   K6  k_keep / k_emit               removeTransitiveEdges                       (OverlapGraph.cpp:623-661)
 //       k_lookup_*                    HashTable::getListOfReads                   (HashTable.cpp:202-221)
 //
 // Everything is integer / bit work bounded by HBM (random 32-byte sector gathers into the index
@@ -28,8 +28,8 @@
 //                 which makes the result exact and independent of hash values.
 //                 4N entries in N buckets = load 0.4: the ten-slot compare is five SIMD instructions
 //                 and fewer than 1 % of the buckets spill.
-//   edges         u64 = offset<<48 | dst<<16 | orient<<8, so integer order = (offset,dst,orient).
-//   nodes         u64 = start<<24 | degree  (adjacency of a node is contiguous and sorted).
+//   edges         u64 = offset<<48 | dst<<16 | orient<<14 | twin<<2 | flags, so integer order = (offset,dst,orient);
+//                 they live in per-read slot regions (see GraphView) from discovery to the final list.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -40,10 +40,7 @@ typedef unsigned int u32;
 #define OGB_SLOTS 10            // slots per bucket (64 bytes = one HBM burst)
 #define OGB_BWORDS 16           // u32 words per bucket
 #define OGB_WARPS 8             // warps per block in the scan / mark kernels
-#define OGB_EC 256              // largest node sorted in shared memory by one warp
 #define OGB_SETCAP 512          // per-warp neighbour set slots in shared memory (degree <= 256)
-#define OGB_DEG_BITS 24
-#define OGB_DEG_MASK 0xFFFFFFull
 
 enum { MODE_OVERLAP = 0, MODE_CONTAIN = 1 };
 
@@ -51,7 +48,7 @@ enum { MODE_OVERLAP = 0, MODE_CONTAIN = 1 };
 enum {
 	CTR_EDGE_CURSOR = 0, CTR_OVERFLOW, CTR_PROBES, CTR_SECTORS, CTR_CANDIDATES, CTR_CONTAIN_HITS,
 	CTR_PIVOT_ENTRIES, CTR_ACTIVE_PIVOTS, CTR_MAX_DEGREE, CTR_N_CONTAINED, CTR_NODES_FINAL,
-	CTR_ASYMMETRIC, CTR_SCRATCH_CURSOR, CTR_SCRATCH_FAIL, CTR_CAND_MAX, CTR_BIG_NODES, CTR_COUNT
+	CTR_ASYMMETRIC, CTR_SCRATCH_CURSOR, CTR_SCRATCH_FAIL, CTR_CAND_MAX, CTR_BIG_NODES, CTR_EXT_CURSOR, CTR_COUNT
 };
 
 struct ReadStore {
@@ -225,10 +222,16 @@ __device__ __forceinline__ bool region_equal_aligned(const u64 *__restrict__ p, 
 	return diff == 0;
 }
 
-__device__ __forceinline__ u64 make_edge(u32 offset, u32 dst, u32 orient) { return ((u64)offset << 48) | ((u64)dst << 16) | ((u64)orient << 8); }
+// Edge word: offset<<48 | dst<<16 | orient<<14 | twin<<2 | flags. Integer order of the upper 50 bits =
+// (offset, dst, orient), the reference's sort key plus the deterministic tie-break of SURVEY.md App. B.1.
+// twin (12 bits) = 1 + position of a (dst,src) entry in dst's list when K5 has seen it (0 = unknown),
+// flags = OGB_ELIM | OGB_KEEP (see GraphView).
+__device__ __forceinline__ u64 make_edge(u32 offset, u32 dst, u32 orient) { return ((u64)offset << 48) | ((u64)dst << 16) | ((u64)orient << 14); }
 __device__ __forceinline__ u32 edge_dst(u64 e) { return (u32)(e >> 16); }
-__device__ __forceinline__ u32 edge_orient(u64 e) { return (u32)(e >> 8) & 3; }
+__device__ __forceinline__ u32 edge_orient(u64 e) { return (u32)(e >> 14) & 3; }
 __device__ __forceinline__ u32 edge_offset(u64 e) { return (u32)(e >> 48); }
+__device__ __forceinline__ u32 edge_twin(u64 e) { return (u32)(e >> 2) & 0xFFFu; }
+__device__ __forceinline__ u64 edge_key(u64 e) { return e & ~0x3FFFull; }     // (offset, dst, orient) without twin / flag bits
 // OverlapGraph.cpp:593-596: the pivot is entered and left on the same strand.
 __device__ __forceinline__ bool compatible(u32 t1, u32 t2) { return ((t1 & 1) == ((t2 >> 1) & 1)); }
 // OverlapGraph.cpp:841-855
@@ -397,14 +400,12 @@ __device__ __forceinline__ u32 bucket_value(const u32 (&w)[OGB_BWORDS], int k)
 //             compare the whole overlap on packed words -- checkOverlap / checkOverlapForContainedRead.
 //             Overlap mode appends the edge to the source read's slot region (deg[] atomics, spread
 //             over N addresses); containment mode does the atomicMax on superRead.
-//   k_nodes / k_place_overflow / k_sort_nodes   node records, heavy nodes, per-node sort (:563).
 //
 // The host runs k_probe + k_verify over chunks of reads sized so that the candidate queue of a chunk
 // stays L2-resident.
 //
-// Adjacency layout: read idx owns edges[idx*cap .. idx*cap+cap) ("slots"); a node with more than cap
-// edges is moved, complete, to an extension area behind the slot region. nodes[idx] = start<<24|deg
-// describes either case, so the later kernels do not care.
+// Adjacency layout: read idx owns slots[(idx-lo)*cap .. +cap); a node with more than cap edges is
+// moved, complete, to an extension area (GraphView below).
 // ------------------------------------------------------------------------------------------------
 #define OGB_QCHUNK 128          // candidate-queue entries a warp reserves at a time
 #define OGB_NOCAND 0xFFFFFFFFu  // sentinel read index of a padding entry
@@ -644,7 +645,8 @@ __global__ void __launch_bounds__(256) k_verify(ScanArgs A)
 					const u64 e = q ? e1 : e0;
 					const u32 pos = base + before + q;
 					if (pos < A.cap) A.slots_e[(u64)(qi - A.slot_lo) * A.cap + pos] = e;
-					else {                                                   // heavy node: spill, placed by k_place_overflow
+					else {                                                   // heavy node: spill, placed by k_heavy_place
+						if (pos == A.cap) atomicAdd(A.ctr + CTR_BIG_NODES, 1ull);   // exactly one entry of a heavy node lands here
 						const u64 ov = atomicAdd(A.ctr + CTR_OVERFLOW, 1ull);
 						if (ov < A.ov_cap) { A.ov_q[ov] = qi; A.ov_e[ov] = e; }
 					}
@@ -659,137 +661,67 @@ __global__ void __launch_bounds__(256) k_verify(ScanArgs A)
 	}
 }
 
-// Node records start<<24|deg from the scanned degrees: pos = exclusive scan over the shard, base =
-// where this rank's segment starts in the (global) dense adjacency array.
-__global__ void __launch_bounds__(256) k_nodes(const u32 *__restrict__ deg, const u64 *__restrict__ pos, u64 *__restrict__ nodes,
-                                               u32 *__restrict__ fill, u32 lo, u32 hi, u32 cap, u64 base)
+// ------------------------------------------------------------------------------------------------
+// The adjacency as the verify kernel leaves it -- and as K5 / K6 consume it, without any copy or sort:
+// read idx of rank r owns slots[r][(idx - r*per)*cap .. +cap) holding deg[r][idx] edge words in
+// discovery order. A heavy node (deg > cap) keeps its whole list in ext[r], at the word offset stored
+// in its first slot (k_heavy_move / k_heavy_place). On several ranks slots[r] / deg[r] / ext[r] of the
+// other ranks are peer mappings (CUDA IPC, i.e. loads over NVLink): a pivot's adjacency or a twin's
+// verdict is read where its owner wrote it, so the pre-reduction adjacency is never exchanged.
+//
+// The low 14 bits of an edge word are annotations (make_edge leaves them 0): bit 0 = OGB_ELIM
+// "eliminated by the marking of its own node" (K5), bit 1 = OGB_KEEP "survives the reduction" (K6),
+// bits 2-13 = where the twin entry sits in the destination's list (K5, for K6). All are written by the
+// owning warp with one aligned 64-bit store while other warps may be reading dst / orient / bit 0 of
+// the same word -- fields that store never changes.
+// ------------------------------------------------------------------------------------------------
+#define OGB_MAX_RANKS 16
+#define OGB_ELIM 1ull
+#define OGB_KEEP 2ull
+
+struct GraphView {
+	const u64 *slots[OGB_MAX_RANKS];
+	const u32 *deg[OGB_MAX_RANKS];   // indexed by global read index; rank r's array is valid on r's range
+	const u64 *ext[OGB_MAX_RANKS];
+	u32 per;                         // reads per rank: rank r owns indices [r*per, (r+1)*per)
+	u32 per_magic;                   // ceil(2^32 / per), clamped
+	u32 cap;                         // slots per read (same on every rank)
+	u32 nranks;
+};
+
+__device__ __forceinline__ u32 owner_of(const GraphView &G, u32 idx)
+{
+	if (G.nranks == 1) return 0;
+	u32 r = __umulhi(idx, G.per_magic);
+	while ((r + 1) * G.per <= idx) r++;
+	while (r * G.per > idx) r--;
+	return r;
+}
+__device__ __forceinline__ const u64 *slot_base(const GraphView &G, u32 r, u32 idx) { return G.slots[r] + (u64)(idx - r * G.per) * G.cap; }
+
+// Heavy nodes (repeats): the cap edges in the slot region and the spilled ones are gathered in ext.
+__global__ void __launch_bounds__(256) k_heavy_move(u64 *__restrict__ slots, const u32 *__restrict__ deg, u32 lo, u32 hi, u32 cap,
+                                                   u64 *__restrict__ ext, u64 ext_cap, u32 *__restrict__ fill, u64 *ctr)
 {
 	const u32 u = lo + blockIdx.x * blockDim.x + threadIdx.x;
 	if (u >= hi) return;
 	const u32 d = deg[u];
-	nodes[u] = d ? (((base + pos[u - lo]) << OGB_DEG_BITS) | d) : 0;
+	if (d <= cap) return;
+	const u64 off = atomicAdd(ctr + CTR_EXT_CURSOR, (u64)d);
+	if (off + d > ext_cap) { atomicAdd(ctr + CTR_SCRATCH_FAIL, 1ull); return; }
+	u64 *s = slots + (u64)(u - lo) * cap;
+	for (u32 k = 0; k < cap; k++) ext[off + k] = s[k];
 	fill[u - lo] = cap;
+	s[0] = off;
 }
-
-// Spilled edges of heavy nodes (degree > cap) go straight to their final range, behind the first
-// `cap` edges that k_sort_nodes copies from the slot region.
-__global__ void __launch_bounds__(256) k_place_overflow(const u32 *__restrict__ ov_q, const u64 *__restrict__ ov_e, u64 n_over,
-                                                        const u64 *__restrict__ nodes, u64 *__restrict__ edges, u32 *__restrict__ fill, u32 lo)
+__global__ void __launch_bounds__(256) k_heavy_place(const u32 *__restrict__ ov_q, const u64 *__restrict__ ov_e, u64 n_over, const u64 *__restrict__ slots,
+                                                    u32 lo, u32 cap, u64 *__restrict__ ext, u32 *__restrict__ fill)
 {
 	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_over) return;
 	const u32 u = ov_q[i];
-	const u64 nd = nodes[u];
-	const u32 p = atomicAdd(fill + (u - lo), 1u);
-	if (p < (u32)(nd & OGB_DEG_MASK)) edges[(nd >> OGB_DEG_BITS) + p] = ov_e[i];
-}
-
-// In-place ascending bitonic sort of n u64 keys in shared memory by one warp (n <= cap, cap a power
-// of two; the tail is padded with ~0).
-__device__ __forceinline__ void warp_sort(u64 *buf, u32 n, u32 lane)
-{
-	u32 m = 32;
-	while (m < n) m <<= 1;
-	for (u32 i = n + lane; i < m; i += 32) buf[i] = ~0ull;
-	__syncwarp();
-	for (u32 k = 2; k <= m; k <<= 1) {
-		for (u32 jj = k >> 1; jj > 0; jj >>= 1) {
-			for (u32 t = lane; t < (m >> 1); t += 32) {
-				u32 i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
-				u32 l = i | jj;
-				bool up = (i & k) == 0;
-				u64 x = buf[i], y = buf[l];
-				if ((x > y) == up) { buf[i] = y; buf[l] = x; }
-			}
-			__syncwarp();
-		}
-	}
-}
-
-// Ascending bitonic sort of one u64 per lane with shuffles (pad unused lanes with ~0).
-__device__ __forceinline__ u64 warp_sort32(u64 v, u32 lane)
-{
-	#pragma unroll
-	for (u32 k = 2; k <= 32; k <<= 1) {
-		#pragma unroll
-		for (u32 jj = k >> 1; jj > 0; jj >>= 1) {
-			u64 o = __shfl_xor_sync(0xFFFFFFFFu, v, jj);
-			bool keep_min = ((lane & jj) == 0) == ((lane & k) == 0);
-			v = (keep_min == (v < o)) ? v : o;
-		}
-	}
-	return v;
-}
-
-// Per-node sort by (offset, dst, orient) = integer order of the edge word (OverlapGraph.cpp:563 plus
-// the deterministic tie-break of SURVEY.md App. B.1), fused with the move from the slot staging
-// area to the dense adjacency array. One warp per node: shuffles up to 32 edges, shared memory up to
-// OGB_EC; larger nodes are copied unsorted and listed for k_sort_big.
-__global__ void __launch_bounds__(OGB_WARPS * 32) k_sort_nodes(const u64 *__restrict__ nodes, const u64 *__restrict__ slots_e, u64 *__restrict__ edges,
-                                                               u32 lo, u32 hi, u32 cap, u32 *__restrict__ big_list, u32 big_cap, u64 *ctr)
-{
-	__shared__ u64 s_buf[OGB_WARPS][OGB_EC];
-	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const u32 gw = blockIdx.x * OGB_WARPS + wib, nwarps = gridDim.x * OGB_WARPS;
-	for (u32 u = lo + gw; u < hi; u += nwarps) {
-		const u64 nd = __ldg(nodes + u);
-		const u32 n = (u32)(nd & OGB_DEG_MASK);
-		if (n == 0) continue;
-		const u64 *src = slots_e + (u64)(u - lo) * cap;
-		u64 *dst = edges + (nd >> OGB_DEG_BITS);
-		const u32 ns = n < cap ? n : cap;                                    // edges still in the slot region
-		if (n <= 32 && n <= cap) {
-			u64 v = lane < n ? src[lane] : ~0ull;
-			v = warp_sort32(v, lane);
-			if (lane < n) dst[lane] = v;
-		} else if (n <= OGB_EC) {
-			u64 *buf = s_buf[wib];
-			for (u32 i = lane; i < ns; i += 32) buf[i] = src[i];
-			for (u32 i = ns + lane; i < n; i += 32) buf[i] = dst[i];         // spilled part, already placed
-			warp_sort(buf, n, lane);
-			for (u32 i = lane; i < n; i += 32) dst[i] = buf[i];
-			__syncwarp();
-		} else {
-			for (u32 i = lane; i < ns; i += 32) dst[i] = src[i];
-			if (lane == 0) {
-				const u64 p = atomicAdd(ctr + CTR_BIG_NODES, 1ull);
-				if (p < big_cap) big_list[p] = u;
-			}
-		}
-	}
-}
-
-// Nodes with more than OGB_EC edges (repeats): one block per node, bitonic sort in global memory
-// through a power-of-two scratch range.
-__global__ void __launch_bounds__(256) k_sort_big(const u64 *__restrict__ nodes, u64 *__restrict__ edges, const u32 *__restrict__ big_list, u32 n_big,
-                                                  u64 *__restrict__ scratch, u64 scratch_cap, u64 *ctr)
-{
-	__shared__ u64 s_base;
-	for (u32 it = blockIdx.x; it < n_big; it += gridDim.x) {
-		const u64 nd = nodes[big_list[it]];
-		const u32 n = (u32)(nd & OGB_DEG_MASK);
-		u64 *a = edges + (nd >> OGB_DEG_BITS);
-		u32 m = 1;
-		while (m < n) m <<= 1;
-		__syncthreads();
-		if (threadIdx.x == 0) s_base = atomicAdd(ctr + CTR_SCRATCH_CURSOR, (u64)m);
-		__syncthreads();
-		if (s_base + m > scratch_cap) { if (threadIdx.x == 0) atomicAdd(ctr + CTR_SCRATCH_FAIL, 1ull); continue; }
-		u64 *buf = scratch + s_base;
-		for (u32 i = threadIdx.x; i < m; i += blockDim.x) buf[i] = i < n ? a[i] : ~0ull;
-		__syncthreads();
-		for (u32 k = 2; k <= m; k <<= 1)
-			for (u32 jj = k >> 1; jj > 0; jj >>= 1) {
-				for (u32 t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
-					u32 i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1)), l = i | jj;
-					bool up = (i & k) == 0;
-					u64 x = buf[i], y = buf[l];
-					if ((x > y) == up) { buf[i] = y; buf[l] = x; }
-				}
-				__syncthreads();
-			}
-		for (u32 i = threadIdx.x; i < n; i += blockDim.x) a[i] = buf[i];
-	}
+	const u64 off = slots[(u64)(u - lo) * cap];
+	ext[off + atomicAdd(fill + (u - lo), 1u)] = ov_e[i];
 }
 
 // superReadID decode + contained bitmap: one thread per read.
@@ -805,17 +737,26 @@ __global__ void k_contained_bitmap(const u64 *__restrict__ sup, u32 n, u32 *__re
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5: transitive-edge marking, one warp per node (OverlapGraph.cpp:574-615).
-// The neighbour set (destination node -> INPLAY/ELIMINATED) is an open-addressing set in shared
-// memory (degree <= 256) or in a global scratch pool (larger). Pivots are walked sequentially in
-// adjacency order; the adjacency of an in-play pivot is scanned by all lanes.
+// K5: transitive-edge marking, one warp per node (OverlapGraph.cpp:574-615), straight on the unsorted
+// slot regions. The reference walks the node's edges in sorted order (:563) and skips the ones whose
+// destination is no longer INPLAY (:583); states only ever go INPLAY -> ELIMINATED, so "the next
+// pivot" is the smallest (offset, dst, orient, slot) above the current one whose destination is still
+// INPLAY: a warp min-reduction (two REDUX + one ballot) per ACTIVE pivot -- about two per node --
+// replaces the per-node sort. The neighbour set (destination node -> INPLAY/ELIMINATED) is an open-
+// addressing set in shared memory (degree <= 256) or in a global scratch pool (larger).
+//
+// The kernel is bound by the chain of dependent fetches own list -> pivot list -> next pivot list.
+// Nodes of degree <= 32 (one edge per lane, in registers) therefore fetch their two likely pivots at
+// once: the first edge overall and the first edge leaving the node on the other side -- the latter is
+// almost always the second and last active pivot. The fetch is only a prefetch into registers; the
+// walk itself follows the reference order.
 // ------------------------------------------------------------------------------------------------
 struct MarkArgs {
-	const u64 *nodes;
-	const u64 *edges;
-	unsigned char *eflag;       // per edge: 1 = eliminated in the marking of its own node
-	u32 lo, hi;                 // node indices [lo, hi) handled by this rank
-	u32 *scratch_keys;          // global pool for big nodes
+	GraphView G;
+	u64 *own_slots, *own_ext;   // this rank's slot region / heavy lists: flag bits are written here
+	u32 lo, hi, rank;           // node indices [lo, hi) of this rank
+	u32 *cnt;                   // K6: survivors per own node, by idx - lo
+	u32 *scratch_keys;          // global pool for the neighbour sets of big nodes
 	unsigned char *scratch_state;
 	u64 scratch_cap;
 	u64 *ctr;
@@ -843,76 +784,141 @@ __device__ __forceinline__ int set_find(const u32 *keys, u32 capmask, u32 key)
 	}
 }
 
+// Lane holding the smallest (w, lane) among the lanes with cand set, -1 if there is none. w < 2^64-2^32.
+__device__ __forceinline__ int pick_min(bool cand, u64 w)
+{
+	const u32 hi = cand ? (u32)(w >> 32) : 0xFFFFFFFFu;
+	const u32 mh = __reduce_min_sync(0xFFFFFFFFu, hi);
+	if (mh == 0xFFFFFFFFu) return -1;
+	const bool c2 = cand && hi == mh;
+	const u32 lo = c2 ? (u32)w : 0xFFFFFFFFu;
+	const u32 ml = __reduce_min_sync(0xFFFFFFFFu, lo);
+	return __ffs(__ballot_sync(0xFFFFFFFFu, c2 && lo == ml)) - 1;
+}
+
+// Adjacency of pivot v (1-based id) against the neighbour set: a neighbour reached through v on the
+// strand v was entered on becomes ELIMINATED (:588-596). pre: the pivot's degree and this lane's entry
+// were fetched ahead. twin = 1 + position of an entry (v, self) in v's list (0 if there is none): K6
+// needs v's verdict on self for the edges that survive, and those are always pivots. Returns v's degree.
+__device__ __forceinline__ u32 scan_pivot(const GraphView &G, u32 v, u32 t1, u32 self, const u32 *keys, unsigned char *st, u32 capmask, u32 lane,
+                                          bool pre, u32 dpre, u64 fpre, u32 &twin)
+{
+	const u32 idx = v - 1, r = owner_of(G, idx);
+	const u64 *base = slot_base(G, r, idx);
+	const u32 dv = pre ? dpre : G.deg[r][idx];
+	if (dv > G.cap) { base = G.ext[r] + base[0]; pre = false; }
+	u32 tw = 0;
+	for (u32 kk = lane; kk < dv; kk += 32) {
+		const u64 f = (pre && kk < 32) ? fpre : base[kk];
+		const u32 x = edge_dst(f);
+		if (x == self) tw = kk + 1;
+		if (compatible(t1, edge_orient(f))) {
+			const int sw = set_find(keys, capmask, x);
+			if (sw >= 0 && st[sw] == 1) st[sw] = 2;
+		}
+	}
+	twin = __reduce_max_sync(0xFFFFFFFFu, tw);
+	__syncwarp();
+	return dv;
+}
+
 __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 {
 	__shared__ u32 s_keys[OGB_WARPS][OGB_SETCAP];
 	__shared__ unsigned char s_state[OGB_WARPS][OGB_SETCAP];
+	const GraphView &G = A.G;
 	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const u32 gw = blockIdx.x * OGB_WARPS + wib, nwarps = gridDim.x * OGB_WARPS;
+	const u32 *own_deg = G.deg[A.rank];
 	u64 c_entries = 0, c_pivots = 0;
 
 	for (u32 u = A.lo + gw; u < A.hi; u += nwarps) {
-		u64 nd = __ldg(A.nodes + u);
-		u32 deg = (u32)(nd & OGB_DEG_MASK);
-		if (deg == 0) continue;
-		const u64 start = nd >> OGB_DEG_BITS;
-		u32 cap = 64;
-		while (cap < 2 * deg) cap <<= 1;
-		u32 *keys; unsigned char *st;
-		if (cap <= OGB_SETCAP) { keys = s_keys[wib]; st = s_state[wib]; }
-		else {
-			u64 base = 0;
-			if (lane == 0) base = atomicAdd(A.ctr + CTR_SCRATCH_CURSOR, (u64)cap);
-			base = __shfl_sync(0xFFFFFFFFu, base, 0);
-			if (base + cap > A.scratch_cap) { if (lane == 0) atomicAdd(A.ctr + CTR_SCRATCH_FAIL, 1ull); continue; }
-			keys = A.scratch_keys + base; st = A.scratch_state + base;
-		}
-		const u32 capmask = cap - 1;
-		for (u32 i = lane; i < cap; i += 32) keys[i] = 0;
-		__syncwarp();
-		// mark all neighbours INPLAY (:577-578); a lane keeps the set slot of its own edge
-		u64 e = 0; int sk = -1;
-		if (deg <= 32) {
-			if (lane < deg) { e = __ldg(A.edges + start + lane); sk = (int)set_insert(keys, capmask, edge_dst(e)); st[sk] = 1; }
-		} else {
-			for (u32 k = lane; k < deg; k += 32) st[set_insert(keys, capmask, edge_dst(__ldg(A.edges + start + k)))] = 1;
-		}
-		__syncwarp();
-		// Pivots in adjacency (offset) order (:580-600). The reference walks every edge and skips
-		// the ones whose destination is no longer INPLAY (:583); states only ever go INPLAY ->
-		// ELIMINATED, so "the next pivot" is simply the lowest-index edge after the current one whose
-		// destination is INPLAY now: one ballot + ffs per ACTIVE pivot (~2 per node) instead of a
-		// dependent shared-memory round trip per edge.
-		for (u32 cb = 0; cb < deg; cb += 32) {
-			const u32 k = cb + lane;
-			if (deg > 32) {
-				e = 0; sk = -1;
-				if (k < deg) { e = __ldg(A.edges + start + k); sk = set_find(keys, capmask, edge_dst(e)); }
+		const u32 d = own_deg[u];
+		if (d == 0) continue;
+		u64 *own = A.own_slots + (u64)(u - A.lo) * G.cap;
+		if (d > G.cap) own = A.own_ext + own[0];
+
+		if (d <= 32) {
+			// ---- one edge per lane, a 64-slot set
+			u32 *keys = s_keys[wib]; unsigned char *st = s_state[wib];
+			const u32 capmask = 63;
+			keys[lane] = 0; keys[lane + 32] = 0;
+			__syncwarp();
+			const bool have = lane < d;
+			const u64 e = have ? own[lane] : 0, w = edge_key(e);
+			int sk = 0;
+			if (have) { sk = (int)set_insert(keys, capmask, edge_dst(e)); st[sk] = 1; }   // all neighbours INPLAY (:577-578)
+			__syncwarp();
+			const int a = pick_min(have, w);                                  // first pivot: nothing is eliminated yet
+			const u64 ea = __shfl_sync(0xFFFFFFFFu, e, a);
+			const int b = pick_min(have && ((edge_orient(e) ^ edge_orient(ea)) & 1), w);   // first edge on the other side of u
+			const u64 eb = __shfl_sync(0xFFFFFFFFu, e, b < 0 ? 0 : b);
+			u32 da, db = 0; u64 fa, fb = 0;
+			{
+				const u32 idx = edge_dst(ea) - 1, r = owner_of(G, idx);
+				da = G.deg[r][idx]; fa = slot_base(G, r, idx)[lane];
 			}
-			int cur = -1;
+			if (b >= 0) {
+				const u32 idx = edge_dst(eb) - 1, r = owner_of(G, idx);
+				db = G.deg[r][idx]; fb = slot_base(G, r, idx)[lane];
+			}
+			u32 tw, mytw = 0;
+			c_pivots++; c_entries += scan_pivot(G, edge_dst(ea), edge_orient(ea), u + 1, keys, st, capmask, lane, true, da, fa, tw);
+			if ((int)lane == a) mytw = tw;
+			u64 cw = edge_key(ea); int ck = a;
 			for (;;) {
-				u32 m = __ballot_sync(0xFFFFFFFFu, k < deg && (int)lane > cur && st[sk] == 1);
-				if (m == 0) break;
-				cur = __ffs(m) - 1;
-				u64 ei = __shfl_sync(0xFFFFFFFFu, e, cur);
-				u32 v = edge_dst(ei), t1 = edge_orient(ei);
-				u64 ndv = __ldg(A.nodes + (v - 1));
-				u32 degv = (u32)(ndv & OGB_DEG_MASK);
-				u64 startv = ndv >> OGB_DEG_BITS;
-				c_pivots++; c_entries += degv;
-				for (u32 kk = lane; kk < degv; kk += 32) {
-					u64 f = __ldg(A.edges + startv + kk);
-					if (compatible(t1, edge_orient(f))) {
-						int sw = set_find(keys, capmask, edge_dst(f));
-						if (sw >= 0 && st[sw] == 1) st[sw] = 2;              // :588-596
-					}
+				const int p = pick_min(have && st[sk] == 1 && (w > cw || (w == cw && (int)lane > ck)), w);
+				if (p < 0) break;
+				const u64 ep = __shfl_sync(0xFFFFFFFFu, e, p);
+				c_pivots++; c_entries += scan_pivot(G, edge_dst(ep), edge_orient(ep), u + 1, keys, st, capmask, lane, p == b, db, fb, tw);
+				if ((int)lane == p) mytw = tw;
+				cw = edge_key(ep); ck = p;
+			}
+			const bool elim = have && st[sk] == 2;                            // :601-607 (the twin half is applied in k_keep)
+			if (elim || mytw) own[lane] = e | (mytw < 4096 ? (u64)mytw << 2 : 0) | (elim ? OGB_ELIM : 0);
+		} else {
+			// ---- any degree: edges stay in memory (L1), a lane looks after entries lane, lane+32, ...
+			u32 cap = 128;
+			while (cap < 2 * d) cap <<= 1;
+			u32 *keys; unsigned char *st;
+			if (cap <= OGB_SETCAP) { keys = s_keys[wib]; st = s_state[wib]; }
+			else {
+				u64 base = 0;
+				if (lane == 0) base = atomicAdd(A.ctr + CTR_SCRATCH_CURSOR, (u64)cap);
+				base = __shfl_sync(0xFFFFFFFFu, base, 0);
+				if (base + cap > A.scratch_cap) { if (lane == 0) atomicAdd(A.ctr + CTR_SCRATCH_FAIL, 1ull); continue; }
+				keys = A.scratch_keys + base; st = A.scratch_state + base;
+			}
+			const u32 capmask = cap - 1;
+			for (u32 i = lane; i < cap; i += 32) keys[i] = 0;
+			__syncwarp();
+			for (u32 k = lane; k < d; k += 32) st[set_insert(keys, capmask, edge_dst(own[k]))] = 1;
+			__syncwarp();
+			u64 cw = 0; u32 ck = 0; bool first = true;
+			for (;;) {
+				u64 bw = ~0ull; u32 bk = 0xFFFFFFFFu;                         // this lane's smallest in-play entry above (cw, ck)
+				for (u32 k = lane; k < d; k += 32) {
+					const u64 x = edge_key(own[k]);
+					if ((first || x > cw || (x == cw && k > ck)) && x < bw && st[set_find(keys, capmask, edge_dst(x))] == 1) { bw = x; bk = k; }
 				}
+				const u32 hi = (u32)(bw >> 32);
+				const u32 mh = __reduce_min_sync(0xFFFFFFFFu, hi);
+				if (mh == 0xFFFFFFFFu) break;
+				const bool c2 = hi == mh;
+				const u32 ml = __reduce_min_sync(0xFFFFFFFFu, c2 ? (u32)bw : 0xFFFFFFFFu);
+				const bool c3 = c2 && (u32)bw == ml;
+				ck = __reduce_min_sync(0xFFFFFFFFu, c3 ? bk : 0xFFFFFFFFu);
+				cw = ((u64)mh << 32) | ml; first = false;
+				u32 tw;
+				c_pivots++; c_entries += scan_pivot(G, edge_dst(cw), edge_orient(cw), u + 1, keys, st, capmask, lane, false, 0, 0, tw);
+				if (lane == 0 && tw && tw < 4096) own[ck] |= (u64)tw << 2;
 				__syncwarp();
 			}
+			for (u32 k = lane; k < d; k += 32) {
+				const u64 x = own[k];
+				if (st[set_find(keys, capmask, edge_dst(x))] == 2) own[k] = x | OGB_ELIM;
+			}
 		}
-		// flag own edges to eliminated nodes (:601-607; the twin half is applied in k_twin_keep)
-		if (deg <= 32) { if (lane < deg) A.eflag[start + lane] = st[sk] == 2; }
-		else for (u32 k = lane; k < deg; k += 32) A.eflag[start + k] = st[set_find(keys, capmask, edge_dst(__ldg(A.edges + start + k)))] == 2;
 		__syncwarp();
 	}
 	if (lane == 0) { atomicAdd(A.ctr + CTR_PIVOT_ENTRIES, c_entries); atomicAdd(A.ctr + CTR_ACTIVE_PIVOTS, c_pivots); }
@@ -921,58 +927,62 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 // ------------------------------------------------------------------------------------------------
 // K6: an edge (u,w) survives iff it was not flagged by u's marking and its twin was not flagged by
 // w's marking (:605-606, :623-661). Marks are per destination NODE, so w's verdict on u is read off
-// any (w,u) entry of w's adjacency -- no twin pointers are needed. One warp per node, one lane per
-// edge: the few edges that u itself kept (~2) look up w's verdict concurrently; survivors are
-// written compacted to surv[start .. start+cnt) as final records, so that the copy kernel after
-// the scan touches survivors only.
+// any (w,u) entry of w's list -- no twin pointers are needed, and K5 has left the position of such an
+// entry in the edge word (an edge u kept was a pivot of u, whose scan met it): one word is fetched
+// from w's list; the list is searched only when the position is missing. One warp per node, one lane
+// per edge. Survivors get OGB_KEEP, the first OGB_SURV of a node are also staged in surv[] for
+// k_emit_small; cnt[u] feeds the scan that positions them in the final list.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(OGB_WARPS * 32) k_twin_keep(const u64 *__restrict__ nodes, const u64 *__restrict__ edges,
-                                                              const unsigned char *__restrict__ eflag, ogb_edge *__restrict__ surv,
-                                                              u32 *__restrict__ cnt, u32 lo, u32 hi, u64 *ctr)
+#define OGB_SURV 4
+__global__ void __launch_bounds__(OGB_WARPS * 32) k_keep(MarkArgs A, u64 *__restrict__ surv)
 {
+	const GraphView &G = A.G;
 	const u32 lane = threadIdx.x & 31;
 	const u32 gw = blockIdx.x * OGB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * OGB_WARPS;
+	const u32 *own_deg = G.deg[A.rank];
 	u32 c_nodes = 0, c_asym = 0;
-	for (u32 u = lo + gw; u < hi; u += nwarps) {
-		u64 nd = __ldg(nodes + u);
-		u32 deg = (u32)(nd & OGB_DEG_MASK);
-		u64 start = nd >> OGB_DEG_BITS;
+	for (u32 u = A.lo + gw; u < A.hi; u += nwarps) {
+		const u32 d = own_deg[u];
 		u32 total = 0;
-		for (u32 kb = 0; kb < deg; kb += 32) {
-			const u32 k = kb + lane;
-			bool keep = k < deg && !eflag[start + k];
-			u64 e = 0;
-			if (keep) {
-				// every lane that still holds an edge looks its twin up on its own: the (few) lookups of a
-				// node run concurrently, each as batches of four independent loads
-				e = __ldg(edges + start + k);
-				const u64 ndw = __ldg(nodes + (edge_dst(e) - 1));
-				const u32 degw = (u32)(ndw & OGB_DEG_MASK);
-				const u64 *aw = edges + (ndw >> OGB_DEG_BITS);
-				const unsigned char *fw = eflag + (ndw >> OGB_DEG_BITS);
-				int at = -1;
-				for (u32 x = 0; x < degw && at < 0; x += 4) {
-					u64 f[4];
-					#pragma unroll
-					for (int q = 0; q < 4; q++) f[q] = x + q < degw ? __ldg(aw + x + q) : 0;
-					#pragma unroll
-					for (int q = 3; q >= 0; q--) if (edge_dst(f[q]) == u + 1) at = (int)x + q;
+		if (d) {
+			u64 *own = A.own_slots + (u64)(u - A.lo) * G.cap;
+			if (d > G.cap) own = A.own_ext + own[0];
+			for (u32 kb = 0; kb < d; kb += 32) {
+				const u32 k = kb + lane;
+				u64 e = 0;
+				bool keep = false;
+				if (k < d) { e = own[k]; keep = !(e & OGB_ELIM); }
+				if (keep) {
+					const u32 idx = edge_dst(e) - 1, r = owner_of(G, idx), tw = edge_twin(e);
+					const u64 *aw = slot_base(G, r, idx);
+					const u32 dw = G.deg[r][idx];
+					u64 fat = tw && tw <= G.cap ? aw[tw - 1] : 0;                // fetched along with the degree
+					if (dw > G.cap) { aw = G.ext[r] + aw[0]; fat = 0; }
+					if (tw && fat == 0 && tw <= dw) fat = aw[tw - 1];
+					bool found = tw && tw <= dw && edge_dst(fat) == u + 1;
+					for (u32 x = 0; x < dw && !found; x += 4) {                  // no position: search, batches of four independent loads
+						u64 f[4];
+						#pragma unroll
+						for (int q = 0; q < 4; q++) f[q] = x + q < dw ? aw[x + q] : 0;
+						#pragma unroll
+						for (int q = 3; q >= 0; q--) if (edge_dst(f[q]) == u + 1) { found = true; fat = f[q]; }
+					}
+					if (!found) c_asym++;
+					else keep = !(fat & OGB_ELIM);
+					if (keep) own[k] = e | OGB_KEEP;
 				}
-				if (at < 0) c_asym++;
-				else keep = fw[at] == 0;
+				const u32 bal = __ballot_sync(0xFFFFFFFFu, keep);
+				if (keep) {
+					const u32 at = total + __popc(bal & ((1u << lane) - 1));
+					if (at < OGB_SURV) surv[(u64)(u - A.lo) * OGB_SURV + at] = e;
+				}
+				total += __popc(bal);
 			}
-			const u32 bal = __ballot_sync(0xFFFFFFFFu, keep);
-			if (keep) {
-				ogb_edge r;
-				r.src = u + 1; r.dst = edge_dst(e); r.offset = (uint16_t)edge_offset(e); r.orient = (uint8_t)edge_orient(e); r.reserved = 0;
-				surv[start + total + __popc(bal & ((1u << lane) - 1))] = r;
-			}
-			total += __popc(bal);
 		}
-		if (lane == 0) { cnt[u] = total; c_nodes += total > 0; }
+		if (lane == 0) { A.cnt[u - A.lo] = total; c_nodes += total > 0; }
 	}
-	if (lane == 0 && c_nodes) atomicAdd(ctr + CTR_NODES_FINAL, (u64)c_nodes);
-	if (c_asym) atomicAdd(ctr + CTR_ASYMMETRIC, (u64)c_asym);
+	if (lane == 0 && c_nodes) atomicAdd(A.ctr + CTR_NODES_FINAL, (u64)c_nodes);
+	if (c_asym) atomicAdd(A.ctr + CTR_ASYMMETRIC, (u64)c_asym);
 }
 
 // Exclusive scan of u32 counts into u64 offsets: (1) per-block sums, (2) one block scans the sums,
@@ -1035,41 +1045,78 @@ __global__ void __launch_bounds__(256) k_scan_apply(const u32 *__restrict__ cnt,
 	for (int i = 0; i < 8; i++) { u64 p = base + threadIdx.x * 8 + i; if (p < n) out[p] = run; run += v[i]; }
 }
 
-// Final edge records, sorted by (src, offset, dst, orient) = node order x adjacency order: one
-// thread per node copies its cnt[u] survivors from surv[start..] to out[pos[u]..].
-__global__ void __launch_bounds__(256) k_compact(const u64 *__restrict__ nodes, const ogb_edge *__restrict__ surv, const u32 *__restrict__ cnt,
-                                                 const u64 *__restrict__ pos, ogb_edge *__restrict__ out, u32 lo, u32 hi, u64 sub, u64 add)
+__device__ __forceinline__ ogb_edge edge_record(u32 src, u64 e)
 {
-	u32 u = lo + blockIdx.x * blockDim.x + threadIdx.x;
-	if (u >= hi) return;
-	u32 c = cnt[u];
-	if (c == 0) return;
-	u64 start = __ldg(nodes + u) >> OGB_DEG_BITS, p = pos[u] - sub + add;     // multi-rank: position inside this rank's padded segment
-	for (u32 i = 0; i < c; i++) out[p + i] = surv[start + i];
+	ogb_edge r;
+	r.src = src; r.dst = edge_dst(e); r.offset = (uint16_t)edge_offset(e); r.orient = (uint8_t)edge_orient(e); r.reserved = 0;
+	return r;
 }
 
-// Pre-reduction edges as records (tests / keep_pre): one warp per node, position = start.
-__global__ void __launch_bounds__(OGB_WARPS * 32) k_export_pre(const u64 *__restrict__ nodes, const u64 *__restrict__ edges,
-                                                               const u64 *__restrict__ pos, ogb_edge *__restrict__ out, u32 n)
+// Final records of the nodes with at most OGB_SURV survivors (nearly all: a reduced node keeps ~2
+// edges): one thread per node sorts the staged words and writes them at pos[u - lo] (+ add).
+__global__ void __launch_bounds__(256) k_emit_small(const u64 *__restrict__ surv, const u32 *__restrict__ cnt, const u64 *__restrict__ pos,
+                                                    ogb_edge *__restrict__ out, u32 lo, u32 hi, u64 add)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (lo + i >= hi) return;
+	const u32 c = cnt[i];
+	if (c == 0 || c > OGB_SURV) return;
+	u64 w[OGB_SURV];
+	#pragma unroll
+	for (int q = 0; q < OGB_SURV; q++) w[q] = q < (int)c ? surv[(u64)i * OGB_SURV + q] : ~0ull;
+	// staged in slot order, so a stable sort keeps the slot tie-break of equal keys
+	#pragma unroll
+	for (int x = 1; x < OGB_SURV; x++)
+		#pragma unroll
+		for (int y = x; y > 0; y--)
+			if (edge_key(w[y]) < edge_key(w[y - 1]) && w[y] != ~0ull) { const u64 t = w[y]; w[y] = w[y - 1]; w[y - 1] = t; }
+	ogb_edge *dst = out + pos[i] + add;
+	#pragma unroll
+	for (int q = 0; q < OGB_SURV; q++) if (q < (int)c) dst[q] = edge_record(lo + i + 1, w[q]);
+}
+
+// Edge records of the own nodes in the reference order (src, offset, dst, orient): the surviving
+// edges of the nodes with more than min_cnt survivors (ALL = false) or every edge (ALL = true;
+// pre-reduction list for tests / keep_pre). One warp per node; pos[u - lo] (+ add) is where the node's
+// records start. Entries are ranked by counting the smaller ones -- shuffles up to degree 32, a plain
+// double loop beyond.
+template <bool ALL>
+__global__ void __launch_bounds__(OGB_WARPS * 32) k_emit(const u64 *__restrict__ own_slots, const u64 *__restrict__ own_ext, const u32 *__restrict__ deg,
+                                                         const u32 *__restrict__ cnt, const u64 *__restrict__ pos, ogb_edge *__restrict__ out,
+                                                         u32 lo, u32 hi, u32 cap, u64 add, u32 min_cnt)
 {
 	const u32 lane = threadIdx.x & 31;
 	const u32 gw = blockIdx.x * OGB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * OGB_WARPS;
-	for (u32 u = gw; u < n; u += nwarps) {
-		u64 nd = __ldg(nodes + u);
-		u32 deg = (u32)(nd & OGB_DEG_MASK);
-		u64 start = nd >> OGB_DEG_BITS, p = pos[u];
-		for (u32 k = lane; k < deg; k += 32) {
-			u64 e = __ldg(edges + start + k);
-			ogb_edge r;
-			r.src = u + 1; r.dst = edge_dst(e); r.offset = (uint16_t)edge_offset(e); r.orient = (uint8_t)edge_orient(e); r.reserved = 0;
-			out[p + k] = r;
+	for (u32 u = lo + gw; u < hi; u += nwarps) {
+		if (!ALL && cnt[u - lo] <= min_cnt) continue;
+		const u32 d = deg[u];
+		if (d == 0) continue;
+		const u64 *own = own_slots + (u64)(u - lo) * cap;
+		if (d > cap) own = own_ext + own[0];
+		ogb_edge *dst = out + pos[u - lo] + add;
+		if (d <= 32) {
+			const u64 e = lane < d ? own[lane] : 0, w = edge_key(e);
+			const bool s = lane < d && (ALL || (e & OGB_KEEP));
+			u32 rank = 0;
+			for (u32 m = __ballot_sync(0xFFFFFFFFu, s); m; m &= m - 1) {
+				const u32 b = __ffs(m) - 1;
+				const u64 o = __shfl_sync(0xFFFFFFFFu, w, b);
+				rank += (o < w) || (o == w && b < lane);
+			}
+			if (s) dst[rank] = edge_record(u + 1, e);
+		} else {
+			for (u32 k = lane; k < d; k += 32) {
+				const u64 e = own[k], w = edge_key(e);
+				if (!(ALL || (e & OGB_KEEP))) continue;
+				u32 rank = 0;
+				for (u32 k2 = 0; k2 < d; k2++) {
+					const u64 e2 = own[k2], w2 = edge_key(e2);
+					if (ALL || (e2 & OGB_KEEP)) rank += (w2 < w) || (w2 == w && k2 < k);
+				}
+				dst[rank] = edge_record(u + 1, e);
+			}
 		}
 	}
-}
-__global__ void k_degrees(const u64 *__restrict__ nodes, u32 n, u32 *__restrict__ cnt)
-{
-	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) cnt[i] = (u32)(nodes[i] & OGB_DEG_MASK);
 }
 
 // ------------------------------------------------------------------------------------------------
