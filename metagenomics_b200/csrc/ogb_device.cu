@@ -449,10 +449,10 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 	c->nb = (u32)nb;
 	OGB_TRY(c->slots.ensure(nb * OGB_BWORDS));
 	{
-		// measured on B200 (profiles/r1_notes.md): with the index L2-resident (83 MB at 1.3 M reads) the summary
-		// costs 4 % of a step; once the index outgrows the 126 MB L2 it removes most HBM bucket fetches
+		// The per-bucket summary (4 B per bucket) lets the probe drop the windows that cannot have an entry before
+		// the bucket fetch and compact the rest (PendQueue); OGB_SUMMARY=0 turns it off (experiment knob).
 		const char *e = getenv("OGB_SUMMARY");
-		c->use_summary = e ? atoi(e) != 0 : nb * OGB_BWORDS * sizeof(u32) > (96ull << 20);
+		c->use_summary = e ? atoi(e) != 0 : true;
 	}
 	if (c->use_summary) OGB_TRY(c->summary.ensure(nb));
 	c->launches = 0;

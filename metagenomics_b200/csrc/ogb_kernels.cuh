@@ -40,6 +40,15 @@ typedef unsigned int u32;
 #define OGB_SLOTS 10            // slots per bucket (64 bytes = one HBM burst)
 #define OGB_BWORDS 16           // u32 words per bucket
 #define OGB_WARPS 8             // warps per block in the scan / mark kernels
+// Resident blocks per SM the probe / verify kernels are compiled for (register cap). Both are latency-bound:
+// 6 blocks (40 registers, no spills) measured 5-15 % faster than 5 (48); 7-8 (32 registers, spills) slower
+// (profiles/r1_notes.md).
+#ifndef OGB_PROBE_MINBLOCKS
+#define OGB_PROBE_MINBLOCKS 6
+#endif
+#ifndef OGB_VERIFY_MINBLOCKS
+#define OGB_VERIFY_MINBLOCKS 6
+#endif
 #define OGB_SETCAP 512          // per-warp neighbour set slots in shared memory (degree <= 256)
 
 enum { MODE_OVERLAP = 0, MODE_CONTAIN = 1 };
@@ -135,13 +144,16 @@ __device__ __forceinline__ u64 hash2(u64 k0, u64 k1)
 	return acc;
 }
 
-// Hash of the h bases starting at base p of a packed strand.
-template <class LD> __device__ __forceinline__ u64 key_hash(const u64 *__restrict__ w, u32 p, u32 h)
+// Hash of the h bases starting at base p of a packed strand. lead = the key's first 16 bases (fewer when
+// h < 16): the hash partition is a function of lead alone, so that the sharded table build can tell
+// from one funnel shift whether a key belongs to this rank's partition (partition_of).
+template <class LD> __device__ __forceinline__ u64 key_hash(const u64 *__restrict__ w, u32 p, u32 h, u32 &lead)
 {
 	const u32 wi = p >> 5, sh = (p & 31) << 1;
 	const u64 a = LD::ld(w + wi), b = LD::ld(w + wi + 1);
 	u64 k0 = funnel(a, b, sh);
-	if (h <= 32) return hash2(k0 & (~0ULL << (64 - 2 * h)), 0);
+	if (h <= 32) { k0 &= ~0ULL << (64 - 2 * h); lead = (u32)(k0 >> 32); return hash2(k0, 0); }
+	lead = (u32)(k0 >> 32);
 	const u64 c = LD::ld(w + wi + 2);
 	u64 k1 = funnel(b, c, sh);
 	if (h <= 64) return hash2(k0, k1 & (~0ULL << (128 - 2 * h)));
@@ -150,6 +162,13 @@ template <class LD> __device__ __forceinline__ u64 key_hash(const u64 *__restric
 	p += 64;
 	for (; rem > 32; rem -= 32, p += 32) acc = mix64(acc, extract32<LD>(w, p));
 	return mix64(acc, extract32<LD>(w, p) & (~0ULL << (64 - 2 * rem)));
+}
+// lead of the key alone (two loads, one funnel shift)
+template <class LD> __device__ __forceinline__ u32 key_lead(const u64 *__restrict__ w, u32 p, u32 h)
+{
+	u64 k0 = extract32<LD>(w, p);
+	if (h < 32) k0 &= ~0ULL << (64 - 2 * h);
+	return (u32)(k0 >> 32);
 }
 
 __device__ __forceinline__ u32 hash_fp(u64 hash) { u32 f = (u32)hash & 0xFFFFu; return f ? f : 1u; }   // 16 bits; 0 is reserved for "empty"
@@ -160,13 +179,13 @@ __device__ __forceinline__ u32 hash_fp(u64 hash) { u32 f = (u32)hash & 0xFFFFu; 
 #define OGB_SPILLED 0x80000000u
 __device__ __forceinline__ u32 summary_bits(u32 fp) { return (1u << min(fp & 31u, 30u)) | (1u << min((fp >> 5) & 31u, 30u)); }
 
-// Two-level range reduction of the high hash half: partition = floor(x*P / 2^32), bucket inside the
-// partition from the fractional part. With one partition this is plain floor(x*nb / 2^32).
-__device__ __forceinline__ u32 bucket_of(u64 hash, const Table &T, u32 &part)
+// Partition = range reduction of a multiplicative hash of the key's lead; bucket inside the partition =
+// range reduction of the high hash half. With one partition this is plain floor(x*nb / 2^32).
+__device__ __forceinline__ u32 partition_of(u32 lead, const Table &T) { return T.nparts == 1 ? 0 : __umulhi(lead * 0x9E3779B1u, T.nparts); }
+__device__ __forceinline__ u32 bucket_of(u64 hash, u32 lead, const Table &T, u32 &part)
 {
-	const u64 t = (u64)(u32)(hash >> 32) * T.nparts;
-	part = (u32)(t >> 32);
-	return part * T.part_buckets + __umulhi((u32)t, T.part_buckets);
+	part = partition_of(lead, T);
+	return part * T.part_buckets + __umulhi((u32)(hash >> 32), T.part_buckets);
 }
 // next bucket of the probe sequence: wraps at the end of the partition (pend = one past its last bucket)
 __device__ __forceinline__ u32 next_bucket(u32 b, u32 pend, const Table &T) { return b + 1 == pend ? pend - T.part_buckets : b + 1; }
@@ -218,6 +237,26 @@ __device__ __forceinline__ bool region_equal_aligned(const u64 *__restrict__ p, 
 		++wp;
 		const u64 p1 = wp <= ep ? LDP::ld(wp) : 0;
 		diff |= (funnel(p0, p1, sh) ^ LDQ::ld(q + (k >> 5))) & (~0ULL << (64 - 2 * rem));
+	}
+	return diff == 0;
+}
+
+// p[pa..pa+len) == q[0..len) for strands of exactly NW words each where the p region runs to the end of
+// its strand (every overlap check on equal-length reads has this shape): straight-line code, no trip
+// count that differs between the lanes of a warp. Words past the strand are not loaded.
+template <int NW>
+__device__ __forceinline__ bool suffix_equals_prefix(const u64 *__restrict__ p, u32 pa, const u64 *__restrict__ q, u32 len)
+{
+	const u32 wi = pa >> 5, sh = (pa & 31) << 1;
+	u64 x[NW + 1];
+	#pragma unroll
+	for (int i = 0; i <= NW; i++) x[i] = wi + i < NW ? __ldg(p + wi + i) : 0;
+	u64 diff = 0;
+	#pragma unroll
+	for (int i = 0; i < NW; i++) {
+		const int r = min(max((int)len - 32 * i, 0), 32);                    // bases of word i inside the region
+		const u64 m = r ? ~0ULL << (64 - 2 * r) : 0;
+		diff |= (funnel(x[i], x[i + 1], sh) ^ __ldg(q + i)) & m;
 	}
 	return diff == 0;
 }
@@ -324,11 +363,12 @@ __global__ void k_hash_insert(ReadStore R, Table T)
 	read_geom(R, idx, off, L);
 	const u64 *w = R.words + off + (o >> 1) * padded_words(L);
 	u32 p = (o & 1) ? L - T.h : 0;
-	u64 hash = key_hash<LdGlobal>(w, p, T.h);
+	if (T.nparts > 1 && partition_of(key_lead<LdGlobal>(w, p, T.h), T) != T.my_part) return;   // another rank builds that partition
+	u32 lead;
+	u64 hash = key_hash<LdGlobal>(w, p, T.h, lead);
 	const u32 fp = hash_fp(hash), val = ((idx + 1) << 2) | o;
 	u32 part;
-	u32 b = bucket_of(hash, T, part);
-	if (T.nparts > 1 && part != T.my_part) return;                           // another rank builds that partition
+	u32 b = bucket_of(hash, lead, T, part);
 	const u32 pend = (part + 1) * T.part_buckets;
 	for (;;) {
 		u32 *w = T.slots + (u64)b * OGB_BWORDS;
@@ -471,13 +511,88 @@ __device__ __forceinline__ void append_matches(const ScanArgs &A, QueueCursor &Q
 	Q.qused += total;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256) k_probe(ScanArgs A)
+// Windows that passed the per-bucket summary wait in a small per-warp queue in shared memory and are
+// taken out 32 at a time: the bucket fetch, the fingerprint compare and the candidate append -- two
+// thirds of the kernel's instructions -- then run with every lane busy instead of with the ~45 % of the
+// lanes whose window can have an entry at all (30x coverage; fewer at low coverage).
+#define OGB_PENDQ 64
+struct PendQueue {
+	u32 b[OGB_WARPS][OGB_PENDQ];      // home bucket
+	u32 f[OGB_WARPS][OGB_PENDQ];      // fingerprint | j << 16
+	u32 q[OGB_WARPS][OGB_PENDQ];      // query read index
+};
+
+// Bucket fetch + fingerprint compare + candidate append for one window per lane (active lanes only).
+__device__ __forceinline__ void probe_buckets(const ScanArgs &A, QueueCursor &Q, u32 lane, bool active, u32 b, u32 fj, u32 qi, u64 &c_sectors)
 {
-	const u32 lane = threadIdx.x & 31;
+	const u32 fp = fj & 0xFFFFu;
+	const u64 tag = (u64)(fj >> 16) << 32;
+	u32 pend = 0;
+	while (__any_sync(0xFFFFFFFFu, active)) {
+		u32 w[OGB_BWORDS];
+		u32 mm = 0;                                                          // slots of this lane's bucket whose fingerprint matches
+		if (active) {
+			load_bucket(A.T.slots, b, w);
+			c_sectors++;
+			mm = match_bucket(w, fp);
+			// K1 fills a bucket front to back, so "last slot taken" = full = the key may continue in the next bucket
+			active = w[5 + OGB_SLOTS - 1] != 0;
+			if (active) {
+				if (pend == 0) pend = (b / A.T.part_buckets + 1) * A.T.part_buckets;
+				b = next_bucket(b, pend, A.T);
+			}
+		}
+		if (__any_sync(0xFFFFFFFFu, mm != 0)) append_matches(A, Q, lane, mm, w, qi, tag);
+	}
+}
+
+// Pushes this lane's window if it passed the filter; when 32 or more are pending, the warp probes 32.
+__device__ __forceinline__ void pend_push(const ScanArgs &A, PendQueue &P, u32 wib, u32 &plen, QueueCursor &Q, u32 lane, bool pass, u32 b, u32 fj, u32 qi, u64 &c_sectors)
+{
+	const u32 bal = __ballot_sync(0xFFFFFFFFu, pass);
+	if (pass) {
+		const u32 at = plen + __popc(bal & ((1u << lane) - 1));
+		P.b[wib][at] = b; P.f[wib][at] = fj; P.q[wib][at] = qi;
+	}
+	plen += __popc(bal);
+	__syncwarp();
+	if (plen >= 32) {
+		plen -= 32;
+		const u32 pb = P.b[wib][plen + lane], pf = P.f[wib][plen + lane], pq = P.q[wib][plen + lane];
+		__syncwarp();
+		probe_buckets(A, Q, lane, true, pb, pf, pq, c_sectors);
+	}
+}
+__device__ __forceinline__ void pend_drain(const ScanArgs &A, PendQueue &P, u32 wib, u32 plen, QueueCursor &Q, u32 lane, u64 &c_sectors)
+{
+	if (plen == 0) return;
+	const bool act = lane < plen;
+	const u32 pb = act ? P.b[wib][lane] : 0, pf = act ? P.f[wib][lane] : 0, pq = act ? P.q[wib][lane] : 0;
+	probe_buckets(A, Q, lane, act, pb, pf, pq, c_sectors);
+}
+
+// Key of window j of strand s -> home bucket, fingerprint | j<<16, and the summary verdict.
+__device__ __forceinline__ bool window_key(const ScanArgs &A, const u64 *__restrict__ s, u32 j, u32 &b, u32 &fj)
+{
+	u32 part, lead;
+	const u64 hash = key_hash<LdGlobal>(s, j, A.T.h, lead);
+	b = bucket_of(hash, lead, A.T, part);
+	const u32 fp = hash_fp(hash);
+	fj = fp | (j << 16);
+	if (!A.T.summary) return true;
+	const u32 sm = ld_na32(A.T.summary + b), need = summary_bits(fp);
+	return (sm & need) == need || (sm & OGB_SPILLED);                        // else: no entry with this fingerprint, no fetch
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, OGB_PROBE_MINBLOCKS) k_probe(ScanArgs A)
+{
+	__shared__ PendQueue P;
+	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 	const u32 h = A.T.h;
 	u64 c_probes = 0, c_sectors = 0;
+	u32 plen = 0;
 	QueueCursor Q = {0, 0, 0};                                               // this warp's piece of the candidate queue (warp-uniform)
 
 	for (u32 qi = A.lo + gw; qi < A.hi; qi += nwarps) {
@@ -489,32 +604,12 @@ __global__ void __launch_bounds__(256) k_probe(ScanArgs A)
 		c_probes += nwin;
 		for (u32 jb = 1; jb <= nwin; jb += 32) {
 			const u32 j = jb + lane;
-			bool active = j <= nwin;
-			u32 b = 0, fp = 0, pend = 0;
-			if (active) {
-				u32 part;
-				const u64 hash = key_hash<LdGlobal>(s, j, h); b = bucket_of(hash, A.T, part); fp = hash_fp(hash); pend = (part + 1) * A.T.part_buckets;
-				if (A.T.summary) {
-					const u32 sm = ld_na32(A.T.summary + b), need = summary_bits(fp);
-					active = (sm & need) == need || (sm & OGB_SPILLED);          // else: no entry with this fingerprint, no fetch
-				}
-			}
-			const u64 tag = (u64)j << 32;
-			while (__any_sync(0xFFFFFFFFu, active)) {
-				u32 w[OGB_BWORDS];
-				u32 mm = 0;                                                  // slots of this lane's bucket whose fingerprint matches
-				if (active) {
-					load_bucket(A.T.slots, b, w);
-					c_sectors++;
-					mm = match_bucket(w, fp);
-					// K1 fills a bucket front to back, so "last slot taken" = full = the key may continue in the next bucket
-					active = w[5 + OGB_SLOTS - 1] != 0;
-					if (active) b = next_bucket(b, pend, A.T);
-				}
-				if (__any_sync(0xFFFFFFFFu, mm != 0)) append_matches(A, Q, lane, mm, w, qi, tag);
-			}
+			u32 b = 0, fj = 0;
+			const bool pass = j <= nwin && window_key(A, s, j, b, fj);
+			pend_push(A, P, wib, plen, Q, lane, pass, b, fj, qi, c_sectors);
 		}
 	}
+	pend_drain(A, P, wib, plen, Q, lane, c_sectors);
 	queue_pad(A, Q, lane);
 	for (int d = 16; d > 0; d >>= 1) c_sectors += __shfl_down_sync(0xFFFFFFFFu, c_sectors, d);
 	if (lane == 0) { atomicAdd(A.ctr + CTR_PROBES, c_probes); atomicAdd(A.ctr + CTR_SECTORS, c_sectors); }
@@ -524,48 +619,27 @@ __global__ void __launch_bounds__(256) k_probe(ScanArgs A)
 // of all reads of the launch are flattened over the threads, x -> (read, j) by an exact multiply-
 // shift division, so every lane of every warp owns a window.
 template <int MODE>
-__global__ void __launch_bounds__(256) k_probe_uniform(ScanArgs A, u32 nwin, u64 div_magic)
+__global__ void __launch_bounds__(256, OGB_PROBE_MINBLOCKS) k_probe_uniform(ScanArgs A, u32 nwin, u64 div_magic)
 {
-	const u32 lane = threadIdx.x & 31;
-	const u32 h = A.T.h;
+	__shared__ PendQueue P;
+	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const u32 total = (A.hi - A.lo) * nwin;                                  // < 2^32: a launch covers at most 2^16 reads
 	const u32 rounds = (total + 31) >> 5;
 	const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 	const u32 stride = 2 * A.R.uniform_pw;
 	u64 c_sectors = 0;
+	u32 plen = 0;
 	QueueCursor Q = {0, 0, 0};
 
 	for (u32 rd = gw; rd < rounds; rd += nwarps) {
 		const u32 x = rd * 32 + lane;
-		bool active = x < total;
 		const u32 qr = nwin == 1 ? x : (u32)__umul64hi(div_magic, (u64)x);  // x / nwin (Lemire: exact for 32-bit x, nwin > 1)
 		const u32 j = x - qr * nwin + 1, qi = A.lo + qr;
-		u32 b = 0, fp = 0, pend = 0;
-		if (active) {
-			u32 part;
-			const u64 hash = key_hash<LdGlobal>(A.R.words + (u64)qi * stride, j, h);
-			b = bucket_of(hash, A.T, part); fp = hash_fp(hash); pend = (part + 1) * A.T.part_buckets;
-			if (A.T.summary) {
-				if (A.T.summary) {
-					const u32 sm = ld_na32(A.T.summary + b), need = summary_bits(fp);
-					active = (sm & need) == need || (sm & OGB_SPILLED);          // else: no entry with this fingerprint, no fetch
-				}
-			}
-		}
-		const u64 tag = (u64)j << 32;
-		while (__any_sync(0xFFFFFFFFu, active)) {
-			u32 w[OGB_BWORDS];
-			u32 mm = 0;
-			if (active) {
-				load_bucket(A.T.slots, b, w);
-				c_sectors++;
-				mm = match_bucket(w, fp);
-				active = w[5 + OGB_SLOTS - 1] != 0;                          // full bucket: the key may continue in the next one
-				if (active) b = next_bucket(b, pend, A.T);
-			}
-			if (__any_sync(0xFFFFFFFFu, mm != 0)) append_matches(A, Q, lane, mm, w, qi, tag);
-		}
+		u32 b = 0, fj = 0;
+		const bool pass = x < total && window_key(A, A.R.words + (u64)qi * stride, j, b, fj);
+		pend_push(A, P, wib, plen, Q, lane, pass, b, fj, qi, c_sectors);
 	}
+	pend_drain(A, P, wib, plen, Q, lane, c_sectors);
 	queue_pad(A, Q, lane);
 	for (int d = 16; d > 0; d >>= 1) c_sectors += __shfl_down_sync(0xFFFFFFFFu, c_sectors, d);
 	if (lane == 0) atomicAdd(A.ctr + CTR_SECTORS, c_sectors);
@@ -577,7 +651,7 @@ __global__ void __launch_bounds__(256) k_probe_uniform(ScanArgs A, u32 nwin, u64
 // the same one or two nodes -- their deg[] increments are aggregated with __match_any_sync into one
 // atomic per distinct node instead of ~26 serialised same-address atomics.
 template <int MODE>
-__global__ void __launch_bounds__(256) k_verify(ScanArgs A)
+__global__ void __launch_bounds__(256, OGB_VERIFY_MINBLOCKS) k_verify(ScanArgs A)
 {
 	const u64 total = min(*A.cand_cursor, A.cand_cap);
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(A.ctr + CTR_CAND_MAX, *A.cand_cursor);
@@ -623,7 +697,10 @@ __global__ void __launch_bounds__(256) k_verify(ScanArgs A)
 						orient = o == 1 ? 0 : 1;  // :553,:555
 						offset = L1 - h - j;      // L1 - overlap, overlap = h + j
 					}
-					ok = fits && region_equal_aligned<LdGlobal, LdGlobal>(pp, pa, qq, len);
+					if (!fits) ok = false;
+					else if (A.R.uniform_pw == 4) ok = suffix_equals_prefix<4>(pp, pa, qq, len);      // 65..128 bp
+					else if (A.R.uniform_pw == 6) ok = suffix_equals_prefix<6>(pp, pa, qq, len);      // 129..192 bp
+					else ok = region_equal_aligned<LdGlobal, LdGlobal>(pp, pa, qq, len);
 				}
 			}
 		}
@@ -1130,9 +1207,9 @@ __global__ void k_lookup(ReadStore R, Table T, const u64 *__restrict__ keys, u32
 	u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= n_keys) return;
 	const u64 *key = keys + k * (kw + 2);
-	u64 hash = key_hash<LdGlobal>(key, 0, T.h);
-	u32 part;
-	u32 fp = hash_fp(hash), b = bucket_of(hash, T, part), c = 0;
+	u32 part, lead;
+	u64 hash = key_hash<LdGlobal>(key, 0, T.h, lead);
+	u32 fp = hash_fp(hash), b = bucket_of(hash, lead, T, part), c = 0;
 	const u32 pend = (part + 1) * T.part_buckets;
 	for (;;) {
 		u32 w[OGB_BWORDS];
