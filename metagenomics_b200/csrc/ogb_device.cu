@@ -5,7 +5,7 @@
 //   ogb_reads_upload*   H2D + K0                         [Read::setRead, Read.cpp:75-82]
 //   ogb_hash_build      K1                               [HashTable::insertDataset, HashTable.cpp:50-80]
 //   ogb_mark_contained  K2 (+ allreduce-max)             [OverlapGraph::markContainedReads, OverlapGraph.cpp:225-290]
-//   ogb_build_graph     K3 -> barrier -> K5 (peer reads) -> barrier -> K6 (peer reads) -> C3   [buildOverlapGraphFromHashTable, OverlapGraph.cpp:107-210]
+//   ogb_build_graph     K3 -> [C1] -> K5 -> [C2] -> K6 -> [C3]   [buildOverlapGraphFromHashTable, OverlapGraph.cpp:107-210]; C* only on several ranks
 // All buffers are grow-only pools owned by the context, so a repeated build allocates nothing.
 
 #include "ogb_internal.h"
@@ -83,8 +83,8 @@ template <class T> struct Pool {
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-// d_xchg layout (u64 words): per-rank verdict vectors, the ranks' IPC handles (3 x 64 bytes each), scratch
-enum { XCHG_PER_RANK = 8, XCHG_HANDLES = XCHG_PER_RANK * OGB_MAX_RANKS, XCHG_SCRATCH = XCHG_HANDLES + 24 * OGB_MAX_RANKS, XCHG_WORDS = XCHG_SCRATCH + 8 };
+// d_xchg layout (u64 words): per-rank verdict vectors, scratch
+enum { OGB_MAX_RANKS = 64, XCHG_PER_RANK = 8, XCHG_SCRATCH = XCHG_PER_RANK * OGB_MAX_RANKS, XCHG_WORDS = XCHG_SCRATCH + 8 };
 
 enum { EV_BEGIN = 0, EV_PACK0, EV_PACK1, EV_HASH0, EV_HASH1, EV_CONT0, EV_CONT1, EV_OVL0, EV_OVL1, EV_XPRE1, EV_MARK1, EV_RED1, EV_K3A, EV_K3B, EV_T0, EV_T1, EV_COUNT };
 
@@ -118,11 +118,12 @@ struct ogb_context {
 	Pool<unsigned char> scratch_state;
 	Pool<u32> cnt, scratch_keys;
 	Pool<ogb_edge> fin, pre, fin_stage;
-	// the adjacency: per-read slot regions, degrees, heavy lists -- the three pools the other ranks map (GraphView)
+	// the adjacency: per-read slot regions, degrees, heavy lists (GraphView)
 	Pool<u64> slots_e, ext;
 	Pool<u32> deg;
-	void *peer_ptr[3][OGB_MAX_RANKS] = {};   // [slots_e, deg, ext][rank]: CUDA IPC mappings of the peers' pools
-	bool shared_ready = false;
+	// several ranks: every rank's lists packed to 4-byte entries + node records + ELIM bits, allgathered
+	Pool<u64> nodes;
+	Pool<u32> adj32, ebits;
 	// scan staging: candidate queue of one chunk, spill list of heavy nodes
 	Pool<u32> cand_q, fill, ov_q;    // cand_q / cand_v hold two ping-pong queues of cand_cap entries
 	Pool<u64> cand_v, ov_e;
@@ -247,9 +248,6 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	if (c->stream2) cudaStreamSynchronize(c->stream2);
-	for (int r = 0; r < OGB_MAX_RANKS; r++)
-		for (int k = 0; k < 3; k++) if (c->peer_ptr[k][r]) cudaIpcCloseMemHandle(c->peer_ptr[k][r]);
-	cudaGetLastError();
 	if (c->comm) g_nccl.CommDestroy(c->comm);
 	c->words.release(); c->meta.release(); c->stage_bytes.release(); c->stage_offs.release(); c->stage_lens.release();
 	c->slots.release(); c->summary.release(); c->sup.release(); c->contained.release(); c->pos.release();
@@ -260,7 +258,7 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	if (c->d_cursor) cudaFree(c->d_cursor);
 	if (c->d_xchg) cudaFree(c->d_xchg);
 	c->cand_q.release(); c->deg.release(); c->fill.release(); c->ov_q.release();
-	c->cand_v.release(); c->slots_e.release(); c->ext.release(); c->ov_e.release();
+	c->cand_v.release(); c->slots_e.release(); c->ext.release(); c->ov_e.release(); c->nodes.release(); c->adj32.release(); c->ebits.release();
 	if (c->h_ctr) cudaFreeHost(c->h_ctr);
 	for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 128; i++) if (c->ev_pk[i]) cudaEventDestroy(c->ev_pk[i]);
@@ -683,84 +681,11 @@ static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *
 	return OGB_OK;
 }
 
-// Device-side barrier over all ranks: a one-word allreduce on the build stream. It completes on a rank
-// only after every rank has enqueued it behind its own earlier work, so whatever the peers wrote
-// before their barrier is in their HBM when the kernels behind ours read it over NVLink.
-static int rank_barrier(ogb_context *c)
-{
-	if (c->nranks > 1) NCCL_TRY(g_nccl.AllReduce(c->d_xchg + XCHG_SCRATCH, c->d_xchg + XCHG_SCRATCH + 1, 1, NCCL_UINT64, 0 /*ncclSum*/, c->comm, c->stream));
-	return OGB_OK;
-}
-
-static void close_peers(ogb_context *c)
-{
-	for (int r = 0; r < OGB_MAX_RANKS; r++)
-		for (int k = 0; k < 3; k++)
-			if (c->peer_ptr[k][r]) { cudaIpcCloseMemHandle(c->peer_ptr[k][r]); c->peer_ptr[k][r] = nullptr; }
-	cudaGetLastError();
-}
-
-// The three pools the other ranks read in K5 / K6 -- slot regions, degrees, heavy lists. Every rank
-// calls this with the same sizes (they derive from collective values only), so growing them is a
-// collective decision: peers unmap, everybody reallocates, the CUDA IPC handles are allgathered and
-// the peers' pools are mapped again. Steady state (sizes unchanged) costs nothing.
-static int ensure_shared(ogb_context *c, size_t need_slots, size_t need_deg, size_t need_ext)
-{
-	if (need_slots <= c->slots_e.cap && need_deg <= c->deg.cap && need_ext <= c->ext.cap && c->shared_ready) return OGB_OK;
-	const int G = c->nranks;
-	if (G > 1 && c->shared_ready) {
-		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		close_peers(c);
-		OGB_TRY(rank_barrier(c));                                            // nobody frees while a peer still has the pool mapped
-		CUDA_TRY(cudaStreamSynchronize(c->stream));
-	}
-	c->shared_ready = false;
-	OGB_TRY(c->slots_e.ensure(need_slots + need_slots / 4));
-	OGB_TRY(c->deg.ensure(need_deg));
-	OGB_TRY(c->ext.ensure(std::max<size_t>(need_ext + need_ext / 4, 1 << 16)));
-	if (G > 1) {
-		if (G > OGB_MAX_RANKS) { ogb_set_error("at most %d ranks", OGB_MAX_RANKS); return OGB_E_ARG; }
-		cudaIpcMemHandle_t mine[3], all[3 * OGB_MAX_RANKS];
-		void *ptrs[3] = {c->slots_e.p, c->deg.p, c->ext.p};
-		for (int k = 0; k < 3; k++) CUDA_TRY(cudaIpcGetMemHandle(&mine[k], ptrs[k]));
-		static_assert(sizeof(mine) == 3 * 64, "cudaIpcMemHandle_t is 64 bytes");
-		u64 *slot = c->d_xchg + XCHG_HANDLES + (size_t)c->rank * 24;
-		CUDA_TRY(cudaMemcpyAsync(slot, mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
-		NCCL_TRY(g_nccl.AllGather(slot, c->d_xchg + XCHG_HANDLES, 24, NCCL_UINT64, c->comm, c->stream));
-		CUDA_TRY(cudaMemcpyAsync(all, c->d_xchg + XCHG_HANDLES, (size_t)G * sizeof mine, cudaMemcpyDeviceToHost, c->stream));
-		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		for (int r = 0; r < G; r++) {
-			if (r == c->rank) continue;
-			for (int k = 0; k < 3; k++) {
-				cudaError_t e = cudaIpcOpenMemHandle(&c->peer_ptr[k][r], all[3 * r + k], cudaIpcMemLazyEnablePeerAccess);
-				if (e != cudaSuccess) {
-					ogb_set_error("cannot map rank %d's adjacency over NVLink (cudaIpcOpenMemHandle: %s); all ranks must be GPUs of one node with peer access",
-					              r, cudaGetErrorString(e));
-					cudaGetLastError();
-					return OGB_E_CUDA;
-				}
-			}
-		}
-	}
-	c->shared_ready = true;
-	return OGB_OK;
-}
-
-static GraphView graph_view(const ogb_context *c)
+static GraphView graph_view(const ogb_context *c, u32 lo)
 {
 	GraphView g;
-	memset(&g, 0, sizeof g);
-	const u64 per = ((u64)c->n + c->nranks - 1) / c->nranks;
-	for (int r = 0; r < c->nranks; r++) {
-		const bool me = r == c->rank;
-		g.slots[r] = me ? c->slots_e.p : (const u64 *)c->peer_ptr[0][r];
-		g.deg[r] = me ? c->deg.p : (const u32 *)c->peer_ptr[1][r];
-		g.ext[r] = me ? c->ext.p : (const u64 *)c->peer_ptr[2][r];
-	}
-	g.per = (u32)std::max<u64>(per, 1);
-	g.per_magic = (u32)std::min<u64>(0xFFFFFFFFull, ((1ull << 32) + g.per - 1) / g.per);
-	g.cap = c->slot_cap;
-	g.nranks = (u32)c->nranks;
+	g.slots = c->slots_e.p; g.deg = c->deg.p; g.ext = c->ext.p; g.lo = lo; g.cap = c->slot_cap;
+	g.nodes = c->nodes.p; g.adj32 = c->adj32.p; g.ebits = c->ebits.p;
 	return g;
 }
 
@@ -811,7 +736,9 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	std::vector<u64> seg_cnt(G, 0);
 	for (int attempt = 0;; attempt++) {
 		if (attempt == 16) { ogb_set_error("ogb_build_graph: staging pools kept overflowing"); return OGB_E_CAPACITY; }
-		OGB_TRY(ensure_shared(c, per * c->slot_cap + 64, (size_t)n + 1, 0));   // +64: K5 fetches 32 slots of a pivot before it knows its degree
+		OGB_TRY(c->slots_e.ensure(per * c->slot_cap + 64));                 // +64: K5 fetches 32 slots of a pivot before it knows its degree
+		OGB_TRY(c->deg.ensure((size_t)n + 1));
+		OGB_TRY(c->ext.ensure(1 << 16));
 		OGB_TRY(ctr_zero(c));
 		if (nloc) CUDA_TRY(cudaMemsetAsync(c->deg.p + lo, 0, (size_t)nloc * sizeof(u32), c->stream));
 		CUDA_TRY(cudaEventRecord(c->ev[EV_K3A], c->stream));
@@ -849,7 +776,8 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		c->st.max_degree = verdict[2];
 		c->st.overflow_reads = n_heavy;
 		if (verdict[1]) {                                                    // repeats: some rank has nodes with more than slot_cap edges
-			OGB_TRY(ensure_shared(c, per * c->slot_cap + 64, (size_t)n + 1, need_ext));
+			(void)need_ext;
+			OGB_TRY(c->ext.ensure(n_over + n_heavy * c->slot_cap + 64));
 			if (n_over) {
 				k_heavy_move<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->slots_e.p, c->deg.p, lo, hi, c->slot_cap, c->ext.p, c->ext.cap, c->fill.p, c->d_ctr);
 				k_heavy_place<<<(unsigned)((n_over + 255) / 256), 256, 0, c->stream>>>(c->ov_q.p, c->ov_e.p, n_over, c->slots_e.p, lo, c->slot_cap, c->ext.p, c->fill.p);
@@ -866,7 +794,24 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	c->st.edges_pre = exact_edges;
 	c->n_pre = exact_edges;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL1], c->stream));
-	OGB_TRY(rank_barrier(c));                                                // every rank's slot regions are complete
+
+	// ---- C1 (several ranks): a pivot can live on any rank. Every rank packs its lists to 4-byte entries
+	// (k_pack_adj) at its segment of the common stride; one in-place allgather each for the entries and
+	// the node records. The ELIM bitmap (C2) has one bit per packed entry.
+	u64 seg_stride = 0;
+	if (G > 1) {
+		for (int r = 0; r < G; r++) seg_stride = std::max(seg_stride, seg_cnt[r]);
+		seg_stride = (seg_stride + 255) & ~255ull;
+		OGB_TRY(c->adj32.ensure(std::max<u64>(seg_stride * G, 1)));
+		OGB_TRY(c->nodes.ensure(per * G + 1));
+		OGB_TRY(c->ebits.ensure(std::max<u64>(seg_stride * G / 32, 1)));
+		if (seg_stride) CUDA_TRY(cudaMemsetAsync(c->ebits.p + seg_stride / 32 * c->rank, 0, seg_stride / 32 * sizeof(u32), c->stream));
+		k_pack_adj<<<grid_for(c, (const void *)k_pack_adj, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(graph_view(c, lo), hi, c->pos.p, seg_stride * c->rank, c->nodes.p, c->adj32.p);
+		CUDA_TRY(cudaGetLastError());
+		c->launches++;
+		if (seg_stride) NCCL_TRY(g_nccl.AllGather(c->adj32.p + seg_stride * c->rank, c->adj32.p, seg_stride, NCCL_UINT32, c->comm, c->stream));
+		NCCL_TRY(g_nccl.AllGather(c->nodes.p + per * c->rank, c->nodes.p, per, NCCL_UINT64, c->comm, c->stream));
+	}
 	CUDA_TRY(cudaEventRecord(c->ev[EV_XPRE1], c->stream));
 
 	const u32 cap_now = c->slot_cap;
@@ -891,14 +836,15 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 
 	// ---- K5
 	MarkArgs m;
-	m.G = graph_view(c);
-	m.own_slots = c->slots_e.p; m.own_ext = c->ext.p; m.lo = lo; m.hi = hi; m.rank = (u32)c->rank; m.cnt = c->cnt.p;
+	m.G = graph_view(c, lo);
+	m.hi = hi; m.cnt = c->cnt.p;
 	if (c->scratch_keys.cap == 0) { OGB_TRY(c->scratch_keys.ensure(1 << 20)); OGB_TRY(c->scratch_state.ensure(1 << 20)); }
 	for (int attempt = 0;; attempt++) {
 		if (attempt == 4) { ogb_set_error("ogb_build_graph: neighbour-set scratch kept overflowing"); return OGB_E_CAPACITY; }
 		OGB_TRY(ctr_zero(c));
 		m.scratch_keys = c->scratch_keys.p; m.scratch_state = c->scratch_state.p; m.scratch_cap = c->scratch_keys.cap; m.ctr = c->d_ctr;
-		k_mark<<<grid_for(c, (const void *)k_mark, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
+		if (G == 1) k_mark<false><<<grid_for(c, (const void *)k_mark<false>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
+		else k_mark<true><<<grid_for(c, (const void *)k_mark<true>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
 		CUDA_TRY(cudaGetLastError());
 		c->launches++;
 		if (c->st.max_degree * 2 <= OGB_SETCAP) break;                      // no node can have used the scratch pool
@@ -908,10 +854,11 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		OGB_TRY(c->scratch_keys.ensure(need)); OGB_TRY(c->scratch_state.ensure(need));
 	}
 	CUDA_TRY(cudaEventRecord(c->ev[EV_MARK1], c->stream));
-	OGB_TRY(rank_barrier(c));                                                // every rank's verdicts are in its edge words
+	if (G > 1 && seg_stride) NCCL_TRY(g_nccl.AllGather(c->ebits.p + seg_stride / 32 * c->rank, c->ebits.p, seg_stride / 32, NCCL_UINT32, c->comm, c->stream));   // C2
 
 	// ---- K6
-	k_keep<<<grid_for(c, (const void *)k_keep, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m, c->surv.p);
+	if (G == 1) k_keep<false><<<grid_for(c, (const void *)k_keep<false>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m, c->surv.p);
+	else k_keep<true><<<grid_for(c, (const void *)k_keep<true>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m, c->surv.p);
 	CUDA_TRY(cudaGetLastError());
 	c->launches++;
 	OGB_TRY(exclusive_scan(c, c->cnt.p, nloc, c->pos.p, c->d_tot + 1));

@@ -740,11 +740,17 @@ __global__ void __launch_bounds__(256, OGB_VERIFY_MINBLOCKS) k_verify(ScanArgs A
 
 // ------------------------------------------------------------------------------------------------
 // The adjacency as the verify kernel leaves it -- and as K5 / K6 consume it, without any copy or sort:
-// read idx of rank r owns slots[r][(idx - r*per)*cap .. +cap) holding deg[r][idx] edge words in
-// discovery order. A heavy node (deg > cap) keeps its whole list in ext[r], at the word offset stored
-// in its first slot (k_heavy_move / k_heavy_place). On several ranks slots[r] / deg[r] / ext[r] of the
-// other ranks are peer mappings (CUDA IPC, i.e. loads over NVLink): a pivot's adjacency or a twin's
-// verdict is read where its owner wrote it, so the pre-reduction adjacency is never exchanged.
+// read idx of this rank owns slots[(idx - lo)*cap .. +cap) holding deg[idx] edge words in discovery
+// order. A heavy node (deg > cap) keeps its whole list in ext, at the word offset stored in its first
+// slot (k_heavy_move / k_heavy_place).
+//
+// One rank (DENSE = false): a pivot's list and a twin's verdict are read straight from these slot
+// regions. Several ranks (DENSE = true): a pivot or a twin can live on any rank, so every rank packs its
+// lists into 4-byte entries dst<<1 | strand (all K5 needs of a foreign list; k_pack_adj), the packed
+// segments and node records start<<24 | deg are allgathered, and after K5 one ELIM bit per packed
+// entry. Reading the peers' slot regions in place (CUDA IPC over NVLink) was built and measured first:
+// peer reads run at 2.4 G rows/s while the mapped footprint stays within the GPU's translation reach
+// and collapse to 0.16 G rows/s beyond it (3 x 664 MB at 4 ranks), see profiles/r1_notes.md.
 //
 // The low 14 bits of an edge word are annotations (make_edge leaves them 0): bit 0 = OGB_ELIM
 // "eliminated by the marking of its own node" (K5), bit 1 = OGB_KEEP "survives the reduction" (K6),
@@ -752,29 +758,45 @@ __global__ void __launch_bounds__(256, OGB_VERIFY_MINBLOCKS) k_verify(ScanArgs A
 // owning warp with one aligned 64-bit store while other warps may be reading dst / orient / bit 0 of
 // the same word -- fields that store never changes.
 // ------------------------------------------------------------------------------------------------
-#define OGB_MAX_RANKS 16
 #define OGB_ELIM 1ull
 #define OGB_KEEP 2ull
+#define OGB_NODE_BITS 24
+#define OGB_NODE_MASK 0xFFFFFFull
 
 struct GraphView {
-	const u64 *slots[OGB_MAX_RANKS];
-	const u32 *deg[OGB_MAX_RANKS];   // indexed by global read index; rank r's array is valid on r's range
-	const u64 *ext[OGB_MAX_RANKS];
-	u32 per;                         // reads per rank: rank r owns indices [r*per, (r+1)*per)
-	u32 per_magic;                   // ceil(2^32 / per), clamped
-	u32 cap;                         // slots per read (same on every rank)
-	u32 nranks;
+	u64 *slots;                      // this rank's slot regions
+	const u32 *deg;                  // by global read index, valid on [lo, hi)
+	u64 *ext;                        // heavy lists of this rank
+	u32 lo, cap;                     // first read index of this rank; slots per read
+	// several ranks only: every rank's lists, packed
+	const u64 *nodes;                // start<<24 | deg by global read index
+	const u32 *adj32;                // dst<<1 | ((orient>>1)&1), in slot order
+	u32 *ebits;                      // one ELIM bit per packed entry
 };
 
-__device__ __forceinline__ u32 owner_of(const GraphView &G, u32 idx)
+// A pivot's list: degree + base pointer (64-bit edge words or packed entries).
+template <bool DENSE> struct PivotList { u32 dv; const u64 *b64; const u32 *b32; };
+template <bool DENSE> __device__ __forceinline__ void pivot_entry(const PivotList<DENSE> &P, u32 kk, u32 &dst, u32 &strand)
 {
-	if (G.nranks == 1) return 0;
-	u32 r = __umulhi(idx, G.per_magic);
-	while ((r + 1) * G.per <= idx) r++;
-	while (r * G.per > idx) r--;
-	return r;
+	if (DENSE) { const u32 f = P.b32[kk]; dst = f >> 1; strand = f & 1; }
+	else { const u64 f = P.b64[kk]; dst = edge_dst(f); strand = (edge_orient(f) >> 1) & 1; }
 }
-__device__ __forceinline__ const u64 *slot_base(const GraphView &G, u32 r, u32 idx) { return G.slots[r] + (u64)(idx - r * G.per) * G.cap; }
+
+// Packs the own lists for the exchange and writes the node records. One warp per node.
+__global__ void __launch_bounds__(OGB_WARPS * 32) k_pack_adj(GraphView G, u32 hi, const u64 *__restrict__ pos, u64 seg_off, u64 *__restrict__ nodes, u32 *__restrict__ adj32)
+{
+	const u32 lane = threadIdx.x & 31;
+	const u32 gw = blockIdx.x * OGB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * OGB_WARPS;
+	for (u32 u = G.lo + gw; u < hi; u += nwarps) {
+		const u32 d = G.deg[u];
+		const u64 start = seg_off + pos[u - G.lo];
+		if (lane == 0) nodes[u] = d ? (start << OGB_NODE_BITS) | d : 0;
+		if (d == 0) continue;
+		const u64 *own = G.slots + (u64)(u - G.lo) * G.cap;
+		if (d > G.cap) own = G.ext + own[0];
+		for (u32 k = lane; k < d; k += 32) { const u64 e = own[k]; adj32[start + k] = (edge_dst(e) << 1) | ((edge_orient(e) >> 1) & 1); }
+	}
+}
 
 // Heavy nodes (repeats): the cap edges in the slot region and the spilled ones are gathered in ext.
 __global__ void __launch_bounds__(256) k_heavy_move(u64 *__restrict__ slots, const u32 *__restrict__ deg, u32 lo, u32 hi, u32 cap,
@@ -830,8 +852,7 @@ __global__ void k_contained_bitmap(const u64 *__restrict__ sup, u32 n, u32 *__re
 // ------------------------------------------------------------------------------------------------
 struct MarkArgs {
 	GraphView G;
-	u64 *own_slots, *own_ext;   // this rank's slot region / heavy lists: flag bits are written here
-	u32 lo, hi, rank;           // node indices [lo, hi) of this rank
+	u32 hi;                     // node indices [G.lo, hi) of this rank
 	u32 *cnt;                   // K6: survivors per own node, by idx - lo
 	u32 *scratch_keys;          // global pool for the neighbour sets of big nodes
 	unsigned char *scratch_state;
@@ -873,32 +894,63 @@ __device__ __forceinline__ int pick_min(bool cand, u64 w)
 	return __ffs(__ballot_sync(0xFFFFFFFFu, c2 && lo == ml)) - 1;
 }
 
-// Adjacency of pivot v (1-based id) against the neighbour set: a neighbour reached through v on the
-// strand v was entered on becomes ELIMINATED (:588-596). pre: the pivot's degree and this lane's entry
-// were fetched ahead. twin = 1 + position of an entry (v, self) in v's list (0 if there is none): K6
-// needs v's verdict on self for the edges that survive, and those are always pivots. Returns v's degree.
-__device__ __forceinline__ u32 scan_pivot(const GraphView &G, u32 v, u32 t1, u32 self, const u32 *keys, unsigned char *st, u32 capmask, u32 lane,
-                                          bool pre, u32 dpre, u64 fpre, u32 &twin)
+// What a lane fetched ahead of a pivot scan: the pivot's degree (slot mode) or node record (packed
+// mode) and the lane's own entry of the list.
+struct PivotPre { u64 head; u64 f; };
+
+template <bool DENSE> __device__ __forceinline__ PivotList<DENSE> pivot_list(const GraphView &G, u32 v, bool pre, u64 head)
 {
-	const u32 idx = v - 1, r = owner_of(G, idx);
-	const u64 *base = slot_base(G, r, idx);
-	const u32 dv = pre ? dpre : G.deg[r][idx];
-	if (dv > G.cap) { base = G.ext[r] + base[0]; pre = false; }
+	PivotList<DENSE> P;
+	const u32 idx = v - 1;
+	if (DENSE) {
+		const u64 nd = pre ? head : G.nodes[idx];
+		P.dv = (u32)(nd & OGB_NODE_MASK); P.b32 = G.adj32 + (nd >> OGB_NODE_BITS); P.b64 = nullptr;
+	} else {
+		P.dv = pre ? (u32)head : G.deg[idx];
+		P.b64 = G.slots + (u64)(idx - G.lo) * G.cap; P.b32 = nullptr;
+		if (P.dv > G.cap) P.b64 = G.ext + P.b64[0];
+	}
+	return P;
+}
+
+// Adjacency of pivot v (1-based id) against the neighbour set: a neighbour reached through v on the
+// strand v was entered on becomes ELIMINATED (:588-596). pre: the list head and this lane's entry were
+// fetched ahead. twin = 1 + position of an entry (v, self) in v's list (0 if there is none): K6 needs
+// v's verdict on self for the edges that survive, and those are always pivots. Returns v's degree.
+template <bool DENSE>
+__device__ __forceinline__ u32 scan_pivot(const GraphView &G, u32 v, u32 t1, u32 self, const u32 *keys, unsigned char *st, u32 capmask, u32 lane,
+                                          bool pre, const PivotPre &pp, u32 &twin)
+{
+	const PivotList<DENSE> P = pivot_list<DENSE>(G, v, pre, pp.head);
+	if (!DENSE && P.dv > G.cap) pre = false;                                 // heavy list: the entry fetched ahead came from the slot region
 	u32 tw = 0;
-	for (u32 kk = lane; kk < dv; kk += 32) {
-		const u64 f = (pre && kk < 32) ? fpre : base[kk];
-		const u32 x = edge_dst(f);
+	for (u32 kk = lane; kk < P.dv; kk += 32) {
+		u32 x, strand;
+		if (pre && kk < 32) {
+			if (DENSE) { x = (u32)pp.f >> 1; strand = (u32)pp.f & 1; }
+			else { x = edge_dst(pp.f); strand = (edge_orient(pp.f) >> 1) & 1; }
+		} else pivot_entry<DENSE>(P, kk, x, strand);
 		if (x == self) tw = kk + 1;
-		if (compatible(t1, edge_orient(f))) {
+		if ((t1 & 1) == strand) {                                             // compatible(): the pivot is entered and left on the same strand
 			const int sw = set_find(keys, capmask, x);
 			if (sw >= 0 && st[sw] == 1) st[sw] = 2;
 		}
 	}
 	twin = __reduce_max_sync(0xFFFFFFFFu, tw);
 	__syncwarp();
-	return dv;
+	return P.dv;
 }
 
+// ELIM verdicts of one node as bits of the packed-position bitmap (several ranks only).
+__device__ __forceinline__ void publish_bits(u32 *ebits, u64 start, u32 m)
+{
+	if (m == 0) return;
+	const u64 wi = start >> 5; const u32 sh = (u32)start & 31;
+	atomicOr(ebits + wi, m << sh);
+	if (sh && (m >> (32 - sh))) atomicOr(ebits + wi + 1, m >> (32 - sh));
+}
+
+template <bool DENSE>
 __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 {
 	__shared__ u32 s_keys[OGB_WARPS][OGB_SETCAP];
@@ -906,14 +958,14 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 	const GraphView &G = A.G;
 	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const u32 gw = blockIdx.x * OGB_WARPS + wib, nwarps = gridDim.x * OGB_WARPS;
-	const u32 *own_deg = G.deg[A.rank];
 	u64 c_entries = 0, c_pivots = 0;
 
-	for (u32 u = A.lo + gw; u < A.hi; u += nwarps) {
-		const u32 d = own_deg[u];
+	for (u32 u = G.lo + gw; u < A.hi; u += nwarps) {
+		const u32 d = G.deg[u];
 		if (d == 0) continue;
-		u64 *own = A.own_slots + (u64)(u - A.lo) * G.cap;
-		if (d > G.cap) own = A.own_ext + own[0];
+		u64 *own = G.slots + (u64)(u - G.lo) * G.cap;
+		if (d > G.cap) own = G.ext + own[0];
+		const u64 ustart = DENSE ? G.nodes[u] >> OGB_NODE_BITS : 0;
 
 		if (d <= 32) {
 			// ---- one edge per lane, a 64-slot set
@@ -930,29 +982,32 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 			const u64 ea = __shfl_sync(0xFFFFFFFFu, e, a);
 			const int b = pick_min(have && ((edge_orient(e) ^ edge_orient(ea)) & 1), w);   // first edge on the other side of u
 			const u64 eb = __shfl_sync(0xFFFFFFFFu, e, b < 0 ? 0 : b);
-			u32 da, db = 0; u64 fa, fb = 0;
-			{
-				const u32 idx = edge_dst(ea) - 1, r = owner_of(G, idx);
-				da = G.deg[r][idx]; fa = slot_base(G, r, idx)[lane];
-			}
-			if (b >= 0) {
-				const u32 idx = edge_dst(eb) - 1, r = owner_of(G, idx);
-				db = G.deg[r][idx]; fb = slot_base(G, r, idx)[lane];
+			PivotPre pa, pb; pb.head = 0; pb.f = 0;
+			const u32 ia = edge_dst(ea) - 1, ib = edge_dst(eb) - 1;
+			if (DENSE) {
+				pa.head = G.nodes[ia];
+				if (b >= 0) pb.head = G.nodes[ib];
+				pa.f = lane < (u32)(pa.head & OGB_NODE_MASK) ? G.adj32[(pa.head >> OGB_NODE_BITS) + lane] : 0;
+				pb.f = lane < (u32)(pb.head & OGB_NODE_MASK) ? G.adj32[(pb.head >> OGB_NODE_BITS) + lane] : 0;
+			} else {
+				pa.head = G.deg[ia]; pa.f = (G.slots + (u64)(ia - G.lo) * G.cap)[lane];
+				if (b >= 0) { pb.head = G.deg[ib]; pb.f = (G.slots + (u64)(ib - G.lo) * G.cap)[lane]; }
 			}
 			u32 tw, mytw = 0;
-			c_pivots++; c_entries += scan_pivot(G, edge_dst(ea), edge_orient(ea), u + 1, keys, st, capmask, lane, true, da, fa, tw);
+			c_pivots++; c_entries += scan_pivot<DENSE>(G, edge_dst(ea), edge_orient(ea), u + 1, keys, st, capmask, lane, true, pa, tw);
 			if ((int)lane == a) mytw = tw;
 			u64 cw = edge_key(ea); int ck = a;
 			for (;;) {
 				const int p = pick_min(have && st[sk] == 1 && (w > cw || (w == cw && (int)lane > ck)), w);
 				if (p < 0) break;
 				const u64 ep = __shfl_sync(0xFFFFFFFFu, e, p);
-				c_pivots++; c_entries += scan_pivot(G, edge_dst(ep), edge_orient(ep), u + 1, keys, st, capmask, lane, p == b, db, fb, tw);
+				c_pivots++; c_entries += scan_pivot<DENSE>(G, edge_dst(ep), edge_orient(ep), u + 1, keys, st, capmask, lane, p == b, pb, tw);
 				if ((int)lane == p) mytw = tw;
 				cw = edge_key(ep); ck = p;
 			}
 			const bool elim = have && st[sk] == 2;                            // :601-607 (the twin half is applied in k_keep)
 			if (elim || mytw) own[lane] = e | (mytw < 4096 ? (u64)mytw << 2 : 0) | (elim ? OGB_ELIM : 0);
+			if (DENSE) { const u32 m = __ballot_sync(0xFFFFFFFFu, elim); if (lane == 0) publish_bits(G.ebits, ustart, m); }
 		} else {
 			// ---- any degree: edges stay in memory (L1), a lane looks after entries lane, lane+32, ...
 			u32 cap = 128;
@@ -972,6 +1027,7 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 			for (u32 k = lane; k < d; k += 32) st[set_insert(keys, capmask, edge_dst(own[k]))] = 1;
 			__syncwarp();
 			u64 cw = 0; u32 ck = 0; bool first = true;
+			const PivotPre none = {0, 0};
 			for (;;) {
 				u64 bw = ~0ull; u32 bk = 0xFFFFFFFFu;                         // this lane's smallest in-play entry above (cw, ck)
 				for (u32 k = lane; k < d; k += 32) {
@@ -987,13 +1043,16 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 				ck = __reduce_min_sync(0xFFFFFFFFu, c3 ? bk : 0xFFFFFFFFu);
 				cw = ((u64)mh << 32) | ml; first = false;
 				u32 tw;
-				c_pivots++; c_entries += scan_pivot(G, edge_dst(cw), edge_orient(cw), u + 1, keys, st, capmask, lane, false, 0, 0, tw);
+				c_pivots++; c_entries += scan_pivot<DENSE>(G, edge_dst(cw), edge_orient(cw), u + 1, keys, st, capmask, lane, false, none, tw);
 				if (lane == 0 && tw && tw < 4096) own[ck] |= (u64)tw << 2;
 				__syncwarp();
 			}
 			for (u32 k = lane; k < d; k += 32) {
 				const u64 x = own[k];
-				if (st[set_find(keys, capmask, edge_dst(x))] == 2) own[k] = x | OGB_ELIM;
+				if (st[set_find(keys, capmask, edge_dst(x))] == 2) {
+					own[k] = x | OGB_ELIM;
+					if (DENSE) atomicOr(G.ebits + ((ustart + k) >> 5), 1u << ((ustart + k) & 31));
+				}
 			}
 		}
 		__syncwarp();
@@ -1005,58 +1064,71 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 // K6: an edge (u,w) survives iff it was not flagged by u's marking and its twin was not flagged by
 // w's marking (:605-606, :623-661). Marks are per destination NODE, so w's verdict on u is read off
 // any (w,u) entry of w's list -- no twin pointers are needed, and K5 has left the position of such an
-// entry in the edge word (an edge u kept was a pivot of u, whose scan met it): one word is fetched
-// from w's list; the list is searched only when the position is missing. One warp per node, one lane
-// per edge. Survivors get OGB_KEEP, the first OGB_SURV of a node are also staged in surv[] for
-// k_emit_small; cnt[u] feeds the scan that positions them in the final list.
+// entry in the edge word (an edge u kept was a pivot of u, whose scan met it): one word (one rank) or
+// one bit of the exchanged bitmap (several ranks) is fetched; w's list is searched only when the
+// position is missing. One warp per node, one lane per edge. Survivors get OGB_KEEP, the first
+// OGB_SURV of a node are also staged in surv[] for k_emit_small; cnt[u] feeds the scan that positions
+// them in the final list.
 // ------------------------------------------------------------------------------------------------
 #define OGB_SURV 4
+template <bool DENSE>
 __global__ void __launch_bounds__(OGB_WARPS * 32) k_keep(MarkArgs A, u64 *__restrict__ surv)
 {
 	const GraphView &G = A.G;
 	const u32 lane = threadIdx.x & 31;
 	const u32 gw = blockIdx.x * OGB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * OGB_WARPS;
-	const u32 *own_deg = G.deg[A.rank];
 	u32 c_nodes = 0, c_asym = 0;
-	for (u32 u = A.lo + gw; u < A.hi; u += nwarps) {
-		const u32 d = own_deg[u];
+	for (u32 u = G.lo + gw; u < A.hi; u += nwarps) {
+		const u32 d = G.deg[u];
 		u32 total = 0;
 		if (d) {
-			u64 *own = A.own_slots + (u64)(u - A.lo) * G.cap;
-			if (d > G.cap) own = A.own_ext + own[0];
+			u64 *own = G.slots + (u64)(u - G.lo) * G.cap;
+			if (d > G.cap) own = G.ext + own[0];
 			for (u32 kb = 0; kb < d; kb += 32) {
 				const u32 k = kb + lane;
 				u64 e = 0;
 				bool keep = false;
 				if (k < d) { e = own[k]; keep = !(e & OGB_ELIM); }
 				if (keep) {
-					const u32 idx = edge_dst(e) - 1, r = owner_of(G, idx), tw = edge_twin(e);
-					const u64 *aw = slot_base(G, r, idx);
-					const u32 dw = G.deg[r][idx];
-					u64 fat = tw && tw <= G.cap ? aw[tw - 1] : 0;                // fetched along with the degree
-					if (dw > G.cap) { aw = G.ext[r] + aw[0]; fat = 0; }
-					if (tw && fat == 0 && tw <= dw) fat = aw[tw - 1];
-					bool found = tw && tw <= dw && edge_dst(fat) == u + 1;
-					for (u32 x = 0; x < dw && !found; x += 4) {                  // no position: search, batches of four independent loads
-						u64 f[4];
-						#pragma unroll
-						for (int q = 0; q < 4; q++) f[q] = x + q < dw ? aw[x + q] : 0;
-						#pragma unroll
-						for (int q = 3; q >= 0; q--) if (edge_dst(f[q]) == u + 1) { found = true; fat = f[q]; }
+					const u32 idx = edge_dst(e) - 1, tw = edge_twin(e);
+					bool found = false, welim = false;
+					if (DENSE) {
+						const u64 nd = G.nodes[idx];
+						const u32 dw = (u32)(nd & OGB_NODE_MASK);
+						const u64 sw = nd >> OGB_NODE_BITS;
+						u64 at = 0;
+						if (tw && tw <= dw) { found = true; at = sw + tw - 1; }
+						for (u32 x = 0; x < dw && !found; x++) if ((G.adj32[sw + x] >> 1) == u + 1) { found = true; at = sw + x; }
+						if (found) welim = (G.ebits[at >> 5] >> (at & 31)) & 1;
+					} else {
+						const u64 *aw = G.slots + (u64)(idx - G.lo) * G.cap;
+						const u32 dw = G.deg[idx];
+						u64 fat = tw && tw <= G.cap ? aw[tw - 1] : 0;            // fetched along with the degree
+						if (dw > G.cap) { aw = G.ext + aw[0]; fat = 0; }
+						if (tw && fat == 0 && tw <= dw) fat = aw[tw - 1];
+						found = tw && tw <= dw && edge_dst(fat) == u + 1;
+						for (u32 x = 0; x < dw && !found; x += 4) {              // no position: search, batches of four independent loads
+							u64 f[4];
+							#pragma unroll
+							for (int q = 0; q < 4; q++) f[q] = x + q < dw ? aw[x + q] : 0;
+							#pragma unroll
+							for (int q = 3; q >= 0; q--) if (edge_dst(f[q]) == u + 1) { found = true; fat = f[q]; }
+						}
+						welim = (fat & OGB_ELIM) != 0;
 					}
 					if (!found) c_asym++;
-					else keep = !(fat & OGB_ELIM);
+					else keep = !welim;
 					if (keep) own[k] = e | OGB_KEEP;
 				}
 				const u32 bal = __ballot_sync(0xFFFFFFFFu, keep);
 				if (keep) {
 					const u32 at = total + __popc(bal & ((1u << lane) - 1));
-					if (at < OGB_SURV) surv[(u64)(u - A.lo) * OGB_SURV + at] = e;
+					if (at < OGB_SURV) surv[(u64)(u - G.lo) * OGB_SURV + at] = e;
 				}
 				total += __popc(bal);
 			}
 		}
-		if (lane == 0) { A.cnt[u - A.lo] = total; c_nodes += total > 0; }
+		if (lane == 0) { A.cnt[u - G.lo] = total; c_nodes += total > 0; }
 	}
 	if (lane == 0 && c_nodes) atomicAdd(A.ctr + CTR_NODES_FINAL, (u64)c_nodes);
 	if (c_asym) atomicAdd(A.ctr + CTR_ASYMMETRIC, (u64)c_asym);
