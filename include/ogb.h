@@ -73,19 +73,20 @@ typedef struct ogb_stats {
 	uint64_t edges_final;      /* E_final directed edges after reduction (global) */
 	uint64_t nodes_final;      /* numberOfNodes (reads with >= 1 surviving edge) */
 	uint64_t max_degree;       /* largest pre-reduction out-degree (this rank) */
-	uint64_t overflow_reads;   /* reads that took the large-degree slow path */
+	uint64_t overflow_reads;   /* heavy nodes of this rank (degree > slots per read: list kept in the extension area) */
 	uint32_t kernel_launches;  /* kernels of this library launched by the last hash_build+build_graph */
 	uint32_t probe_launches;   /* launches of the probe kernel (one per chunk of query reads) */
 	float ms_pack;             /* K0 */
 	float ms_hash_build;       /* K1 */
 	float ms_contain;          /* K2 (+ allreduce) */
-	float ms_overlap;          /* K3 probe + verify (all chunks) and K4 node records + per-node sort */
-	float ms_exchange_pre;     /* C1 allgatherv of pre-reduction edges (0 on one GPU) */
+	float ms_overlap;          /* K3 probe + verify (all chunks), degree scan, heavy-list placement */
+	float ms_exchange_pre;     /* C1: k_pack_adj + allgather of packed lists and node records (0 on one GPU) */
 	float ms_mark;             /* K5 */
 	float ms_reduce;           /* K6 (+C2/C3) */
 	float ms_total;            /* hash_build + mark_contained + build_graph, device time */
 	float ms_scan_kernel;      /* K3 alone: all probe + verify launches */
-	float ms_probe_launch;     /* average duration of one probe launch (the roofline kernel), measured in place */
+	float ms_probe_launch;     /* average duration of the probe of one chunk (the roofline kernel(s): k_window_part + k_probe_parts, or k_probe), measured in place */
+	float ms_window_launch;    /* of which k_window_part (hash + filter + scatter to the partition queues); 0 on the direct path */
 } ogb_stats;
 
 int ogb_version(void);

@@ -27,7 +27,7 @@ class Stats(C.Structure):
         "active_pivots", "edges_final", "nodes_final", "max_degree", "overflow_reads")] + [
         ("kernel_launches", C.c_uint32), ("probe_launches", C.c_uint32)] + [(n, C.c_float) for n in (
             "ms_pack", "ms_hash_build", "ms_contain", "ms_overlap", "ms_exchange_pre", "ms_mark", "ms_reduce",
-            "ms_total", "ms_scan_kernel", "ms_probe_launch")]
+            "ms_total", "ms_scan_kernel", "ms_probe_launch", "ms_window_launch")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}

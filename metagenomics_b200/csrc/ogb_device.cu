@@ -94,6 +94,7 @@ struct ogb_context {
 	cudaStream_t stream2 = nullptr;   // verify kernels run here, overlapping the next chunk's probe
 	cudaEvent_t ev_probe[2] = {}, ev_verify[2] = {};
 	cudaEvent_t ev_pk[2 * 64] = {};   // timing pairs around the first 64 probe launches of a build
+	cudaEvent_t ev_pm[64] = {};       // ... and between k_window_part and k_probe_parts
 	u32 n_pk = 0;
 	ncclComm_t comm = nullptr;
 	cudaEvent_t ev[EV_COUNT] = {};
@@ -128,6 +129,11 @@ struct ogb_context {
 	Pool<u32> cand_q, fill, ov_q;    // cand_q / cand_v hold two ping-pong queues of cand_cap entries
 	Pool<u64> cand_v, ov_e;
 	u64 cand_cap = 0;
+	// partitioned probe (index beyond L2): per-partition window queues of one chunk
+	Pool<u32> pq_b, pq_f, pq_q;
+	u64 *d_pq_cursor = nullptr;
+	bool partitioned = false, part_chunk_set = false;
+	u64 pq_cap = 0;
 	u64 *d_cursor = nullptr;         // the two candidate-queue cursors
 	u64 *d_xchg = nullptr;           // small per-rank values exchanged with NCCL (XCHG_* layout)
 	u32 slot_cap = 64;               // slots per read (adapted to the largest degree seen)
@@ -146,7 +152,7 @@ struct ogb_context {
 	{
 		Table t;
 		t.slots = slots.p; t.summary = use_summary ? summary.p : nullptr; t.nb = nb; t.nparts = nparts; t.part_buckets = nb / nparts;
-		t.my_part = rank; t.h = h;
+		t.sub = nparts / nranks; t.my_rank = rank; t.h = h;
 		return t;
 	}
 	void shard(u32 &lo, u32 &hi) const
@@ -200,9 +206,11 @@ static int context_create_common(ogb_context **out, int device)
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (int i = 0; i < EV_COUNT; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
 	for (int i = 0; i < 128; i++) CUDA_TRY(cudaEventCreate(&c->ev_pk[i]));
+	for (int i = 0; i < 64; i++) CUDA_TRY(cudaEventCreate(&c->ev_pm[i]));
 	CUDA_TRY(cudaMalloc((void **)&c->d_ctr, CTR_COUNT * sizeof(u64)));
 	CUDA_TRY(cudaMalloc((void **)&c->d_tot, 2 * sizeof(u64)));
 	CUDA_TRY(cudaMalloc((void **)&c->d_cursor, 2 * sizeof(u64)));
+	CUDA_TRY(cudaMalloc((void **)&c->d_pq_cursor, OGB_MAXPART * sizeof(u64)));
 	CUDA_TRY(cudaMalloc((void **)&c->d_xchg, XCHG_WORDS * sizeof(u64)));
 	CUDA_TRY(cudaMemset(c->d_xchg, 0, XCHG_WORDS * sizeof(u64)));
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
@@ -256,12 +264,15 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	if (c->d_ctr) cudaFree(c->d_ctr);
 	if (c->d_tot) cudaFree(c->d_tot);
 	if (c->d_cursor) cudaFree(c->d_cursor);
+	if (c->d_pq_cursor) cudaFree(c->d_pq_cursor);
+	c->pq_b.release(); c->pq_f.release(); c->pq_q.release();
 	if (c->d_xchg) cudaFree(c->d_xchg);
 	c->cand_q.release(); c->deg.release(); c->fill.release(); c->ov_q.release();
 	c->cand_v.release(); c->slots_e.release(); c->ext.release(); c->ov_e.release(); c->nodes.release(); c->adj32.release(); c->ebits.release();
 	if (c->h_ctr) cudaFreeHost(c->h_ctr);
 	for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 128; i++) if (c->ev_pk[i]) cudaEventDestroy(c->ev_pk[i]);
+	for (int i = 0; i < 64; i++) if (c->ev_pm[i]) cudaEventDestroy(c->ev_pm[i]);
 	for (int i = 0; i < 2; i++) { if (c->ev_probe[i]) cudaEventDestroy(c->ev_probe[i]); if (c->ev_verify[i]) cudaEventDestroy(c->ev_verify[i]); }
 	if (c->stream2) cudaStreamDestroy(c->stream2);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -441,7 +452,16 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 	// One hash partition per rank: every rank inserts only the keys of its own partition (a slice of
 	// nb/G buckets that stays L2- and TLB-friendly), then the slices are allgathered. A replicated build
 	// of the whole table cost 3.8 ms at 8 ranks (TLB-bound inserts into 664 MB).
-	c->nparts = (u32)c->nranks;
+	// Partitions per rank: 1 while a rank's slice fits L2; beyond that the slice is cut into pieces of <= 48 MB, the
+	// unit the partitioned probe (k_window_part / k_probe_parts) works through at a time.
+	{
+		const u64 slice_bytes = nb * OGB_BWORDS * sizeof(u32) / c->nranks;
+		u64 sub = slice_bytes > (96ull << 20) ? (slice_bytes + (48ull << 20) - 1) / (48ull << 20) : 1;
+		const char *e = getenv("OGB_SUB_PARTITIONS");                        // experiment knob
+		if (e && atoi(e) >= 1) sub = (u64)atoi(e);
+		sub = std::max<u64>(1, std::min<u64>(sub, OGB_MAXPART / c->nranks));
+		c->nparts = (u32)(c->nranks * sub);
+	}
 	nb = (nb + c->nparts - 1) / c->nparts * c->nparts;
 	if (nb >= (1ull << 32)) { ogb_set_error("index too large"); return OGB_E_CAPACITY; }
 	c->nb = (u32)nb;
@@ -451,6 +471,13 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 		// the bucket fetch and compact the rest (PendQueue); OGB_SUMMARY=0 turns it off (experiment knob).
 		const char *e = getenv("OGB_SUMMARY");
 		c->use_summary = e ? atoi(e) != 0 : true;
+	}
+	{
+		// Probe through per-partition window queues (k_window_part_uniform + k_probe_parts) whenever the summary exists: measured
+		// faster than the direct kernel even with an L2-resident index (config 2: K3 2.21 -> 1.91 ms), and the only way to keep
+		// the bucket fetches in L2 beyond it (config 3: 24.7 -> 18.2 ms). OGB_PARTITIONED=0: direct path (experiment knob).
+		const char *e = getenv("OGB_PARTITIONED");
+		c->partitioned = e ? atoi(e) != 0 : true;
 	}
 	if (c->use_summary) OGB_TRY(c->summary.ensure(nb));
 	c->launches = 0;
@@ -464,7 +491,7 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 		c->launches++;
 	}
 	if (c->nranks > 1) {
-		const u64 pb = nb / c->nparts;
+		const u64 pb = nb / c->nranks;
 		NCCL_TRY(g_nccl.AllGather(c->slots.p + pb * OGB_BWORDS * c->rank, c->slots.p, pb * OGB_BWORDS, NCCL_UINT32, c->comm, c->stream));
 		if (c->use_summary) NCCL_TRY(g_nccl.AllGather(c->summary.p + pb * c->rank, c->summary.p, pb, NCCL_UINT32, c->comm, c->stream));
 	}
@@ -473,6 +500,8 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 	c->st.ms_hash_build = ev_ms(c, EV_HASH0, EV_HASH1);
 	c->st.table_buckets = nb;
 	c->st.table_bytes = nb * OGB_BWORDS * sizeof(u32);
+	c->part_chunk_set = false;
+	if (!c->partitioned && c->chunk_reads > (1u << 16)) c->chunk_reads = 1u << 16;
 	c->have_table = true; c->contain_done = false; c->any_contained = false; c->have_graph = false;
 	c->st.ms_contain = 0; c->st.n_contained = 0; c->st.contain_probes = 0; c->st.contain_hits = 0;
 	return OGB_OK;
@@ -548,7 +577,7 @@ static ScanArgs scan_args(ogb_context *c, u32 lo, u32 hi)
 	a.contained = c->any_contained ? c->contained.p : nullptr;
 	a.cand_q = c->cand_q.p; a.cand_v = c->cand_v.p; a.cand_cap = c->cand_cap; a.cand_cursor = c->d_cursor;
 	a.sup = c->sup.p; a.slots_e = c->slots_e.p; a.slot_lo = lo; a.cap = c->slot_cap; a.deg = c->deg.p;
-	a.ov_q = c->ov_q.p; a.ov_e = c->ov_e.p; a.ov_cap = c->ov_q.cap; a.ctr = c->d_ctr;
+	a.ov_q = c->ov_q.p; a.ov_e = c->ov_e.p; a.ov_cap = c->ov_q.cap; a.ctr = c->d_ctr; a.prefetch = 1;
 	return a;
 }
 
@@ -559,12 +588,22 @@ static ScanArgs scan_args(ogb_context *c, u32 lo, u32 hi)
 // Nothing here synchronises with the host.
 template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 {
+	// Index beyond L2 and one read length: partitioned probe over larger chunks (see k_window_part_uniform).
+	const bool part_mode = c->partitioned && c->uniform_len && !c->any_contained && hi > lo;
+	const u32 nwin_u = c->uniform_len ? c->uniform_len - c->h - 1 : 0;
 	{
 		const char *e = getenv("OGB_CHUNK_READS");                           // experiment knob
-		if (e && atoll(e) >= 256) c->chunk_reads = (u32)std::min<long long>(atoll(e), 1ll << 16);
-		const u64 want = 8ull << 20;
+		if (e && atoll(e) >= 256 && !part_mode) c->chunk_reads = (u32)std::min<long long>(atoll(e), 1ll << 16);
+		const u64 want = part_mode ? 32ull << 20 : 8ull << 20;
 		if (c->cand_cap < want) { OGB_TRY(c->cand_q.ensure(2 * want)); OGB_TRY(c->cand_v.ensure(2 * want)); c->cand_cap = want; }
 	}
+	if (part_mode) {
+		if (!c->part_chunk_set) { const char *e = getenv("OGB_CHUNK_READS"); c->chunk_reads = e && atoll(e) >= 256 ? (u32)std::min<long long>(atoll(e), 1ll << 20) : 1u << 18; c->part_chunk_set = true; }
+		c->chunk_reads = (u32)std::min<u64>(c->chunk_reads, (1ull << 31) / std::max<u32>(nwin_u, 1));
+		const u64 pcap = std::min<u64>(c->chunk_reads, hi - lo) * nwin_u / c->nparts * 5 / 4 + 4096;   // a quarter of slack over a perfectly even split
+		OGB_TRY(c->pq_b.ensure(pcap * c->nparts)); OGB_TRY(c->pq_f.ensure(pcap * c->nparts)); OGB_TRY(c->pq_q.ensure(pcap * c->nparts));
+		c->pq_cap = pcap;
+	} else
 	if (c->chunk_reads > (1u << 16)) c->chunk_reads = 1u << 16;             // k_probe_uniform indexes windows with 32 bits
 	int gp = grid_for(c, (const void *)k_probe<MODE>, 256), gv = grid_for(c, (const void *)k_verify<MODE>, 256);
 	int gu = grid_for(c, (const void *)k_probe_uniform<MODE>, 256);
@@ -589,7 +628,18 @@ template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 		const u32 warps = a.hi - a.lo;
 		const bool timed = MODE == MODE_OVERLAP && i < 64;
 		if (timed) CUDA_TRY(cudaEventRecord(c->ev_pk[2 * i], c->stream));
-		if (c->uniform_len && !a.contained) {
+		if (part_mode) {
+			PartQueue pq;
+			pq.b = c->pq_b.p; pq.f = c->pq_f.p; pq.q = c->pq_q.p; pq.cursor = c->d_pq_cursor; pq.cap = c->pq_cap; pq.nparts = c->nparts;
+			a.prefetch = 0;
+			CUDA_TRY(cudaMemsetAsync(c->d_pq_cursor, 0, OGB_MAXPART * sizeof(u64), c->stream));
+			const u64 tiles = ((u64)warps * nwin_u + 256 * OGB_WPT - 1) / (256 * OGB_WPT);
+			const int gw = grid_for(c, (const void *)k_window_part_uniform<MODE>, 256), gb = grid_for(c, (const void *)k_probe_parts<MODE>, 256);
+			k_window_part_uniform<MODE><<<(unsigned)std::min<u64>(gw, tiles), 256, 0, c->stream>>>(a, nwin_u, ~0ull / nwin_u + 1, pq);
+			if (timed) CUDA_TRY(cudaEventRecord(c->ev_pm[i], c->stream));
+			k_probe_parts<MODE><<<gb, 256, 0, c->stream>>>(a, pq);
+			c->launches++;
+		} else if (c->uniform_len && !a.contained) {
 			const u32 nwin = c->uniform_len - c->h - 1;
 			const u64 rounds = ((u64)warps * nwin + 31) / 32;
 			k_probe_uniform<MODE><<<(unsigned)std::min<u64>(gu, (rounds * 32 + 255) / 256), 256, 0, c->stream>>>(a, nwin, ~0ull / nwin + 1);
@@ -915,6 +965,10 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		float sum = 0;
 		for (u32 i = 0; i < c->n_pk; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev_pk[2 * i], c->ev_pk[2 * i + 1]) == cudaSuccess) sum += ms; else cudaGetLastError(); }
 		c->st.ms_probe_launch = c->n_pk ? sum / c->n_pk : 0;
+		float wsum = 0;
+		if (c->partitioned && c->uniform_len)
+			for (u32 i = 0; i < c->n_pk; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev_pk[2 * i], c->ev_pm[i]) == cudaSuccess) wsum += ms; else cudaGetLastError(); }
+		c->st.ms_window_launch = c->n_pk ? wsum / c->n_pk : 0;
 		c->st.probe_launches = (nloc + c->chunk_reads - 1) / c->chunk_reads;
 	}
 	c->st.ms_exchange_pre = ev_ms(c, EV_OVL1, EV_XPRE1);

@@ -72,9 +72,11 @@ struct Table {
 	u32 *slots;          // nb * OGB_BWORDS words
 	u32 *summary;        // nb words: Bloom bits of the fingerprints stored in the bucket | OGB_SPILLED; null = not used
 	u32 nb;              // buckets = nparts * part_buckets
-	u32 nparts;          // hash partitions (= ranks: every rank builds one partition, then the slices are allgathered)
+	u32 nparts;          // hash partitions = ranks x sub: rank r builds partitions [r*sub, (r+1)*sub), then the slices are allgathered;
+	                     // a partition is also the unit the probe of a big index works through at a time (L2-sized)
 	u32 part_buckets;    // buckets per partition; linear probing wraps inside a partition
-	u32 my_part;         // K1: insert only keys of this partition (nparts > 1)
+	u32 sub;             // partitions per rank
+	u32 my_rank;         // K1: insert only the keys of this rank's partitions
 	u32 h;               // hashStringLength = minOverlap-1 (HashTable.cpp:54)
 };
 
@@ -363,7 +365,7 @@ __global__ void k_hash_insert(ReadStore R, Table T)
 	read_geom(R, idx, off, L);
 	const u64 *w = R.words + off + (o >> 1) * padded_words(L);
 	u32 p = (o & 1) ? L - T.h : 0;
-	if (T.nparts > 1 && partition_of(key_lead<LdGlobal>(w, p, T.h), T) != T.my_part) return;   // another rank builds that partition
+	if (T.nparts > T.sub && partition_of(key_lead<LdGlobal>(w, p, T.h), T) / T.sub != T.my_rank) return;   // another rank builds that partition
 	u32 lead;
 	u64 hash = key_hash<LdGlobal>(w, p, T.h, lead);
 	const u32 fp = hash_fp(hash), val = ((idx + 1) << 2) | o;
@@ -470,6 +472,7 @@ struct ScanArgs {
 	u64 *ov_e;
 	u64 ov_cap;
 	u64 *ctr;
+	u32 prefetch;               // probe: prefetch each candidate's partner strand to L2 (chunks whose candidates stay L2-resident)
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -504,9 +507,11 @@ __device__ __forceinline__ void append_matches(const ScanArgs &A, QueueCursor &Q
 	for (; mm; mm &= mm - 1, at++) {
 		const u32 v = bucket_value(w, __ffs(mm) - 1);
 		if (at < A.cand_cap) { A.cand_q[at] = qi; A.cand_v[at] = tag | v; }
-		const u32 ri = (v >> 2) - 1;
-		if (A.R.uniform_len) prefetch_l2(A.R.words + (u64)ri * (2 * A.R.uniform_pw) + ((v >> 1) & 1) * A.R.uniform_pw);
-		else prefetch_l2(A.R.meta + ri);
+		if (A.prefetch) {
+			const u32 ri = (v >> 2) - 1;
+			if (A.R.uniform_len) prefetch_l2(A.R.words + (u64)ri * (2 * A.R.uniform_pw) + ((v >> 1) & 1) * A.R.uniform_pw);
+			else prefetch_l2(A.R.meta + ri);
+		}
 	}
 	Q.qused += total;
 }
@@ -572,9 +577,9 @@ __device__ __forceinline__ void pend_drain(const ScanArgs &A, PendQueue &P, u32 
 }
 
 // Key of window j of strand s -> home bucket, fingerprint | j<<16, and the summary verdict.
-__device__ __forceinline__ bool window_key(const ScanArgs &A, const u64 *__restrict__ s, u32 j, u32 &b, u32 &fj)
+__device__ __forceinline__ bool window_key(const ScanArgs &A, const u64 *__restrict__ s, u32 j, u32 &b, u32 &fj, u32 &part)
 {
-	u32 part, lead;
+	u32 lead;
 	const u64 hash = key_hash<LdGlobal>(s, j, A.T.h, lead);
 	b = bucket_of(hash, lead, A.T, part);
 	const u32 fp = hash_fp(hash);
@@ -604,8 +609,8 @@ __global__ void __launch_bounds__(256, OGB_PROBE_MINBLOCKS) k_probe(ScanArgs A)
 		c_probes += nwin;
 		for (u32 jb = 1; jb <= nwin; jb += 32) {
 			const u32 j = jb + lane;
-			u32 b = 0, fj = 0;
-			const bool pass = j <= nwin && window_key(A, s, j, b, fj);
+			u32 b = 0, fj = 0, part;
+			const bool pass = j <= nwin && window_key(A, s, j, b, fj, part);
 			pend_push(A, P, wib, plen, Q, lane, pass, b, fj, qi, c_sectors);
 		}
 	}
@@ -635,8 +640,8 @@ __global__ void __launch_bounds__(256, OGB_PROBE_MINBLOCKS) k_probe_uniform(Scan
 		const u32 x = rd * 32 + lane;
 		const u32 qr = nwin == 1 ? x : (u32)__umul64hi(div_magic, (u64)x);  // x / nwin (Lemire: exact for 32-bit x, nwin > 1)
 		const u32 j = x - qr * nwin + 1, qi = A.lo + qr;
-		u32 b = 0, fj = 0;
-		const bool pass = x < total && window_key(A, A.R.words + (u64)qi * stride, j, b, fj);
+		u32 b = 0, fj = 0, part;
+		const bool pass = x < total && window_key(A, A.R.words + (u64)qi * stride, j, b, fj, part);
 		pend_push(A, P, wib, plen, Q, lane, pass, b, fj, qi, c_sectors);
 	}
 	pend_drain(A, P, wib, plen, Q, lane, c_sectors);
@@ -644,6 +649,85 @@ __global__ void __launch_bounds__(256, OGB_PROBE_MINBLOCKS) k_probe_uniform(Scan
 	for (int d = 16; d > 0; d >>= 1) c_sectors += __shfl_down_sync(0xFFFFFFFFu, c_sectors, d);
 	if (lane == 0) atomicAdd(A.ctr + CTR_SECTORS, c_sectors);
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.ctr + CTR_PROBES, (u64)total);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Probe of an index that does not fit L2 (uniform read length): random 64-byte bucket fetches over
+// hundreds of MB run at the DRAM row / translation rate (~25 G/s measured, profiles/gather_bench_b200.txt)
+// instead of the L2 rate. So the windows of a chunk are first hashed, filtered by the summary and
+// SCATTERED into one queue per hash partition (k_window_part: a block counts its tile's windows per
+// partition in shared memory, reserves queue space with one atomic per partition and tile, then
+// writes), and the queues are probed one partition at a time (k_probe_parts): while a partition is
+// being probed its 32-64 MB of buckets are L2-resident.
+// ------------------------------------------------------------------------------------------------
+#define OGB_MAXPART 64
+#define OGB_WPT 4               // windows per thread and tile in k_window_part
+struct PartQueue {
+	u32 *b, *f, *q;             // nparts regions of cap records: bucket, fingerprint | j<<16, query read index
+	u64 *cursor;                // records appended per partition (may exceed cap: the excess is dropped and the chunk retried)
+	u64 cap;
+	u32 nparts;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 6) k_window_part_uniform(ScanArgs A, u32 nwin, u64 div_magic, PartQueue PQ)
+{
+	__shared__ u32 s_cnt[OGB_MAXPART];
+	__shared__ u64 s_base[OGB_MAXPART];
+	const u32 total = (A.hi - A.lo) * nwin;
+	const u32 stride = 2 * A.R.uniform_pw;
+	const u32 tile_windows = 256 * OGB_WPT;
+	const u32 tiles = (total + tile_windows - 1) / tile_windows;
+	for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+		if (threadIdx.x < PQ.nparts) s_cnt[threadIdx.x] = 0;
+		__syncthreads();
+		u32 eb[OGB_WPT], ef[OGB_WPT], eq[OGB_WPT], ep[OGB_WPT];            // ep = partition<<16 | rank inside the tile's share of it
+		#pragma unroll
+		for (int r = 0; r < OGB_WPT; r++) {
+			const u32 x = tile * tile_windows + r * 256 + threadIdx.x;
+			const u32 qr = nwin == 1 ? x : (u32)__umul64hi(div_magic, (u64)x);
+			const u32 j = x - qr * nwin + 1;
+			eq[r] = A.lo + qr; eb[r] = 0; ef[r] = 0;
+			u32 part = 0;
+			const bool pass = x < total && window_key(A, A.R.words + (u64)eq[r] * stride, j, eb[r], ef[r], part);
+			ep[r] = pass ? (part << 16) | atomicAdd(&s_cnt[part], 1u) : 0xFFFFFFFFu;
+		}
+		__syncthreads();
+		if (threadIdx.x < PQ.nparts) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(PQ.cursor + threadIdx.x, (u64)s_cnt[threadIdx.x]) : 0;
+		__syncthreads();
+		#pragma unroll
+		for (int r = 0; r < OGB_WPT; r++)
+			if (ep[r] != 0xFFFFFFFFu) {
+				const u32 part = ep[r] >> 16;
+				const u64 at = s_base[part] + (ep[r] & 0xFFFFu);
+				if (at < PQ.cap) { const u64 i = part * PQ.cap + at; PQ.b[i] = eb[r]; PQ.f[i] = ef[r]; PQ.q[i] = eq[r]; }
+			}
+		__syncthreads();
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.ctr + CTR_PROBES, (u64)total);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, OGB_PROBE_MINBLOCKS) k_probe_parts(ScanArgs A, PartQueue PQ)
+{
+	const u32 lane = threadIdx.x & 31;
+	const u64 gw = (blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * (u64)blockDim.x) >> 5;
+	u64 c_sectors = 0;
+	QueueCursor Q = {0, 0, 0};
+	for (u32 part = 0; part < PQ.nparts; part++) {
+		const u64 filled = PQ.cursor[part];
+		if (filled > PQ.cap && gw == 0 && lane == 0) atomicMax(A.ctr + CTR_CAND_MAX, ~0ull >> 1);   // a queue overflowed: retry with smaller chunks
+		const u64 n = min(filled, PQ.cap), base = part * PQ.cap;
+		for (u64 i0 = gw * 32; i0 < n; i0 += nwarps * 32) {
+			const u64 i = i0 + lane;
+			const bool act = i < n;
+			const u32 pb = act ? PQ.b[base + i] : 0, pf = act ? PQ.f[base + i] : 0, pq = act ? PQ.q[base + i] : 0;
+			probe_buckets(A, Q, lane, act, pb, pf, pq, c_sectors);
+		}
+	}
+	queue_pad(A, Q, lane);
+	for (int d = 16; d > 0; d >>= 1) c_sectors += __shfl_down_sync(0xFFFFFFFFu, c_sectors, d);
+	if (lane == 0) atomicAdd(A.ctr + CTR_SECTORS, c_sectors);
 }
 
 // One thread per candidate. The loop is warp-uniform (32 consecutive candidates per warp and

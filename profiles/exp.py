@@ -57,11 +57,11 @@ def main():
         check(lib().ogb_timer_end(ctx._h, C.byref(ms)))
         if i >= a.warmup:
             st = ctx.stats()
-            rows.append([ms.value] + [st[k] for k in ("ms_hash_build", "ms_contain", "ms_overlap", "ms_scan_kernel", "ms_probe_launch", "ms_exchange_pre", "ms_mark", "ms_reduce")])
+            rows.append([ms.value] + [st[k] for k in ("ms_hash_build", "ms_contain", "ms_overlap", "ms_scan_kernel", "ms_probe_launch", "ms_exchange_pre", "ms_mark", "ms_reduce", "ms_window_launch")])
     r = np.array(rows).mean(axis=0)
     st = ctx.stats()
     print(f"[{a.tag or 'exp'}] config{a.config}@{a.scale} n={st['n_reads']} {verdict} | step {r[0]:.3f} ms | hash {r[1]:.3f} contain {r[2]:.3f} overlap {r[3]:.3f} "
-          f"(scan {r[4]:.3f}, probe launch {r[5]:.4f} x{st['probe_launches']}) barrier {r[6]:.3f} mark {r[7]:.3f} reduce {r[8]:.3f} | "
+          f"(scan {r[4]:.3f}, probe launch {r[5]:.4f} [window part {r[9]:.4f}] x{st['probe_launches']}) barrier {r[6]:.3f} mark {r[7]:.3f} reduce {r[8]:.3f} | "
           f"E_pre {st['edges_pre']} E_final {st['edges_final']} heavy {st['overflow_reads']} launches {st['kernel_launches']} | host setup {t_host:.1f} s", flush=True)
     ctx.close()
 

@@ -178,3 +178,19 @@ def test_cpp_dropin_matches_reference_dump(ctx, tmp_path):
         assert np.array_equal(d["reads"]["sup"], z["sup"]) and np.array_equal(d["reads"]["freq"], z["freq"]), name
         assert np.array_equal(d["edges"], z["edges"]), name
         assert d["number_of_nodes"] == int(z["number_of_nodes"]) and d["number_of_edges"] == int(z["number_of_edges"]), name
+
+
+@pytest.mark.parametrize("cap", [8, 16])
+def test_heavy_lists_match_oracle(ctx, cap, monkeypatch):
+    """Slot regions of only `cap` edge words (OGB_SLOT_CAP): most nodes become heavy nodes whose lists are
+    gathered in the extension area (k_heavy_move / k_heavy_place), K5 takes the any-degree path for degree
+    > 32 and K6 / k_emit read the moved lists -- same graph as the oracle."""
+    from metagenomics_b200 import edges_as_tuples, synth
+    monkeypatch.setenv("OGB_SLOT_CAP", str(cap))
+    for cfg in (synth.config(2, scale=0.02), datasets.tandem(), synth.containment_stress(7, genome_len=6000, n_primary=1500)):
+        ds, ht, og = build_gpu(ctx, cfg)
+        orc = Oracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"]).run_all(Oracle.BFS)
+        assert ctx.stats()["overflow_reads"] > 0 or orc.counters()["max_degree"] <= cap
+        assert_same_edges(edges_as_tuples(og.edges(pre=True)), orc.edges(pre=True), f"pre-reduction, cap {cap}")
+        assert_same_edges(edges_as_tuples(og.edges()), orc.edges(), f"post-reduction, cap {cap}")
+        assert og.getNumberOfNodes() == orc.counters()["number_of_nodes"]
