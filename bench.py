@@ -305,11 +305,11 @@ def main():
             "per_step_ms": [round(float(x), 3) for x in per_step],
             "gpu_launches": int(st["kernel_launches"]) * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": "k_probe_uniform (K3 probe: window hash + 64-byte bucket gather + fingerprint match), one launch per chunk of 65536 reads",
+            "roofline": {"kernel": "K3 probe of one chunk of query reads: k_window_part_uniform (window hash + summary filter + scatter to partition queues) + k_probe_parts (64-byte bucket gather + fingerprint match)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": scan_bytes, "kernel_ms": st["ms_probe_launch"],
                          "launches_per_step": launches, "share_of_step": st["ms_probe_launch"] * launches / ms_step if ms_step else None,
-                         "note": "the index (64 B per read) is L2-resident at this size, so DRAM traffic is below the algorithmic bytes; the kernel is issue-bound (profiles/r1_notes.md)"},
+                         "note": "kernel_ms is measured in place while the previous chunk's verify runs on the second stream; the index partition being probed is L2-resident, so the pair is latency/issue-bound rather than HBM-bound (profiles/r1_notes.md)"},
             "phases_ms": {k: st[k] for k in ("ms_hash_build", "ms_contain", "ms_overlap", "ms_scan_kernel", "ms_exchange_pre", "ms_mark", "ms_reduce", "ms_total")},
             "stats": {k: st[k] for k in ("table_bytes", "overlap_probes", "probe_sectors", "candidates", "pivot_entries", "active_pivots",
                                          "max_degree", "overflow_reads", "n_contained", "nodes_final")},

@@ -482,8 +482,12 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 	if (c->use_summary) OGB_TRY(c->summary.ensure(nb));
 	c->launches = 0;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_HASH0], c->stream));
-	CUDA_TRY(cudaMemsetAsync(c->slots.p, 0, nb * OGB_BWORDS * sizeof(u32), c->stream));
-	if (c->use_summary) CUDA_TRY(cudaMemsetAsync(c->summary.p, 0, nb * sizeof(u32), c->stream));
+	{
+		// only this rank's slice is cleared and filled; the allgather below overwrites the others
+		const u64 pb = nb / c->nranks;
+		CUDA_TRY(cudaMemsetAsync(c->slots.p + pb * OGB_BWORDS * c->rank, 0, pb * OGB_BWORDS * sizeof(u32), c->stream));
+		if (c->use_summary) CUDA_TRY(cudaMemsetAsync(c->summary.p + pb * c->rank, 0, pb * sizeof(u32), c->stream));
+	}
 	if (c->n) {
 		u64 threads = (u64)c->n * 4;
 		k_hash_insert<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->rs(), c->tb());
