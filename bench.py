@@ -46,42 +46,54 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md): a thread polling NVML every 2 ms
+    (the timed region of this bench lasts tens of milliseconds -- `nvidia-smi -lms` would not produce a line in time)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, device):
-        self.device, self.proc, self.lines = device, None, []
+        self.sm, self.mask, self.h, self.nv, self.run, self.mx = [], 0, None, None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _reasons(self):
+        for name in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+            f = getattr(self.nv, name, None)
+            if f is not None:
+                try:
+                    return int(f(self.h))
+                except Exception:
+                    pass
+        return 0
+
+    def _poll(self):
+        while self.run:
+            try:
+                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self.mask |= self._reasons()
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
+        if self.h is None:
+            return
+        self.run = True
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self.run = False
         self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(v for k, v in self.REASONS.items() if self.mask & k), "samples": len(self.sm)}
 
 
 def workload(cfg_id, scale, n_gpus):
@@ -285,12 +297,13 @@ def main():
     if rank == 0:
         achieved = scan_bytes / (st["ms_probe_launch"] * 1e-3) / 1e9 if st["ms_probe_launch"] > 0 else 0.0
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "probe_kernel_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
                 tj = json.load(f)
             if tj.get("workload") == f"config{args.config}@{args.scale}x{world}":
                 traffic = tj.get("dram_bytes_per_launch")
+        mark_bytes = 8.0 * (st["edges_pre_local"] + st["pivot_entries"])
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
@@ -305,11 +318,20 @@ def main():
             "per_step_ms": [round(float(x), 3) for x in per_step],
             "gpu_launches": int(st["kernel_launches"]) * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": "K3 probe of one chunk of query reads: k_window_part_uniform (window hash + summary filter + scatter to partition queues) + k_probe_parts (64-byte bucket gather + fingerprint match)",
-                         "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": scan_bytes, "kernel_ms": st["ms_probe_launch"],
+            # Dominant single kernel of a step (ncu launch list profiles/launches_r1b.csv: 29 % of the GPU time): K5 k_mark, one launch per step.
+            # Algorithmic bytes (SURVEY.md 8(d), K5 term): (E_pre + T) * B_e -- every node's own list plus the list of each active pivot, 8-byte edge words.
+            "roofline": {"kernel": "k_mark (K5 markTransitiveEdges: warp per node on the unsorted slot regions, pivot order by warp min-reduction)",
+                         "bound": "hbm", "achieved": mark_bytes / (st["ms_mark"] * 1e-3) / 1e9 if st["ms_mark"] > 0 else 0.0, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": (mark_bytes / (st["ms_mark"] * 1e-3) / 1e9 / peak) if st["ms_mark"] > 0 else 0.0,
+                         "traffic": traffic.get("k_mark") if traffic else None, "algorithmic_bytes_per_launch": mark_bytes, "kernel_ms": st["ms_mark"],
+                         "launches_per_step": 1, "share_of_step": st["ms_mark"] / ms_step if ms_step else None,
+                         "note": "random 208-byte list fetches (~2.6 pivots per node) from GB-sized slot regions: 62-68 % of the issue slots busy, DRAM at ~20 % of peak -- issue/latency-bound, not bandwidth-bound (profiles/r1_notes.md, profiles/prof_r1b_reduce_summary.txt)"},
+            # The K3 probe of one chunk (two kernels back to back), same definition as in the first half of the round.
+            "roofline_k3_probe": {"kernel": "k_window_part_uniform (window hash + summary filter + scatter to partition queues) + k_probe_parts (64-byte bucket gather + fingerprint match), per chunk of query reads",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic.get("k3_probe") if traffic else None, "algorithmic_bytes_per_launch": scan_bytes, "kernel_ms": st["ms_probe_launch"],
                          "launches_per_step": launches, "share_of_step": st["ms_probe_launch"] * launches / ms_step if ms_step else None,
-                         "note": "kernel_ms is measured in place while the previous chunk's verify runs on the second stream; the index partition being probed is L2-resident, so the pair is latency/issue-bound rather than HBM-bound (profiles/r1_notes.md)"},
+                         "note": "kernel_ms is measured in place while the previous chunk's verify runs on the second stream (alone: 0.23 ms per 256 k reads); the index partition being probed is L2-resident"},
             "phases_ms": {k: st[k] for k in ("ms_hash_build", "ms_contain", "ms_overlap", "ms_scan_kernel", "ms_exchange_pre", "ms_mark", "ms_reduce", "ms_total")},
             "stats": {k: st[k] for k in ("table_bytes", "overlap_probes", "probe_sectors", "candidates", "pivot_entries", "active_pivots",
                                          "max_degree", "overflow_reads", "n_contained", "nodes_final")},

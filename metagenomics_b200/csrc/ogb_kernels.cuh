@@ -1320,10 +1320,11 @@ __global__ void __launch_bounds__(OGB_WARPS * 32) k_emit(const u64 *__restrict__
 {
 	const u32 lane = threadIdx.x & 31;
 	const u32 gw = blockIdx.x * OGB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * OGB_WARPS;
-	for (u32 u = lo + gw; u < hi; u += nwarps) {
-		if (!ALL && cnt[u - lo] <= min_cnt) continue;
+	// a warp looks at 32 nodes at a time and visits only the ones that have records to write here
+	for (u32 base = lo + gw * 32; base < hi; base += nwarps * 32)
+	for (u32 todo = __ballot_sync(0xFFFFFFFFu, base + lane < hi && (ALL ? deg[base + lane] > 0 : cnt[base + lane - lo] > min_cnt)); todo; todo &= todo - 1) {
+		const u32 u = base + __ffs(todo) - 1;
 		const u32 d = deg[u];
-		if (d == 0) continue;
 		const u64 *own = own_slots + (u64)(u - lo) * cap;
 		if (d > cap) own = own_ext + own[0];
 		ogb_edge *dst = out + pos[u - lo] + add;
