@@ -162,7 +162,9 @@ int ogb_reads_upload_dataset(ogb_context *ctx, const ogb_dataset *ds);
 
 /* HashTable::insertDataset(Dataset*, minOverlapLength) (HashTable.cpp:50-80): hashStringLength =
  * minOverlap-1 (:54); 4 keys per read -- prefix/suffix of forward and of reverse complement
- * (hashRead :88-104) -- inserted by K1 into an open-addressing table of 32-byte buckets. */
+ * (hashRead :88-104) -- inserted by K1 into an open-addressing table of 64-byte buckets (ten
+ * fingerprint/value slots each), cut into L2-sized hash partitions; on several ranks every rank builds the partitions
+ * it owns and the slices are allgathered. */
 int ogb_hash_build(ogb_context *ctx, uint32_t min_overlap);
 
 /* HashTable::getListOfReads(string) (HashTable.cpp:202-221) for n_keys keys of hashStringLength
@@ -182,7 +184,7 @@ int ogb_super_read_ids(ogb_context *ctx, uint64_t *out, uint64_t cap);
 
 /* OverlapGraph::buildOverlapGraphFromHashTable (OverlapGraph.cpp:107-210, up to `delete hashTable`)
  * minus markContainedReads/readMatePairsFromFile: insertAllEdgesOfRead + checkOverlap (K3, :354-383,
- * :529-565), per-node sort by offset (:563), markTransitiveEdges (K5, :574-615),
+ * :529-565), the per-node order by offset (:563, produced on the fly by K5/K6), markTransitiveEdges (K5, :574-615),
  * removeTransitiveEdges (K6, :623-661) and, on several ranks, the edge exchanges. The result stays
  * on the device until ogb_graph_edges. keep_pre != 0 keeps the pre-reduction edge list readable. */
 int ogb_build_graph(ogb_context *ctx, int keep_pre);

@@ -1,5 +1,5 @@
 """One-process-per-GPU plumbing around libogb's multi-rank contexts (torch.distributed only moves the
-NCCL unique id and the timing scalars; the data-path collectives -- allgatherv of the pre-reduction
+NCCL unique id and the timing scalars; the data-path collectives -- allgather of the index slices, of the packed pre-reduction
 adjacency, flags and final edges -- are NCCL calls inside libogb, see csrc/ogb_device.cu)."""
 import os
 

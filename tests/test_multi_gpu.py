@@ -1,5 +1,5 @@
-"""GPU, N > 1: the sharded path (query-read shards, replicated index, NCCL allgatherv of the
-pre-reduction adjacency, flags and final edges) gives every rank the oracle's graph. Needs >= 2 GPUs
+"""GPU, N > 1: the sharded path (query-read shards, index built partition-wise and replicated, NCCL allgather of
+the packed pre-reduction adjacency, verdict bits and final edges) gives every rank the oracle's graph. Needs >= 2 GPUs
 (`gpurun --gpus 2`); skipped otherwise."""
 import os
 import subprocess
