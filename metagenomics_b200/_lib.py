@@ -44,6 +44,7 @@ PROTOTYPES = {
     "ogb_dataset_add_reads": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
     "ogb_dataset_add_file": (C.c_int, [_vp, C.c_char_p]),
     "ogb_dataset_finalize": (C.c_int, [_vp, C.c_uint32]),
+    "ogb_dataset_finalize_device": (C.c_int, [_vp, _vp, C.c_uint32]),
     "ogb_dataset_n_reads": (C.c_uint64, [_vp]),
     "ogb_dataset_n_unique": (C.c_uint64, [_vp]),
     "ogb_dataset_shortest": (C.c_uint64, [_vp]),

@@ -29,7 +29,9 @@ def _reads_to_buffers(reads):
 class Dataset:
     """Dataset(pairedEndFileNames, singleEndFileNames, minOverlap) (Dataset.cpp:39-65)."""
 
-    def __init__(self, pairedEndFileNames=(), singleEndFileNames=(), minOverlap=0, reads=None, bases=None, offsets=None):
+    def __init__(self, pairedEndFileNames=(), singleEndFileNames=(), minOverlap=0, reads=None, bases=None, offsets=None, device=None):
+        """device: a Context -- canonical strand, sort and dedupe run on that GPU (ogb_dataset_finalize_device) and the
+        packed reads stay in its HBM; None: the host threads do it (ogb_dataset_finalize)."""
         self._h = C.c_void_p()
         check(lib().ogb_dataset_create(C.byref(self._h)))
         self.pairedEndDatasetFileNames = list(pairedEndFileNames)
@@ -42,7 +44,10 @@ class Dataset:
             bases = np.ascontiguousarray(bases, dtype=np.uint8)
             offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
             check(lib().ogb_dataset_add_reads(self._h, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1))
-        check(lib().ogb_dataset_finalize(self._h, int(minOverlap)))
+        if device is not None:
+            check(lib().ogb_dataset_finalize_device(self._h, device._h, int(minOverlap)))
+        else:
+            check(lib().ogb_dataset_finalize(self._h, int(minOverlap)))
 
     def __del__(self):
         if getattr(self, "_h", None):

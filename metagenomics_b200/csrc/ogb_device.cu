@@ -11,7 +11,10 @@
 #include "ogb_internal.h"
 #include "ogb_kernels.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
@@ -86,6 +89,23 @@ template <class T> struct Pool {
 // d_xchg layout (u64 words): per-rank verdict vectors, scratch
 enum { OGB_MAX_RANKS = 64, XCHG_PER_RANK = 8, XCHG_SCRATCH = XCHG_PER_RANK * OGB_MAX_RANKS, XCHG_WORDS = XCHG_SCRATCH + 8 };
 
+
+// Stream-ordered temporaries (cudaMallocAsync on the context's stream): the Dataset stage needs a dozen scratch arrays for
+// a few milliseconds; plain cudaMalloc / cudaFree of them cost more than the kernels (measured: 80 ms + up to seconds).
+template <class T> struct Tmp {
+	T *p = nullptr;
+	cudaStream_t st = nullptr;
+	int ensure(size_t need, cudaStream_t stream)
+	{
+		if (p) return OGB_OK;
+		st = stream;
+		cudaError_t e = cudaMallocAsync((void **)&p, std::max<size_t>(need, 1) * sizeof(T), stream);
+		if (e != cudaSuccess) { ogb_set_error("cudaMallocAsync of %zu bytes failed: %s", need * sizeof(T), cudaGetErrorString(e)); p = nullptr; return OGB_E_NOMEM; }
+		return OGB_OK;
+	}
+	void release() { if (p) cudaFreeAsync(p, st); p = nullptr; }
+};
+
 enum { EV_BEGIN = 0, EV_PACK0, EV_PACK1, EV_HASH0, EV_HASH1, EV_CONT0, EV_CONT1, EV_OVL0, EV_OVL1, EV_XPRE1, EV_MARK1, EV_RED1, EV_K3A, EV_K3B, EV_T0, EV_T1, EV_COUNT };
 
 struct ogb_context {
@@ -105,6 +125,7 @@ struct ogb_context {
 	Pool<unsigned short> stage_lens;
 	u32 n = 0, uniform_len = 0, uniform_pw = 0, min_len = 0, max_len = 0;
 	bool have_reads = false;
+	uint64_t reads_stamp = 0;        // changes with every upload (ogb_dataset::resident_stamp)
 	// index
 	Pool<u32> slots, summary;
 	u32 nb = 0, h = 0, nparts = 1;
@@ -204,6 +225,12 @@ static int context_create_common(ogb_context **out, int device)
 		cudaGetLastError();
 	}
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	{
+		// keep up to 2 GB of freed stream-ordered temporaries cached in the device's default pool (Dataset stage scratch)
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { uint64_t keep = 2ull << 30; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+		cudaGetLastError();
+	}
 	for (int i = 0; i < EV_COUNT; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
 	for (int i = 0; i < 128; i++) CUDA_TRY(cudaEventCreate(&c->ev_pk[i]));
 	for (int i = 0; i < 64; i++) CUDA_TRY(cudaEventCreate(&c->ev_pm[i]));
@@ -335,6 +362,7 @@ static int upload_common(ogb_context *c, u64 total_words, const std::vector<u64>
 		CUDA_TRY(cudaMemcpyAsync(c->meta.p, meta_host.data(), meta_host.size() * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
 	}
 	c->slot_cap = 64;
+	c->reads_stamp++;
 	c->have_reads = true; c->have_table = false; c->contain_done = false; c->any_contained = false; c->have_graph = false; c->have_pre = false;
 	return OGB_OK;
 }
@@ -428,9 +456,130 @@ extern "C" int ogb_reads_upload_packed(ogb_context *c, const uint64_t *words, co
 extern "C" int ogb_reads_upload_dataset(ogb_context *c, const ogb_dataset *ds)
 {
 	if (!c || !ds) { ogb_set_error("ogb_reads_upload_dataset: NULL argument"); return OGB_E_ARG; }
+	if (ds->resident_ctx == c && ds->resident_stamp == c->reads_stamp && c->have_reads) return OGB_OK;   // ogb_dataset_finalize_device left them in HBM
 	uint64_t nw = 0;
 	const uint64_t *w = ogb_dataset_words(ds, &nw);
 	return ogb_reads_upload_packed(c, w, ogb_dataset_word_offsets(ds), ogb_dataset_lengths(ds), ogb_dataset_n_unique(ds));
+}
+
+static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *d_total, u64 *d_max = nullptr);
+
+// ------------------------------------------------------------------------------------------------
+// Dataset stage on the device
+// ------------------------------------------------------------------------------------------------
+extern "C" int ogb_dataset_finalize_device(ogb_dataset *ds, ogb_context *c, uint32_t min_overlap)
+{
+	if (!c) { ogb_set_error("ogb_dataset_finalize_device: NULL context"); return OGB_E_ARG; }
+	const bool dbg = getenv("OGB_DBG_TIMING") != nullptr;
+	auto t_last = std::chrono::steady_clock::now();
+	auto lap = [&](const char *what) {
+		if (!dbg) return;
+		cudaStreamSynchronize(c->stream);
+		auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "[finalize_device] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+		t_last = now;
+	};
+	std::vector<uint64_t> idx;
+	OGB_TRY(ogb_dataset_filter(ds, min_overlap, idx));
+	lap("host filter");
+	const u64 n64 = idx.size();
+	if (n64 == 0) return OGB_OK;
+	if (n64 >= (1ull << 30)) { ogb_set_error("ogb_dataset_finalize_device: at most 2^30-1 reads per context"); return OGB_E_CAPACITY; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	const u32 n = (u32)n64, W = (u32)((ds->longest + 31) / 32);
+	const uint64_t *ro = ds->raw_offs.data();
+	std::vector<u64> gstart(n);
+	std::vector<unsigned short> glen(n);
+	for (u32 g = 0; g < n; g++) { gstart[g] = ro[idx[g]]; glen[g] = (unsigned short)(ro[idx[g] + 1] - ro[idx[g]]); }
+	lap("host start/len arrays");
+
+	Tmp<char> d_raw, d_tmp;
+	Tmp<u64> d_start, d_rows, d_key, d_key2, d_pos, d_woff, d_words;
+	Tmp<unsigned short> d_len, d_ulen;
+	Tmp<u32> d_perm, d_perm2, d_head, d_usrc, d_unw, d_ustart, d_freq;
+	auto release = [&]() {
+		d_raw.release(); d_tmp.release(); d_start.release(); d_rows.release(); d_key.release(); d_key2.release(); d_pos.release(); d_woff.release();
+		d_words.release(); d_len.release(); d_ulen.release(); d_perm.release(); d_perm2.release(); d_head.release(); d_usrc.release(); d_unw.release();
+		d_ustart.release(); d_freq.release();
+	};
+	auto run = [&]() -> int {
+		OGB_TRY(d_raw.ensure(ds->raw.size() + 1, c->stream)); OGB_TRY(d_start.ensure(n, c->stream)); OGB_TRY(d_len.ensure(n, c->stream)); OGB_TRY(d_rows.ensure((u64)n * W, c->stream));
+		OGB_TRY(d_key.ensure(n, c->stream)); OGB_TRY(d_key2.ensure(n, c->stream)); OGB_TRY(d_perm.ensure(n, c->stream)); OGB_TRY(d_perm2.ensure(n, c->stream)); OGB_TRY(d_head.ensure(n, c->stream)); OGB_TRY(d_pos.ensure((u64)n + 1, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(d_raw.p, ds->raw.data(), ds->raw.size(), cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(d_start.p, gstart.data(), n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(d_len.p, glen.data(), n * sizeof(unsigned short), cudaMemcpyHostToDevice, c->stream));
+		lap("alloc + H2D");
+		const unsigned g256 = (n + 255) / 256;
+		k_ds_canon<<<(n + 127) / 128, 128, 0, c->stream>>>(d_raw.p, d_start.p, d_len.p, d_rows.p, n, W);
+		k_ds_iota<<<g256, 256, 0, c->stream>>>(d_perm.p, n);
+		CUDA_TRY(cudaGetLastError());
+		lap("canonical strand kernel");
+		// LSD radix sort: length first (least significant), then the words from last to first; every pass is stable
+		size_t tmp_bytes = 0;
+		CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key.p, d_key2.p, d_perm.p, d_perm2.p, (int)n, 0, 64, c->stream));
+		OGB_TRY(d_tmp.ensure(tmp_bytes + 16, c->stream));
+		u32 *pa = d_perm.p, *pb = d_perm2.p;
+		for (int word = (int)W; word >= 0; word--) {
+			k_ds_key<<<g256, 256, 0, c->stream>>>(d_rows.p, d_len.p, pa, d_key.p, n, W, (u32)word);
+			CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_key.p, d_key2.p, pa, pb, (int)n, 0, word == (int)W ? 16 : 64, c->stream));
+			std::swap(pa, pb);
+		}
+		lap("radix sort passes");
+		// dedupe: heads -> unique index, run lengths = frequencies
+		k_ds_heads<<<g256, 256, 0, c->stream>>>(d_rows.p, d_len.p, pa, d_head.p, n, W);
+		CUDA_TRY(cudaGetLastError());
+		OGB_TRY(exclusive_scan(c, d_head.p, n, d_pos.p, c->d_tot));
+		u64 nu64 = 0;
+		CUDA_TRY(cudaMemcpyAsync(&nu64, c->d_tot, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		const u32 nu = (u32)nu64;
+		OGB_TRY(d_usrc.ensure(nu, c->stream)); OGB_TRY(d_ulen.ensure(nu, c->stream)); OGB_TRY(d_unw.ensure(nu, c->stream)); OGB_TRY(d_ustart.ensure(nu, c->stream)); OGB_TRY(d_freq.ensure(nu, c->stream)); OGB_TRY(d_woff.ensure((u64)nu + 1, c->stream));
+		k_ds_unique<<<g256, 256, 0, c->stream>>>(d_head.p, d_pos.p, pa, d_len.p, d_usrc.p, d_ulen.p, d_unw.p, d_ustart.p, n);
+		CUDA_TRY(cudaGetLastError());
+		OGB_TRY(exclusive_scan(c, d_unw.p, nu, d_woff.p, c->d_tot));
+		u64 total_in = 0;
+		CUDA_TRY(cudaMemcpyAsync(&total_in, c->d_tot, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		CUDA_TRY(cudaMemcpyAsync(d_woff.p + nu, c->d_tot, sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+		OGB_TRY(d_words.ensure(total_in + 4, c->stream));
+		k_ds_emit<<<(nu + 255) / 256, 256, 0, c->stream>>>(d_rows.p, d_usrc.p, d_unw.p, d_ustart.p, d_woff.p, d_freq.p, d_words.p, nu, n, W);
+		CUDA_TRY(cudaGetLastError());
+		lap("dedupe + emit");
+		// the host keeps the same views as after ogb_dataset_finalize
+		ds->lens.resize(nu); ds->freq.resize(nu); ds->word_offs.resize((size_t)nu + 1); ds->words.resize(total_in);
+		CUDA_TRY(cudaMemcpyAsync(ds->lens.data(), d_ulen.p, nu * sizeof(unsigned short), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(ds->freq.data(), d_freq.p, nu * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(ds->word_offs.data(), d_woff.p, ((size_t)nu + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(ds->words.data(), d_words.p, total_in * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		lap("D2H of the host views");
+		// ... and the read store of the context is filled straight from the device copy (K0), no second upload
+		u64 total_words = 0;
+		std::vector<u64> meta_host;
+		std::vector<u32> lens32(ds->lens.begin(), ds->lens.end());
+		OGB_TRY(layout_reads(c, lens32, total_words, meta_host));
+		OGB_TRY(upload_common(c, total_words, meta_host));
+		const u32 max_pw = ((c->max_len + 63) >> 6) << 1;
+		const u64 threads = (u64)nu * max_pw;
+		CUDA_TRY(cudaEventRecord(c->ev[EV_PACK0], c->stream));
+		k_pack_words<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(d_words.p, d_woff.p, d_ulen.p, c->words.p, c->uniform_len ? nullptr : c->meta.p,
+		                                                                      nu, c->uniform_len, c->uniform_pw, max_pw);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaEventRecord(c->ev[EV_PACK1], c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		c->st.ms_pack = ev_ms(c, EV_PACK0, EV_PACK1);
+		c->st.n_reads = nu;
+		ds->resident_ctx = c; ds->resident_stamp = c->reads_stamp;
+		lap("layout + K0");
+		return OGB_OK;
+	};
+	const int rc = run();
+	release();
+	lap("cudaFree");
+	ds->raw.clear(); ds->raw.shrink_to_fit();
+	ds->raw_offs.clear(); ds->raw_offs.shrink_to_fit();
+	lap("free raw");
+	return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -722,7 +871,7 @@ extern "C" int ogb_super_read_ids(ogb_context *c, uint64_t *out, uint64_t cap)
 // ------------------------------------------------------------------------------------------------
 // K3..K6
 // ------------------------------------------------------------------------------------------------
-static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *d_total, u64 *d_max = nullptr)
+static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *d_total, u64 *d_max)
 {
 	u32 nblocks = (n + OGB_SCAN_ITEMS - 1) / OGB_SCAN_ITEMS;
 	if (nblocks == 0) nblocks = 1;

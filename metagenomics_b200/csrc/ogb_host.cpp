@@ -92,19 +92,6 @@ inline void pack_both(const char *s, uint32_t len, uint64_t *fw, uint64_t *rc, u
 
 }  // namespace
 
-struct ogb_dataset {
-	std::vector<char> raw;
-	std::vector<uint64_t> raw_offs{0};
-	bool finalized = false;
-	uint32_t min_overlap = 0;
-	uint64_t n_good = 0, shortest = ~0ULL, longest = 0;
-	std::vector<uint64_t> words;
-	std::vector<uint64_t> word_offs;
-	std::vector<uint16_t> lens;
-	std::vector<uint32_t> freq;
-	uint64_t n_unique() const { return lens.size(); }
-};
-
 extern "C" int ogb_dataset_create(ogb_dataset **out)
 {
 	if (!out) { ogb_set_error("ogb_dataset_create: out is NULL"); return OGB_E_ARG; }
@@ -168,7 +155,7 @@ extern "C" int ogb_dataset_add_file(ogb_dataset *ds, const char *path)
 	return OGB_OK;
 }
 
-extern "C" int ogb_dataset_finalize(ogb_dataset *ds, uint32_t min_overlap)
+int ogb_dataset_filter(ogb_dataset *ds, uint32_t min_overlap, std::vector<uint64_t> &idx)
 {
 	if (!ds) { ogb_set_error("ogb_dataset_finalize: NULL dataset"); return OGB_E_ARG; }
 	if (ds->finalized) { ogb_set_error("ogb_dataset_finalize: already finalized"); return OGB_E_STATE; }
@@ -178,7 +165,7 @@ extern "C" int ogb_dataset_finalize(ogb_dataset *ds, uint32_t min_overlap)
 	char *raw = ds->raw.data();
 	const uint64_t *ro = ds->raw_offs.data();
 
-	// pass 1: case folding (Dataset.cpp:155-156) + filter (:158, testRead :398-413)
+	// case folding (Dataset.cpp:155-156) + filter (:158, testRead :398-413)
 	std::vector<uint8_t> good(n_raw, 0);
 	parallel_for(n_raw, 1 << 14, [&](uint64_t lo, uint64_t hi) {
 		for (uint64_t i = lo; i < hi; i++) {
@@ -199,7 +186,7 @@ extern "C" int ogb_dataset_finalize(ogb_dataset *ds, uint32_t min_overlap)
 			good[i] = ok;
 		}
 	});
-	std::vector<uint64_t> idx;
+	idx.clear();
 	idx.reserve(n_raw);
 	uint64_t shortest = ~0ULL, longest = 0;
 	for (uint64_t i = 0; i < n_raw; i++)
@@ -209,13 +196,25 @@ extern "C" int ogb_dataset_finalize(ogb_dataset *ds, uint32_t min_overlap)
 			shortest = std::min(shortest, len);
 			longest = std::max(longest, len);
 		}
-	const uint64_t n_good = idx.size();
-	ds->n_good = n_good;
+	ds->n_good = idx.size();
 	ds->shortest = shortest;
 	ds->longest = longest;
 	ds->finalized = true;
 	ds->word_offs.assign(1, 0);
-	if (n_good == 0) { ds->raw.clear(); ds->raw.shrink_to_fit(); return OGB_OK; }
+	if (idx.empty()) { ds->raw.clear(); ds->raw.shrink_to_fit(); }
+	return OGB_OK;
+}
+
+extern "C" int ogb_dataset_finalize(ogb_dataset *ds, uint32_t min_overlap)
+{
+	std::vector<uint64_t> idx;
+	int rc = ogb_dataset_filter(ds, min_overlap, idx);
+	if (rc != OGB_OK) return rc;
+	const uint64_t n_good = idx.size();
+	if (n_good == 0) return OGB_OK;
+	char *raw = ds->raw.data();
+	const uint64_t *ro = ds->raw_offs.data();
+	const uint64_t longest = ds->longest;
 
 	// pass 2: pack forward + reverse complement, keep the smaller (:161-164; equal -> same string)
 	const uint32_t W = (uint32_t)((longest + 31) / 32);

@@ -5,9 +5,30 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdlib>
+#include <vector>
 
 #include "../../include/ogb.h"
 
 void ogb_set_error(const char *fmt, ...);
+
+// Dataset (Dataset.h:17-62): raw reads until finalize, then the sorted unique reads, 2-bit packed.
+struct ogb_dataset {
+	std::vector<char> raw;
+	std::vector<uint64_t> raw_offs{0};
+	bool finalized = false;
+	uint32_t min_overlap = 0;
+	uint64_t n_good = 0, shortest = ~0ULL, longest = 0;
+	std::vector<uint64_t> words;
+	std::vector<uint64_t> word_offs;
+	std::vector<uint16_t> lens;
+	std::vector<uint32_t> freq;
+	const void *resident_ctx = nullptr;   // context whose HBM already holds these reads (ogb_dataset_finalize_device)
+	uint64_t resident_stamp = 0;
+	uint64_t n_unique() const { return lens.size(); }
+};
+
+// First half of the Dataset constructor, on the host: case folding + filter (Dataset.cpp:155-158, testRead :398-413).
+// Fills idx with the raw indices of the reads that stay and sets n_good / shortest / longest / min_overlap / finalized.
+int ogb_dataset_filter(ogb_dataset *ds, uint32_t min_overlap, std::vector<uint64_t> &idx);
 
 #endif

@@ -352,6 +352,93 @@ __global__ void k_pack_words(const u64 *__restrict__ in_words, const u64 *__rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// Dataset stage on the device (Dataset.cpp:161-164, 197-202, 316-345):
+// canonical strand, lexicographic sort, dedupe with frequencies, IDs = ranks. Reads are rows of W
+// zero-padded words; padding is 'A' = 0, the smallest base, so row order followed by length is exactly
+// std::string operator< (a proper prefix sorts first). The sort is an LSD radix sort over the words
+// (cub::DeviceRadixSort per 64-bit word, driven from ogb_device.cu); these kernels do the rest.
+// ------------------------------------------------------------------------------------------------
+
+// One thread per kept read: pack forward and reverse complement word by word, keep the smaller row (:161-164).
+__global__ void __launch_bounds__(128) k_ds_canon(const char *__restrict__ raw, const u64 *__restrict__ start, const unsigned short *__restrict__ len,
+                                                  u64 *__restrict__ rows, u32 n, u32 W)
+{
+	const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= n) return;
+	const char *s = raw + start[g];
+	const u32 L = len[g], nw = (L + 31) >> 5;
+	u64 *row = rows + (u64)g * W;
+	int pick = 0;                                                           // 0 undecided, 1 forward, 2 reverse complement
+	for (u32 k = 0; k < nw; k++) {
+		u64 fw = 0, rc = 0;
+		for (u32 i = 0; i < 32; i++) {
+			const u32 p = k * 32 + i;
+			if (p < L) {
+				u32 c = ((u32)s[p] >> 1) & 3; c ^= c >> 1;                      // A C G T -> 0 1 2 3
+				u32 d = ((u32)s[L - 1 - p] >> 1) & 3; d ^= d >> 1;
+				fw |= (u64)c << (62 - 2 * i);
+				rc |= (u64)(3 - d) << (62 - 2 * i);
+			}
+		}
+		if (pick == 0 && fw != rc) pick = fw < rc ? 1 : 2;
+		row[k] = pick == 2 ? rc : fw;                                       // words before the first difference are equal on both strands
+	}
+	for (u32 k = nw; k < W; k++) row[k] = 0;
+}
+
+// Key of one LSD pass: word `word` of the row (word == W: the length), in the current order.
+__global__ void __launch_bounds__(256) k_ds_key(const u64 *__restrict__ rows, const unsigned short *__restrict__ len, const u32 *__restrict__ perm,
+                                                u64 *__restrict__ key, u32 n, u32 W, u32 word)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const u32 g = perm[i];
+	key[i] = word == W ? (u64)len[g] : rows[(u64)g * W + word];
+}
+__global__ void __launch_bounds__(256) k_ds_iota(u32 *__restrict__ perm, u32 n)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) perm[i] = i;
+}
+
+// head[i] = 1 when the read at sorted position i differs from its predecessor (:316-345).
+__global__ void __launch_bounds__(256) k_ds_heads(const u64 *__restrict__ rows, const unsigned short *__restrict__ len, const u32 *__restrict__ perm,
+                                                  u32 *__restrict__ head, u32 n, u32 W)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	u32 h = 1;
+	if (i > 0) {
+		const u32 a = perm[i - 1], b = perm[i];
+		h = len[a] != len[b];
+		for (u32 k = 0; k < W && !h; k++) h = rows[(u64)a * W + k] != rows[(u64)b * W + k];
+	}
+	head[i] = h;
+}
+// Unique read u = number of heads before its first sorted position: source row, length, words needed, run start.
+__global__ void __launch_bounds__(256) k_ds_unique(const u32 *__restrict__ head, const u64 *__restrict__ pos, const u32 *__restrict__ perm,
+                                                   const unsigned short *__restrict__ len, u32 *__restrict__ usrc, unsigned short *__restrict__ ulen,
+                                                   u32 *__restrict__ unw, u32 *__restrict__ ustart, u32 n)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || !head[i]) return;
+	const u64 u = pos[i];
+	const u32 g = perm[i];
+	usrc[u] = g; ulen[u] = len[g]; unw[u] = ((u32)len[g] + 31) >> 5; ustart[u] = i;
+}
+// Frequencies = run lengths; tight packed words of the unique reads (the host-side Dataset layout).
+__global__ void __launch_bounds__(256) k_ds_emit(const u64 *__restrict__ rows, const u32 *__restrict__ usrc, const u32 *__restrict__ unw, const u32 *__restrict__ ustart,
+                                                 const u64 *__restrict__ woff, u32 *__restrict__ freq, u64 *__restrict__ words, u32 nu, u32 n, u32 W)
+{
+	const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= nu) return;
+	freq[u] = (u + 1 < nu ? ustart[u + 1] : n) - ustart[u];
+	const u64 *row = rows + (u64)usrc[u] * W;
+	u64 *dst = words + woff[u];
+	for (u32 k = 0; k < unw[u]; k++) dst[k] = row[k];
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1: hash insert. One thread per (read, orientation): o=0 prefix(fwd), 1 suffix(fwd),
 // 2 prefix(rc), 3 suffix(rc) (HashTable.cpp:93-101). Claims the first empty slot along the probe
 // sequence with a 64-bit CAS. Slot order inside a bucket is arbitrary (unobservable).

@@ -194,3 +194,37 @@ def test_heavy_lists_match_oracle(ctx, cap, monkeypatch):
         assert_same_edges(edges_as_tuples(og.edges(pre=True)), orc.edges(pre=True), f"pre-reduction, cap {cap}")
         assert_same_edges(edges_as_tuples(og.edges()), orc.edges(), f"post-reduction, cap {cap}")
         assert og.getNumberOfNodes() == orc.counters()["number_of_nodes"]
+
+
+DS_SETS = datasets.small_configs() + datasets.adversarial()
+
+
+@pytest.mark.parametrize("cfg", DS_SETS, ids=[c["name"][:28] for c in DS_SETS])
+def test_device_dataset_equals_host_dataset(ctx, cfg):
+    """Dataset stage on the GPU (canonical strand, LSD radix sort over packed words, dedupe, frequencies) against the
+    host implementation, which the CPU suite pins to the oracle and the reference: same IDs, lengths, frequencies and
+    packed words; and the graph built from the reads it leaves in HBM is the oracle's."""
+    from metagenomics_b200 import Dataset, HashTable, OverlapGraph, edges_as_tuples
+    host = Dataset(bases=cfg["bases"], offsets=cfg["offsets"], minOverlap=cfg["min_overlap"])
+    dev = Dataset(bases=cfg["bases"], offsets=cfg["offsets"], minOverlap=cfg["min_overlap"], device=ctx)
+    assert dev.getNumberOfReads() == host.getNumberOfReads() and dev.getNumberOfUniqueReads() == host.getNumberOfUniqueReads()
+    assert dev.shortestReadLength == host.shortestReadLength and dev.longestReadLength == host.longestReadLength
+    assert np.array_equal(dev.lengths(), host.lengths()) and np.array_equal(dev.frequencies(), host.frequencies())
+    hw, ho, _ = host.packed(); dw, do, _ = dev.packed()
+    assert np.array_equal(do, ho) and np.array_equal(dw, hw)
+    ht = HashTable(ctx)
+    ht.insertDataset(dev, cfg["min_overlap"])          # nothing to upload: the reads are resident
+    og = OverlapGraph(ht)
+    orc = Oracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"]).run_all(Oracle.BFS)
+    assert_same_edges(edges_as_tuples(og.edges()), orc.edges(), "post-reduction, device Dataset")
+    assert np.array_equal(og.superReadIDs()[1:], orc.read_info()["sup"])
+
+
+def test_device_dataset_config2_scale(ctx):
+    from metagenomics_b200 import Dataset, synth
+    cfg = synth.config(2, scale=0.2)
+    host = Dataset(bases=cfg["bases"], offsets=cfg["offsets"], minOverlap=cfg["min_overlap"])
+    dev = Dataset(bases=cfg["bases"], offsets=cfg["offsets"], minOverlap=cfg["min_overlap"], device=ctx)
+    assert np.array_equal(dev.frequencies(), host.frequencies())
+    hw, ho, _ = host.packed(); dw, do, _ = dev.packed()
+    assert np.array_equal(do, ho) and np.array_equal(dw, hw)
