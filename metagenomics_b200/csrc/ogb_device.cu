@@ -155,6 +155,7 @@ struct ogb_context {
 	u64 *d_pq_cursor = nullptr;
 	bool partitioned = false, part_chunk_set = false;
 	u64 pq_cap = 0;
+	u32 pq_slack = 5;                // queue capacity = even share x pq_slack / 4 (5/4 at first; doubled when a skewed partition overflows)
 	u64 *d_cursor = nullptr;         // the two candidate-queue cursors
 	u64 *d_xchg = nullptr;           // small per-rank values exchanged with NCCL (XCHG_* layout)
 	u32 slot_cap = 64;               // slots per read (adapted to the largest degree seen)
@@ -653,7 +654,7 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 	c->st.ms_hash_build = ev_ms(c, EV_HASH0, EV_HASH1);
 	c->st.table_buckets = nb;
 	c->st.table_bytes = nb * OGB_BWORDS * sizeof(u32);
-	c->part_chunk_set = false;
+	c->part_chunk_set = false; c->pq_slack = 5;
 	if (!c->partitioned && c->chunk_reads > (1u << 16)) c->chunk_reads = 1u << 16;
 	c->have_table = true; c->contain_done = false; c->any_contained = false; c->have_graph = false;
 	c->st.ms_contain = 0; c->st.n_contained = 0; c->st.contain_probes = 0; c->st.contain_hits = 0;
@@ -753,7 +754,7 @@ template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 	if (part_mode) {
 		if (!c->part_chunk_set) { const char *e = getenv("OGB_CHUNK_READS"); c->chunk_reads = e && atoll(e) >= 256 ? (u32)std::min<long long>(atoll(e), 1ll << 20) : 1u << 18; c->part_chunk_set = true; }
 		c->chunk_reads = (u32)std::min<u64>(c->chunk_reads, (1ull << 31) / std::max<u32>(nwin_u, 1));
-		const u64 pcap = std::min<u64>(c->chunk_reads, hi - lo) * nwin_u / c->nparts * 5 / 4 + 4096;   // a quarter of slack over a perfectly even split
+		const u64 pcap = std::min<u64>(c->chunk_reads, hi - lo) * nwin_u / c->nparts * std::min<u64>(c->pq_slack, 4ull * c->nparts) / 4 + 4096;   // a quarter of slack over a perfectly even split at first
 		OGB_TRY(c->pq_b.ensure(pcap * c->nparts)); OGB_TRY(c->pq_f.ensure(pcap * c->nparts)); OGB_TRY(c->pq_q.ensure(pcap * c->nparts));
 		c->pq_cap = pcap;
 	} else
@@ -952,7 +953,7 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		OGB_TRY(ctr_fetch(c));
 		const u64 n_over = c->h_ctr[CTR_OVERFLOW], n_heavy = c->h_ctr[CTR_BIG_NODES];
 		// [0] candidate queue overflowed, [1] spilled edges, [2] largest degree, [3] edges of this rank, [4] words its heavy lists need
-		u64 verdict[XCHG_PER_RANK] = {c->h_ctr[CTR_CAND_MAX] > c->cand_cap, n_over, c->h_ctr[CTR_MAX_DEGREE], local_edges, n_over + n_heavy * c->slot_cap, 0, 0, 0};
+		u64 verdict[XCHG_PER_RANK] = {c->h_ctr[CTR_CAND_MAX] > c->cand_cap, n_over, c->h_ctr[CTR_MAX_DEGREE], local_edges, n_over + n_heavy * c->slot_cap, c->h_ctr[CTR_PQ_OVERFLOW] != 0, 0, 0};
 		u64 need_ext = verdict[4];
 		seg_cnt[0] = local_edges; exact_edges = local_edges;
 		if (G > 1) {
@@ -965,11 +966,12 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 			exact_edges = 0;
 			for (int r = 0; r < G; r++) {
 				const u64 *v = &all[(size_t)XCHG_PER_RANK * r];
-				verdict[0] = std::max(verdict[0], v[0]); verdict[1] = std::max(verdict[1], v[1]); verdict[2] = std::max(verdict[2], v[2]);
+				verdict[0] = std::max(verdict[0], v[0]); verdict[1] = std::max(verdict[1], v[1]); verdict[2] = std::max(verdict[2], v[2]); verdict[5] = std::max(verdict[5], v[5]);
 				need_ext = std::max(need_ext, v[4]);
 				seg_cnt[r] = v[3]; exact_edges += v[3];
 			}
 		}
+		if (verdict[5]) { c->pq_slack *= 2; continue; }                      // a partition's window queue overflowed (skewed keys): more slack, up to everything in one partition
 		if (verdict[0]) { c->chunk_reads = std::max<u32>(256, c->chunk_reads / 2); continue; }
 		if (verdict[1] > c->ov_q.cap) {                                      // many heavy nodes: more slots per read, bigger spill list
 			if (c->slot_cap < 256) c->slot_cap *= 2;

@@ -57,7 +57,7 @@ enum { MODE_OVERLAP = 0, MODE_CONTAIN = 1 };
 enum {
 	CTR_EDGE_CURSOR = 0, CTR_OVERFLOW, CTR_PROBES, CTR_SECTORS, CTR_CANDIDATES, CTR_CONTAIN_HITS,
 	CTR_PIVOT_ENTRIES, CTR_ACTIVE_PIVOTS, CTR_MAX_DEGREE, CTR_N_CONTAINED, CTR_NODES_FINAL,
-	CTR_ASYMMETRIC, CTR_SCRATCH_CURSOR, CTR_SCRATCH_FAIL, CTR_CAND_MAX, CTR_BIG_NODES, CTR_EXT_CURSOR, CTR_COUNT
+	CTR_ASYMMETRIC, CTR_SCRATCH_CURSOR, CTR_SCRATCH_FAIL, CTR_CAND_MAX, CTR_BIG_NODES, CTR_EXT_CURSOR, CTR_PQ_OVERFLOW, CTR_COUNT
 };
 
 struct ReadStore {
@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(256, OGB_PROBE_MINBLOCKS) k_probe_parts(ScanAr
 	QueueCursor Q = {0, 0, 0};
 	for (u32 part = 0; part < PQ.nparts; part++) {
 		const u64 filled = PQ.cursor[part];
-		if (filled > PQ.cap && gw == 0 && lane == 0) atomicMax(A.ctr + CTR_CAND_MAX, ~0ull >> 1);   // a queue overflowed: retry with smaller chunks
+		if (filled > PQ.cap && gw == 0 && lane == 0) atomicMax(A.ctr + CTR_PQ_OVERFLOW, filled);   // a skewed partition outgrew its queue: the host retries with more slack
 		const u64 n = min(filled, PQ.cap), base = part * PQ.cap;
 		for (u64 i0 = gw * 32; i0 < n; i0 += nwarps * 32) {
 			const u64 i = i0 + lane;

@@ -228,3 +228,16 @@ def test_device_dataset_config2_scale(ctx):
     assert np.array_equal(dev.frequencies(), host.frequencies())
     hw, ho, _ = host.packed(); dw, do, _ = dev.packed()
     assert np.array_equal(do, ho) and np.array_equal(dw, hw)
+
+
+def test_partitioned_probe_with_skewed_partitions(ctx, monkeypatch):
+    """Eight hash partitions forced on small, repetitive data sets (OGB_SUB_PARTITIONS): the windows of a tandem array or
+    an inverted repeat share their leading bases, so one partition's window queue receives far more than its even
+    share -- the build retries with more slack and still returns the oracle's graph."""
+    from metagenomics_b200 import edges_as_tuples, synth
+    monkeypatch.setenv("OGB_SUB_PARTITIONS", "8")
+    for cfg in (datasets.tandem(), datasets.repeats(), datasets.palindromes(), datasets.from_strings(["ACACACACACACACACACACACACACACACACACACACACACAC" + "G" * i + "T" for i in range(1, 12)], 10, "same lead"), synth.config(2, scale=0.02)):
+        ds, ht, og = build_gpu(ctx, cfg)
+        orc = Oracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"]).run_all(Oracle.BFS)
+        assert_same_edges(edges_as_tuples(og.edges(pre=True)), orc.edges(pre=True), "pre-reduction, 8 partitions")
+        assert_same_edges(edges_as_tuples(og.edges()), orc.edges(), "post-reduction, 8 partitions")
