@@ -748,7 +748,9 @@ __global__ void __launch_bounds__(256, OGB_PROBE_MINBLOCKS) k_probe_uniform(Scan
 // being probed its 32-64 MB of buckets are L2-resident.
 // ------------------------------------------------------------------------------------------------
 #define OGB_MAXPART 64
+#ifndef OGB_WPT
 #define OGB_WPT 4               // windows per thread and tile in k_window_part
+#endif
 struct PartQueue {
 	u32 *b, *f, *q;             // nparts regions of cap records: bucket, fingerprint | j<<16, query read index
 	u64 *cursor;                // records appended per partition (may exceed cap: the excess is dropped and the chunk retried)
