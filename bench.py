@@ -336,7 +336,7 @@ def main():
                          "launches_per_step": 1, "share_of_step": st["ms_mark"] / ms_step if ms_step else None,
                          "note": "random 208-byte list fetches (~2.6 pivots per node) from GB-sized slot regions: 62-68 % of the issue slots busy, DRAM at ~20 % of peak -- issue/latency-bound, not bandwidth-bound (profiles/r1_notes.md, profiles/prof_r1b_reduce_summary.txt)"},
             # The K3 probe of one chunk (two kernels back to back), same definition as in the first half of the round.
-            "roofline_k3_probe": {"kernel": "k_window_part_uniform (window hash + summary filter + scatter to partition queues) + k_probe_parts (64-byte bucket gather + fingerprint match), per chunk of query reads",
+            "roofline_k3_probe": {"kernel": "k_window_part (window hash + summary filter + scatter to partition queues) + k_probe_parts (64-byte bucket gather + fingerprint match), per chunk of query reads",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic.get("k3_probe") if traffic else None, "algorithmic_bytes_per_launch": scan_bytes, "kernel_ms": st["ms_probe_launch"],
                          "launches_per_step": launches, "share_of_step": st["ms_probe_launch"] * launches / ms_step if ms_step else None,

@@ -623,7 +623,7 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 		c->use_summary = e ? atoi(e) != 0 : true;
 	}
 	{
-		// Probe through per-partition window queues (k_window_part_uniform + k_probe_parts) whenever the summary exists: measured
+		// Probe through per-partition window queues (k_window_part + k_probe_parts) whenever the summary exists: measured
 		// faster than the direct kernel even with an L2-resident index (config 2: K3 2.21 -> 1.91 ms), and the only way to keep
 		// the bucket fetches in L2 beyond it (config 3: 24.7 -> 18.2 ms). OGB_PARTITIONED=0: direct path (experiment knob).
 		const char *e = getenv("OGB_PARTITIONED");
@@ -742,9 +742,10 @@ static ScanArgs scan_args(ogb_context *c, u32 lo, u32 hi)
 // Nothing here synchronises with the host.
 template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 {
-	// Index beyond L2 and one read length: partitioned probe over larger chunks (see k_window_part_uniform).
-	const bool part_mode = c->partitioned && c->uniform_len && !c->any_contained && hi > lo;
-	const u32 nwin_u = c->uniform_len ? c->uniform_len - c->h - 1 : 0;
+	// Partitioned probe over larger chunks (k_window_part + k_probe_parts). Mixed read lengths: the windows are laid out
+	// with the stride of the longest read.
+	const bool part_mode = c->partitioned && hi > lo;
+	const u32 nwin_u = (c->uniform_len ? c->uniform_len : c->max_len) - c->h - 1;
 	{
 		const char *e = getenv("OGB_CHUNK_READS");                           // experiment knob
 		if (e && atoll(e) >= 256 && !part_mode) c->chunk_reads = (u32)std::min<long long>(atoll(e), 1ll << 16);
@@ -788,8 +789,10 @@ template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 			a.prefetch = 0;
 			CUDA_TRY(cudaMemsetAsync(c->d_pq_cursor, 0, OGB_MAXPART * sizeof(u64), c->stream));
 			const u64 tiles = ((u64)warps * nwin_u + 256 * OGB_WPT - 1) / (256 * OGB_WPT);
-			const int gw = grid_for(c, (const void *)k_window_part_uniform<MODE>, 256), gb = grid_for(c, (const void *)k_probe_parts<MODE>, 256);
-			k_window_part_uniform<MODE><<<(unsigned)std::min<u64>(gw, tiles), 256, 0, c->stream>>>(a, nwin_u, ~0ull / nwin_u + 1, pq);
+			const bool uni = c->uniform_len && !a.contained;
+			const int gw = grid_for(c, uni ? (const void *)k_window_part<MODE, true> : (const void *)k_window_part<MODE, false>, 256), gb = grid_for(c, (const void *)k_probe_parts<MODE>, 256);
+			if (uni) k_window_part<MODE, true><<<(unsigned)std::min<u64>(gw, tiles), 256, 0, c->stream>>>(a, nwin_u, ~0ull / nwin_u + 1, pq);
+			else k_window_part<MODE, false><<<(unsigned)std::min<u64>(gw, tiles), 256, 0, c->stream>>>(a, nwin_u, ~0ull / nwin_u + 1, pq);
 			if (timed) CUDA_TRY(cudaEventRecord(c->ev_pm[i], c->stream));
 			k_probe_parts<MODE><<<gb, 256, 0, c->stream>>>(a, pq);
 			c->launches++;
@@ -1121,7 +1124,7 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		for (u32 i = 0; i < c->n_pk; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev_pk[2 * i], c->ev_pk[2 * i + 1]) == cudaSuccess) sum += ms; else cudaGetLastError(); }
 		c->st.ms_probe_launch = c->n_pk ? sum / c->n_pk : 0;
 		float wsum = 0;
-		if (c->partitioned && c->uniform_len)
+		if (c->partitioned)
 			for (u32 i = 0; i < c->n_pk; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev_pk[2 * i], c->ev_pm[i]) == cudaSuccess) wsum += ms; else cudaGetLastError(); }
 		c->st.ms_window_launch = c->n_pk ? wsum / c->n_pk : 0;
 		c->st.probe_launches = (nloc + c->chunk_reads - 1) / c->chunk_reads;

@@ -758,15 +758,21 @@ struct PartQueue {
 	u32 nparts;
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(256, 6) k_window_part_uniform(ScanArgs A, u32 nwin, u64 div_magic, PartQueue PQ)
+template <int MODE, bool UNIFORM>
+__global__ void __launch_bounds__(256, 6) k_window_part(ScanArgs A, u32 nwin, u64 div_magic, PartQueue PQ)
 {
+	// nwin = windows per read (one read length) or of the longest read (mixed lengths: window x -> read x / nwin,
+	// j = x % nwin + 1; the threads whose j lies past their read's last window, or whose read is contained, drop out)
 	__shared__ u32 s_cnt[OGB_MAXPART];
 	__shared__ u64 s_base[OGB_MAXPART];
+	__shared__ u32 s_valid;
 	const u32 total = (A.hi - A.lo) * nwin;
 	const u32 stride = 2 * A.R.uniform_pw;
 	const u32 tile_windows = 256 * OGB_WPT;
 	const u32 tiles = (total + tile_windows - 1) / tile_windows;
+	const u32 h = A.T.h;
+	u32 c_valid = 0;
+	if (threadIdx.x == 0) s_valid = 0;
 	for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
 		if (threadIdx.x < PQ.nparts) s_cnt[threadIdx.x] = 0;
 		__syncthreads();
@@ -778,7 +784,18 @@ __global__ void __launch_bounds__(256, 6) k_window_part_uniform(ScanArgs A, u32 
 			const u32 j = x - qr * nwin + 1;
 			eq[r] = A.lo + qr; eb[r] = 0; ef[r] = 0;
 			u32 part = 0;
-			const bool pass = x < total && window_key(A, A.R.words + (u64)eq[r] * stride, j, eb[r], ef[r], part);
+			bool valid = x < total;
+			const u64 *s = nullptr;
+			if (UNIFORM) s = A.R.words + (u64)eq[r] * stride;                   // one read length: no geometry load, no contained reads
+			else if (valid) {
+				u64 off; u32 L1;
+				read_geom(A.R, eq[r], off, L1);
+				s = A.R.words + off;
+				valid = j <= L1 - h - 1;
+				if (MODE == MODE_OVERLAP && valid && A.contained) valid = !((__ldg(A.contained + (eq[r] >> 5)) >> (eq[r] & 31)) & 1);   // (:548)
+				c_valid += valid;
+			}
+			const bool pass = valid && window_key(A, s, j, eb[r], ef[r], part);
 			ep[r] = pass ? (part << 16) | atomicAdd(&s_cnt[part], 1u) : 0xFFFFFFFFu;
 		}
 		__syncthreads();
@@ -793,7 +810,13 @@ __global__ void __launch_bounds__(256, 6) k_window_part_uniform(ScanArgs A, u32 
 			}
 		__syncthreads();
 	}
-	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.ctr + CTR_PROBES, (u64)total);
+	if (UNIFORM) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.ctr + CTR_PROBES, (u64)total); }
+	else {
+		c_valid = __reduce_add_sync(0xFFFFFFFFu, c_valid);
+		if ((threadIdx.x & 31) == 0 && c_valid) atomicAdd(&s_valid, c_valid);
+		__syncthreads();
+		if (threadIdx.x == 0 && s_valid) atomicAdd(A.ctr + CTR_PROBES, (u64)s_valid);
+	}
 }
 
 template <int MODE>
