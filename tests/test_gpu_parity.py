@@ -236,8 +236,10 @@ def test_partitioned_probe_with_skewed_partitions(ctx, monkeypatch):
     share -- the build retries with more slack and still returns the oracle's graph."""
     from metagenomics_b200 import edges_as_tuples, synth
     monkeypatch.setenv("OGB_SUB_PARTITIONS", "8")
-    for cfg in (datasets.tandem(), datasets.repeats(), datasets.palindromes(), datasets.from_strings(["ACACACACACACACACACACACACACACACACACACACACACAC" + "G" * i + "T" for i in range(1, 12)], 10, "same lead"), synth.config(2, scale=0.02)):
+    for cfg in (datasets.tandem(), datasets.repeats(), datasets.palindromes(), datasets.from_strings(["ACACACACACACACACACACACACACACACACACACACACACAC" + "G" * i + "T" for i in range(1, 12)], 10, "same lead"), synth.config(2, scale=0.02),
+                datasets.tandem(mixed=True), synth.containment_stress(7, genome_len=6000, n_primary=1500)):   # mixed lengths: K2 through the queues too
         ds, ht, og = build_gpu(ctx, cfg)
         orc = Oracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"]).run_all(Oracle.BFS)
+        assert np.array_equal(og.superReadIDs()[1:], orc.read_info()["sup"])
         assert_same_edges(edges_as_tuples(og.edges(pre=True)), orc.edges(pre=True), "pre-reduction, 8 partitions")
         assert_same_edges(edges_as_tuples(og.edges()), orc.edges(), "post-reduction, 8 partitions")
