@@ -5,7 +5,9 @@ built by oracle/Makefile from /root/reference/MetaGenomics). Run in the build co
 
 Each .npz holds the raw input reads and the reference's own output at OverlapGraph.cpp:210:
 edges (src, dst, overlapOffset, orientation) sorted canonically, superReadID, frequency, read
-lengths, fnv1a of every forward string (pins the Dataset sort/dedupe order), numberOfNodes/Edges."""
+lengths, fnv1a of every forward string (pins the Dataset sort/dedupe order), numberOfNodes/Edges -- and, for the next row of
+SURVEY.md 8(f), the reference graph after its contractCompositePaths / removeDeadEndNodes fix-point (:211-215):
+c_edges (src, dst, orient, nlist, overlapOffset), c_list_start, c_lists (read, overlapOffset, orientation)."""
 import os
 import sys
 import tempfile
@@ -37,13 +39,15 @@ def main():
         with tempfile.TemporaryDirectory() as td:
             fa = os.path.join(td, "in.fa")
             synth.write_fasta(fa, cfg["bases"], cfg["offsets"])
-            d, t, _ = run_reference([fa], cfg["min_overlap"], paired=cfg["paired"])
+            d, t, _ = run_reference([fa], cfg["min_overlap"], paired=cfg["paired"], contracted=True)
         out = os.path.join(HERE, name + ".npz")
         np.savez_compressed(out, bases=cfg["bases"], offsets=cfg["offsets"], min_overlap=np.int64(cfg["min_overlap"]),
                             edges=d["edges"], sup=d["reads"]["sup"], freq=d["reads"]["freq"], len=d["reads"]["len"],
                             fnv=d["reads"]["fnv"], number_of_nodes=np.int64(d["number_of_nodes"]),
-                            number_of_edges=np.int64(d["number_of_edges"]), n_good=np.int64(t["n_reads"]))
-        print(f"{name}: {d['n']} unique reads, {len(d['edges'])} edges -> {os.path.getsize(out)} bytes")
+                            number_of_edges=np.int64(d["number_of_edges"]), n_good=np.int64(t["n_reads"]),
+                            c_edges=d["contracted"]["edges"], c_list_start=d["contracted"]["list_start"], c_lists=d["contracted"]["lists"],
+                            c_number_of_nodes=np.int64(d["contracted"]["number_of_nodes"]), c_number_of_edges=np.int64(d["contracted"]["number_of_edges"]))
+        print(f"{name}: {d['n']} unique reads, {len(d['edges'])} edges, {len(d['contracted']['edges'])} after contraction -> {os.path.getsize(out)} bytes")
 
 
 if __name__ == "__main__":

@@ -136,6 +136,27 @@ def read_dump(path):
                 edges=sort_tuples(edges))
 
 
+def read_dump2(path):
+    """Second dump of oracle/ref_harness.cpp (--dump2): the reference graph after its contractCompositePaths /
+    removeDeadEndNodes fix-point (OverlapGraph.cpp:211-215). Returns edges (n,5) [src,dst,orient,nlist,offset] (uint64),
+    and the concatenated per-edge lists (m,3) [read, overlapOffset, orientation] with list_start (n+1)."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    hdr = np.frombuffer(raw[:40].tobytes(), dtype="<u8")
+    assert hdr[0] == 0x32504d554442474f, "bad dump2 magic"
+    n, ne = int(hdr[1]), int(hdr[2])
+    edges = np.zeros((ne, 5), np.uint64); starts = np.zeros(ne + 1, np.int64); lists = []
+    p = 40
+    for i in range(ne):
+        a = np.frombuffer(raw[p:p + 16].tobytes(), dtype="<u4"); off = int(np.frombuffer(raw[p + 16:p + 24].tobytes(), dtype="<u8")[0]); p += 24
+        nl = int(a[3])
+        edges[i] = (a[0], a[1], a[2], nl, off)
+        lists.append(np.frombuffer(raw[p:p + 12 * nl].tobytes(), dtype="<u4").reshape(nl, 3)); p += 12 * nl
+        starts[i + 1] = starts[i] + nl
+    assert p == len(raw)
+    return dict(n=n, number_of_nodes=int(hdr[3]), number_of_edges=int(hdr[4]), edges=edges, list_start=starts,
+                lists=np.concatenate(lists) if lists else np.zeros((0, 3), np.uint32))
+
+
 def sort_tuples(e):
     """canonical order (src, offset, dst, orient) of an (n,4) [src,dst,offset,orient] array."""
     e = np.asarray(e, dtype=np.uint32).reshape(-1, 4)
@@ -145,17 +166,22 @@ def sort_tuples(e):
     return np.ascontiguousarray(e[idx])
 
 
-def run_reference(fasta_paths, min_overlap, paired=False, want_table=False, binary=REF_BIN, timeout=3600):
-    """Runs the unmodified reference on FASTA files; returns (dump dict, timing json, table lists|None)."""
+def run_reference(fasta_paths, min_overlap, paired=False, want_table=False, binary=REF_BIN, timeout=3600, contracted=False):
+    """Runs the unmodified reference on FASTA files; returns (dump dict, timing json, table lists|None). contracted=True:
+    the dump dict gets a "contracted" entry (read_dump2: the graph after OverlapGraph.cpp:211-215)."""
     with tempfile.TemporaryDirectory() as td:
         dump, js, tab = os.path.join(td, "d.bin"), os.path.join(td, "t.json"), os.path.join(td, "tab.bin")
         cmd = [binary, "-l", str(min_overlap), "--dump", dump, "--json", js]
+        if contracted:
+            cmd += ["--dump2", os.path.join(td, "d2.bin")]
         for p in fasta_paths:
             cmd += ["-pe" if paired else "-se", p]
         if want_table:
             cmd += ["--table", tab]
         subprocess.run(cmd, check=True, timeout=timeout, cwd=td)
         d = read_dump(dump)
+        if contracted:
+            d["contracted"] = read_dump2(os.path.join(td, "d2.bin"))
         with open(js) as f:
             t = json.load(f)
         table = None

@@ -56,3 +56,40 @@ def test_oracle_matches_live_reference(tmp_path):
             f, r = orc.get_read(i), orc.get_read(i, True)
             for k, key in enumerate([f[:h], f[-h:], r[:h], r[-h:]]):
                 assert np.array_equal(orc.lookup(key), table[(i - 1) * 4 + k])
+
+
+@pytest.mark.parametrize("name", sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))))
+def test_contracted_fixture_is_consistent(name):
+    """Fixtures for the next row of SURVEY.md 8(f) (contractCompositePaths + removeDeadEndNodes, OverlapGraph.cpp:211-215),
+    dumped from the unmodified reference by tests/golden/make_golden.py: structural invariants of the composite edges
+    (OverlapGraph.cpp:702-785 mergeEdges / mergeList) relative to the graph at :210 that the CUDA path reproduces."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    if "c_edges" not in g.files:
+        pytest.skip("fixture predates the contracted dump")
+    ce, ls, cl = g["c_edges"].astype(np.int64), g["c_list_start"], g["c_lists"].astype(np.int64)
+    assert int(g["c_number_of_edges"]) == len(ce)
+    assert int(g["c_number_of_nodes"]) == len(set(ce[:, 0].tolist()))
+    simple = {(int(s), int(d), int(o), int(t)) for s, d, o, t in g["edges"].tolist()}          # (src, dst, overlapOffset, orientation) at :210
+    twin_or = {0: 3, 3: 0, 1: 1, 2: 2}
+    have = {}
+    for i, (s, d, o, nl, off) in enumerate(ce.tolist()):
+        have.setdefault((s, d, o), []).append(i)
+    interior = set()
+    for i, (s, d, o, nl, off) in enumerate(ce.tolist()):
+        lst = cl[ls[i]:ls[i + 1]]
+        assert len(lst) == nl
+        if nl == 0:
+            assert (s, d, off, o) in simple                            # an edge the contraction left alone
+        else:
+            assert lst[:, 1].sum() < off                               # mergeList: the last hop is overlapOffset - sum
+            interior.update(lst[:, 0].tolist())
+            # the path s -> r1 -> ... -> rk -> d consists of simple edges of the graph at :210 with these hop offsets
+            path = [s] + lst[:, 0].tolist() + [d]
+            hops = lst[:, 1].tolist() + [off - int(lst[:, 1].sum())]
+            for a, b, h in zip(path[:-1], path[1:], hops):
+                assert any((a, b, h, t) in simple for t in range(4)), (name, a, b, h)
+        # twin: reverse direction, twin orientation (:841-855), the reads of the list reversed
+        cands = have.get((d, s, twin_or[o]), [])
+        assert any(cl[ls[j]:ls[j + 1], 0].tolist() == cl[ls[i]:ls[i + 1], 0].tolist()[::-1] for j in cands), (name, s, d)
+    # a read inside a composite edge has been contracted away: it owns no edge any more
+    assert not (interior & set(ce[:, 0].tolist()))
