@@ -93,3 +93,23 @@ def test_contracted_fixture_is_consistent(name):
         assert any(cl[ls[j]:ls[j + 1], 0].tolist() == cl[ls[i]:ls[i + 1], 0].tolist()[::-1] for j in cands), (name, s, d)
     # a read inside a composite edge has been contracted away: it owns no edge any more
     assert not (interior & set(ce[:, 0].tolist()))
+
+
+@pytest.mark.parametrize("name", sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))))
+def test_contraction_restatement_matches_reference(name):
+    """oracle/contract_oracle.py (plain-Python restatement of OverlapGraph.cpp:211-215), started from the CANONICAL order
+    of the graph at :210, reproduces the unmodified reference's composite edges -- endpoints, orientation, offset and the
+    read / offset / orientation lists -- on every fixture: the stage does not depend on the reference's list order."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("contract_oracle", os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "contract_oracle.py"))
+    co = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(co)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    if "c_edges" not in g.files:
+        pytest.skip("fixture predates the contracted dump")
+    got = co.Graph(g["edges"].tolist(), g["len"].tolist()).simplify().edge_records()
+    ce, ls, cl = g["c_edges"].astype(np.int64), g["c_list_start"], g["c_lists"].astype(np.int64)
+    want = sorted((int(s), int(d), int(o), int(off), tuple(cl[ls[i]:ls[i + 1], 0].tolist()), tuple(cl[ls[i]:ls[i + 1], 1].tolist()),
+                   tuple(cl[ls[i]:ls[i + 1], 2].tolist())) for i, (s, d, o, nl, off) in enumerate(ce.tolist()))
+    assert len(got) == len(want), (len(got), len(want))
+    assert got == want
