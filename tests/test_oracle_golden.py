@@ -113,3 +113,25 @@ def test_contraction_restatement_matches_reference(name):
                    tuple(cl[ls[i]:ls[i + 1], 2].tolist())) for i, (s, d, o, nl, off) in enumerate(ce.tolist()))
     assert len(got) == len(want), (len(got), len(want))
     assert got == want
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref/ref_overlap not built (needs /root/reference)")
+def test_contraction_restatement_matches_live_reference(tmp_path):
+    """The same comparison against the unmodified reference run here (--dump2), on seeded sets beyond the fixtures:
+    every adversarial set plus larger samples of configs 2, 3 and 5."""
+    import importlib.util
+    from metagenomics_b200 import synth
+    spec = importlib.util.spec_from_file_location("contract_oracle", os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "contract_oracle.py"))
+    co = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(co)
+    sets = datasets.adversarial() + [synth.config(2, scale=0.004), synth.config(3, scale=0.0006), synth.containment_stress(9, genome_len=9000, n_primary=2500)]
+    for k, cfg in enumerate(sets):
+        fa = str(tmp_path / f"in{k}.fa")
+        synth.write_fasta(fa, cfg["bases"], cfg["offsets"])
+        d, _, _ = run_reference([fa], cfg["min_overlap"], paired=cfg["paired"], contracted=True)
+        c = d["contracted"]
+        ce, ls, cl = c["edges"].astype(np.int64), c["list_start"], c["lists"].astype(np.int64)
+        want = sorted((int(s), int(t), int(o), int(off), tuple(cl[ls[i]:ls[i + 1], 0].tolist()), tuple(cl[ls[i]:ls[i + 1], 1].tolist()),
+                       tuple(cl[ls[i]:ls[i + 1], 2].tolist())) for i, (s, t, o, nl, off) in enumerate(ce.tolist()))
+        got = co.Graph(d["edges"].tolist(), d["reads"]["len"].tolist()).simplify().edge_records()
+        assert got == want, (cfg["name"], len(got), len(want))
