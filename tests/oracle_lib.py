@@ -118,6 +118,93 @@ class Oracle:
         return self
 
 
+LEAN_SO = os.path.join(ROOT, "oracle", "liblean.so")
+_lean = None
+
+
+def _llib():
+    global _lean
+    if _lean is None:
+        l = C.CDLL(LEAN_SO)
+        vp, u64 = C.c_void_p, C.c_uint64
+        l.lean_create.restype = vp
+        l.lean_create.argtypes = [C.c_int]
+        l.lean_destroy.argtypes = [vp]
+        l.lean_load_reads.argtypes = [vp, vp, vp, u64, C.c_uint32]
+        for f in ("lean_n_unique", "lean_n_good", "lean_n_edges"):
+            getattr(l, f).restype = u64
+            getattr(l, f).argtypes = [vp]
+        l.lean_run.argtypes = [vp, C.c_int]
+        l.lean_read_info.argtypes = [vp, vp, vp, vp, vp]
+        l.lean_counters.argtypes = [vp, vp]
+        l.lean_get_edges.argtypes = [vp, vp]
+        l.lean_degrees.argtypes = [vp, vp]
+        _lean = l
+    return _lean
+
+
+class LeanOracle:
+    """Memory-lean three-phase restatement (oracle/lean_oracle.cpp) for BASELINE.json sizes: counters and an
+    order-independent checksum of the final edge set; the tuples themselves only when keep_edges is set."""
+
+    def __init__(self, bases, offsets, min_overlap, threads=None):
+        self.l = _llib()
+        self.h = self.l.lean_create(threads or os.cpu_count() or 1)
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.l.lean_load_reads(self.h, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, min_overlap)
+        self.n = self.l.lean_n_unique(self.h)
+        self.n_good = self.l.lean_n_good(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.l.lean_destroy(self.h)
+            self.h = None
+
+    def run(self, keep_edges=False):
+        if self.l.lean_run(self.h, 1 if keep_edges else 0) != 0:
+            raise RuntimeError("lean oracle: hashStringLength must be 1..64")
+        return self
+
+    def counters(self):
+        out = np.zeros(14, np.uint64)
+        self.l.lean_counters(self.h, out.ctypes.data)
+        keys = ["n_unique", "E_pre", "E_final", "nodes", "contained", "max_degree", "P_e", "T", "active_pivots", "P_c", "C_c",
+                "ck_xor", "ck_sum", "asymmetric"]
+        return dict(zip(keys, (int(x) for x in out)))
+
+    def checksum(self):
+        c = self.counters()
+        return [c["ck_xor"], c["ck_sum"]]
+
+    def edges(self):
+        n = self.l.lean_n_edges(self.h)
+        out = np.zeros((n, 4), np.uint32)
+        self.l.lean_get_edges(self.h, out.ctypes.data)
+        return out
+
+    def read_info(self):
+        sup = np.zeros(self.n, np.uint64); ln = np.zeros(self.n, np.uint32)
+        fr = np.zeros(self.n, np.uint32); fnv = np.zeros(self.n, np.uint64)
+        self.l.lean_read_info(self.h, sup.ctypes.data, ln.ctypes.data, fr.ctypes.data, fnv.ctypes.data)
+        return dict(sup=sup, len=ln, freq=fr, fnv=fnv)
+
+    def degrees(self):
+        out = np.zeros(self.n, np.uint32)
+        self.l.lean_degrees(self.h, out.ctypes.data)
+        return out
+
+
+def edge_checksum(e):
+    """xor and sum of a 64-bit mix of every (src, dst, offset, orient) tuple: independent of order
+    (the same mix as lean_oracle.cpp mix_tuple and tests/golden/make_full_size.py)."""
+    e = np.asarray(e).astype(np.uint64).reshape(-1, 4)
+    x = (e[:, 0] * np.uint64(0x9E3779B97F4A7C15) ^ e[:, 1] * np.uint64(0xC2B2AE3D27D4EB4F) ^ e[:, 2] * np.uint64(0x165667B19E3779F9)
+         ^ e[:, 3] * np.uint64(0x27D4EB2F165667C5))
+    x ^= x >> np.uint64(29); x *= np.uint64(0xBF58476D1CE4E5B9); x ^= x >> np.uint64(32)
+    return [int(np.bitwise_xor.reduce(x)) if len(x) else 0, int(x.sum(dtype=np.uint64))]
+
+
 def have_reference():
     return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
 

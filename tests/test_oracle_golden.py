@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import datasets
-from oracle_lib import Oracle, have_reference, run_reference
+from oracle_lib import LeanOracle, Oracle, edge_checksum, have_reference, run_reference
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FILES = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
@@ -38,6 +38,37 @@ def test_formulations_agree_on_pre_reduction_edges():
         b = Oracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"]).run_all(Oracle.THREE_PHASE, threads=3)
         assert np.array_equal(a.edges(pre=True), b.edges(pre=True)), cfg["name"]
         assert np.array_equal(a.edges(), b.edges()), cfg["name"]
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
+def test_lean_oracle_matches_golden(path):
+    """oracle/lean_oracle.cpp (the memory-lean three-phase form behind the full-size goldens) against the committed dumps of
+    the unmodified reference: read IDs, lengths, frequencies, superReadID, the final edge tuples and the node / edge counts."""
+    z = np.load(path)
+    lean = LeanOracle(z["bases"], z["offsets"], int(z["min_overlap"]), threads=3).run(keep_edges=True)
+    info = lean.read_info()
+    assert lean.n_good == int(z["n_good"])
+    assert np.array_equal(info["fnv"], z["fnv"]) and np.array_equal(info["len"], z["len"]) and np.array_equal(info["freq"], z["freq"])
+    assert np.array_equal(info["sup"], z["sup"])
+    assert np.array_equal(lean.edges(), z["edges"])
+    c = lean.counters()
+    assert c["nodes"] == int(z["number_of_nodes"]) and c["E_final"] == int(z["number_of_edges"]) and c["asymmetric"] == 0
+    assert lean.checksum() == edge_checksum(z["edges"])
+
+
+def test_lean_oracle_matches_port():
+    """... and against omega_oracle.cpp (pinned to the reference) on every seeded set of the parity suite, counters included."""
+    for cfg in datasets.adversarial() + datasets.small_configs():
+        a = Oracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"]).run_all(Oracle.THREE_PHASE, threads=3)
+        b = LeanOracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"], threads=3).run(keep_edges=True)
+        ia, ib = a.read_info(), b.read_info()
+        for k in ("fnv", "len", "freq", "sup"):
+            assert np.array_equal(ia[k], ib[k]), (cfg["name"], k)
+        assert np.array_equal(a.edges(), b.edges()), cfg["name"]
+        ca, cb = a.counters(), b.counters()
+        assert (ca["E_pre"], ca["number_of_edges"], ca["number_of_nodes"], ca["P_e"], ca["T"], ca["active_pivots"], ca["max_degree"], ca["P_c"], ca["C_c"]) == \
+               (cb["E_pre"], cb["E_final"], cb["nodes"], cb["P_e"], cb["T"], cb["active_pivots"], cb["max_degree"], cb["P_c"], cb["C_c"]), cfg["name"]
+        assert b.checksum() == edge_checksum(a.edges())
 
 
 @pytest.mark.skipif(not have_reference(), reason="oracle/_ref/ref_overlap not built (needs /root/reference)")
