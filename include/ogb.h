@@ -76,11 +76,13 @@ typedef struct ogb_stats {
 	uint64_t overflow_reads;   /* heavy nodes of this rank (degree > slots per read: list kept in the extension area) */
 	uint32_t kernel_launches;  /* kernels of this library launched by the last hash_build+build_graph */
 	uint32_t probe_launches;   /* launches of the probe kernel (one per chunk of query reads) */
+	uint32_t hash_partitions;  /* hash partitions of the index (ranks x partitions per rank) */
+	uint32_t hash_build_attempts; /* 1 + retries of K1 after a partition filled up (skewed keys) */
 	float ms_pack;             /* K0 */
 	float ms_hash_build;       /* K1 */
 	float ms_contain;          /* K2 (+ allreduce) */
 	float ms_overlap;          /* K3 probe + verify (all chunks), degree scan, heavy-list placement */
-	float ms_exchange_pre;     /* C1: k_pack_adj + allgather of packed lists and node records (0 on one GPU) */
+	float ms_exchange_pre;     /* row headers + overflow entries (k_rows_finish) and, on several ranks, C1: allgather of the adjacency rows */
 	float ms_mark;             /* K5 */
 	float ms_reduce;           /* K6 (+C2/C3) */
 	float ms_total;            /* hash_build + mark_contained + build_graph, device time */

@@ -25,7 +25,7 @@ class Stats(C.Structure):
         "n_reads", "table_buckets", "table_bytes", "n_contained", "contain_probes", "contain_hits",
         "overlap_probes", "probe_sectors", "candidates", "edges_pre", "edges_pre_local", "pivot_entries",
         "active_pivots", "edges_final", "nodes_final", "max_degree", "overflow_reads")] + [
-        ("kernel_launches", C.c_uint32), ("probe_launches", C.c_uint32)] + [(n, C.c_float) for n in (
+        ("kernel_launches", C.c_uint32), ("probe_launches", C.c_uint32), ("hash_partitions", C.c_uint32), ("hash_build_attempts", C.c_uint32)] + [(n, C.c_float) for n in (
             "ms_pack", "ms_hash_build", "ms_contain", "ms_overlap", "ms_exchange_pre", "ms_mark", "ms_reduce",
             "ms_total", "ms_scan_kernel", "ms_probe_launch", "ms_window_launch")]
 

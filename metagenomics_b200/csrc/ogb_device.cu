@@ -136,16 +136,17 @@ struct ogb_context {
 	Pool<u32> contained;
 	bool contain_done = false, any_contained = false;
 	// graph
-	Pool<u64> pos, sums, surv;       // surv: the first OGB_SURV surviving edge words of every own node
-	Pool<unsigned char> scratch_state;
-	Pool<u32> cnt, scratch_keys;
+	Pool<u64> pos, sums, surv;       // surv: the (at most OGB_SURV) surviving edge words of every own node
+	Pool<u64> cand, big;             // K5 -> K6: candidates per own node (edge word, twin bit address); record list of the nodes with more
+	Pool<u32> cnt, cntc, scratch_keys;
 	Pool<ogb_edge> fin, pre, fin_stage;
 	// the adjacency: per-read slot regions, degrees, heavy lists (GraphView)
 	Pool<u64> slots_e, ext;
 	Pool<u32> deg;
-	// several ranks: every rank's lists packed to 4-byte entries + node records + ELIM bits, allgathered
-	Pool<u64> nodes;
-	Pool<u32> adj32, ebits;
+	// what a node looks like to the others (pivot scans, twin verdicts): 128-byte rows by global read index, overflow
+	// entries per rank segment, one ELIM bit per entry (GraphView); on several ranks each is allgathered
+	Pool<u32> rows, more, ebits;
+	u64 more_stride = 0;
 	// scan staging: candidate queue of one chunk, spill list of heavy nodes
 	Pool<u32> cand_q, fill, ov_q;    // cand_q / cand_v hold two ping-pong queues of cand_cap entries
 	Pool<u64> cand_v, ov_e;
@@ -174,7 +175,7 @@ struct ogb_context {
 	{
 		Table t;
 		t.slots = slots.p; t.summary = use_summary ? summary.p : nullptr; t.nb = nb; t.nparts = nparts; t.part_buckets = nb / nparts;
-		t.sub = nparts / nranks; t.my_rank = rank; t.h = h;
+		t.sub = nparts / nranks; t.my_rank = rank; t.h = h; t.ctr = d_ctr;
 		return t;
 	}
 	void shard(u32 &lo, u32 &hi) const
@@ -265,6 +266,7 @@ extern "C" int ogb_nccl_unique_id(void *out128)
 extern "C" int ogb_context_create_dist(ogb_context **out, int device, int rank, int n_ranks, const void *nccl_uid)
 {
 	if (n_ranks < 1 || rank < 0 || rank >= n_ranks) { ogb_set_error("ogb_context_create_dist: bad rank %d of %d", rank, n_ranks); return OGB_E_ARG; }
+	if (n_ranks > OGB_MAX_RANKS || n_ranks > OGB_MAXPART) { ogb_set_error("ogb_context_create_dist: at most %d ranks", OGB_MAX_RANKS < OGB_MAXPART ? OGB_MAX_RANKS : OGB_MAXPART); return OGB_E_ARG; }
 	OGB_TRY(context_create_common(out, device));
 	ogb_context *c = *out;
 	c->rank = rank; c->nranks = n_ranks;
@@ -287,7 +289,7 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	if (c->comm) g_nccl.CommDestroy(c->comm);
 	c->words.release(); c->meta.release(); c->stage_bytes.release(); c->stage_offs.release(); c->stage_lens.release();
 	c->slots.release(); c->summary.release(); c->sup.release(); c->contained.release(); c->pos.release();
-	c->sums.release(); c->surv.release(); c->scratch_state.release(); c->cnt.release();
+	c->sums.release(); c->surv.release(); c->cand.release(); c->big.release(); c->cntc.release(); c->cnt.release();
 	c->scratch_keys.release(); c->fin.release(); c->pre.release(); c->flush.release(); c->fin_stage.release();
 	if (c->d_ctr) cudaFree(c->d_ctr);
 	if (c->d_tot) cudaFree(c->d_tot);
@@ -296,7 +298,7 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	c->pq_b.release(); c->pq_f.release(); c->pq_q.release();
 	if (c->d_xchg) cudaFree(c->d_xchg);
 	c->cand_q.release(); c->deg.release(); c->fill.release(); c->ov_q.release();
-	c->cand_v.release(); c->slots_e.release(); c->ext.release(); c->ov_e.release(); c->nodes.release(); c->adj32.release(); c->ebits.release();
+	c->cand_v.release(); c->slots_e.release(); c->ext.release(); c->ov_e.release(); c->rows.release(); c->more.release(); c->ebits.release();
 	if (c->h_ctr) cudaFreeHost(c->h_ctr);
 	for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 128; i++) if (c->ev_pk[i]) cudaEventDestroy(c->ev_pk[i]);
@@ -463,7 +465,7 @@ extern "C" int ogb_reads_upload_dataset(ogb_context *c, const ogb_dataset *ds)
 	return ogb_reads_upload_packed(c, w, ogb_dataset_word_offsets(ds), ogb_dataset_lengths(ds), ogb_dataset_n_unique(ds));
 }
 
-static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *d_total, u64 *d_max = nullptr);
+static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *d_total, u64 *d_max = nullptr, u64 *d_more = nullptr);
 
 // ------------------------------------------------------------------------------------------------
 // Dataset stage on the device
@@ -577,6 +579,13 @@ extern "C" int ogb_dataset_finalize_device(ogb_dataset *ds, ogb_context *c, uint
 	const int rc = run();
 	release();
 	lap("cudaFree");
+	if (rc != OGB_OK) {
+		// leave the dataset as it was before the call: the raw reads stay, so the caller can still run ogb_dataset_finalize on the host
+		ds->finalized = false;
+		ds->lens.clear(); ds->freq.clear(); ds->word_offs.clear(); ds->words.clear();
+		ds->resident_ctx = nullptr;
+		return rc;
+	}
 	ds->raw.clear(); ds->raw.shrink_to_fit();
 	ds->raw_offs.clear(); ds->raw_offs.shrink_to_fit();
 	lap("free raw");
@@ -596,26 +605,11 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 	c->h = min_overlap - 1;                                                 // HashTable.cpp:54
 	// The reference sizes the table at the first listed prime > 8N+1 slots (HashTable.cpp:56), i.e.
 	// load factor <= 0.5 for its 4N entries. Here: N buckets of 10 slots (64 B per read, load 0.4).
-	u64 nb = std::max<u64>((u64)c->n + 1, 512);
-	const char *lf = getenv("OGB_TABLE_BUCKETS_PER_READ");
-	if (lf && atof(lf) >= 0.5) nb = std::max<u64>((u64)(atof(lf) * c->n) + 1, 512);
-	// One hash partition per rank: every rank inserts only the keys of its own partition (a slice of
-	// nb/G buckets that stays L2- and TLB-friendly), then the slices are allgathered. A replicated build
-	// of the whole table cost 3.8 ms at 8 ranks (TLB-bound inserts into 664 MB).
-	// Partitions per rank: 1 while a rank's slice fits L2; beyond that the slice is cut into pieces of <= 48 MB, the
-	// unit the partitioned probe (k_window_part / k_probe_parts) works through at a time.
+	double buckets_per_read = 1.0;
 	{
-		const u64 slice_bytes = nb * OGB_BWORDS * sizeof(u32) / c->nranks;
-		u64 sub = slice_bytes > (96ull << 20) ? (slice_bytes + (48ull << 20) - 1) / (48ull << 20) : 1;
-		const char *e = getenv("OGB_SUB_PARTITIONS");                        // experiment knob
-		if (e && atoi(e) >= 1) sub = (u64)atoi(e);
-		sub = std::max<u64>(1, std::min<u64>(sub, OGB_MAXPART / c->nranks));
-		c->nparts = (u32)(c->nranks * sub);
+		const char *lf = getenv("OGB_TABLE_BUCKETS_PER_READ");
+		if (lf && atof(lf) >= 0.5) buckets_per_read = atof(lf);
 	}
-	nb = (nb + c->nparts - 1) / c->nparts * c->nparts;
-	if (nb >= (1ull << 32)) { ogb_set_error("index too large"); return OGB_E_CAPACITY; }
-	c->nb = (u32)nb;
-	OGB_TRY(c->slots.ensure(nb * OGB_BWORDS));
 	{
 		// The per-bucket summary (4 B per bucket) lets the probe drop the windows that cannot have an entry before
 		// the bucket fetch and compact the rest (PendQueue); OGB_SUMMARY=0 turns it off (experiment knob).
@@ -629,30 +623,66 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 		const char *e = getenv("OGB_PARTITIONED");
 		c->partitioned = e ? atoi(e) != 0 : true;
 	}
-	if (c->use_summary) OGB_TRY(c->summary.ensure(nb));
 	c->launches = 0;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_HASH0], c->stream));
-	{
-		// only this rank's slice is cleared and filled; the allgather below overwrites the others
-		const u64 pb = nb / c->nranks;
-		CUDA_TRY(cudaMemsetAsync(c->slots.p + pb * OGB_BWORDS * c->rank, 0, pb * OGB_BWORDS * sizeof(u32), c->stream));
-		if (c->use_summary) CUDA_TRY(cudaMemsetAsync(c->summary.p + pb * c->rank, 0, pb * sizeof(u32), c->stream));
+	// One hash partition per rank: every rank inserts only the keys of its own partition (a slice of
+	// nb/G buckets that stays L2- and TLB-friendly), then the slices are allgathered. A replicated build
+	// of the whole table cost 3.8 ms at 8 ranks (TLB-bound inserts into 664 MB).
+	// Partitions per rank: 1 while a rank's slice fits L2; beyond that the slice is cut into pieces of <= 48 MB, the
+	// unit the partitioned probe (k_window_part / k_probe_parts) works through at a time.
+	// A partition is chosen by the key's first 16 bases alone and linear probing wraps inside it, so a skewed read set can
+	// fill one up (K1 raises CTR_TABLE_FULL after a whole lap): the build is then repeated with half as many partitions per
+	// rank and, once there is one per rank, with twice the buckets -- a collective decision, all ranks see the same flag.
+	u64 sub_limit = OGB_MAXPART / c->nranks, nb = 0;
+	for (int attempt = 0;; attempt++) {
+		if (attempt == 12) { ogb_set_error("ogb_hash_build: a hash partition kept filling up (%u partitions, %.1f buckets per read)", c->nparts, buckets_per_read); return OGB_E_CAPACITY; }
+		nb = std::max<u64>((u64)(buckets_per_read * c->n) + 1, 512);
+		{
+			const u64 slice_bytes = nb * OGB_BWORDS * sizeof(u32) / c->nranks;
+			u64 sub = slice_bytes > (96ull << 20) ? (slice_bytes + (48ull << 20) - 1) / (48ull << 20) : 1;
+			const char *e = getenv("OGB_SUB_PARTITIONS");                        // experiment knob
+			if (e && atoi(e) >= 1) sub = (u64)atoi(e);
+			sub = std::max<u64>(1, std::min<u64>(sub, sub_limit));
+			c->nparts = (u32)(c->nranks * sub);
+		}
+		nb = (nb + c->nparts - 1) / c->nparts * c->nparts;
+		if (nb >= (1ull << 32)) { ogb_set_error("index too large"); return OGB_E_CAPACITY; }
+		c->nb = (u32)nb;
+		OGB_TRY(c->slots.ensure(nb * OGB_BWORDS));
+		if (c->use_summary) OGB_TRY(c->summary.ensure(nb));
+		{
+			// only this rank's slice is cleared and filled; the allgather below overwrites the others
+			const u64 pb = nb / c->nranks;
+			CUDA_TRY(cudaMemsetAsync(c->slots.p + pb * OGB_BWORDS * c->rank, 0, pb * OGB_BWORDS * sizeof(u32), c->stream));
+			if (c->use_summary) CUDA_TRY(cudaMemsetAsync(c->summary.p + pb * c->rank, 0, pb * sizeof(u32), c->stream));
+		}
+		CUDA_TRY(cudaMemsetAsync(c->d_ctr + CTR_TABLE_FULL, 0, sizeof(u64), c->stream));
+		if (c->n) {
+			u64 threads = (u64)c->n * 4;
+			k_hash_insert<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->rs(), c->tb());
+			CUDA_TRY(cudaGetLastError());
+			c->launches++;
+		}
+		// the verdict travels with the slices: on several ranks it is max-reduced first (tiny), then every rank decides alike
+		u64 full = 0;
+		if (c->nranks > 1) NCCL_TRY(g_nccl.AllReduce(c->d_ctr + CTR_TABLE_FULL, c->d_ctr + CTR_TABLE_FULL, 1, NCCL_UINT64, NCCL_MAX, c->comm, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(c->h_ctr + CTR_TABLE_FULL, c->d_ctr + CTR_TABLE_FULL, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		if (c->nranks > 1) {
+			const u64 pb = nb / c->nranks;
+			NCCL_TRY(g_nccl.AllGather(c->slots.p + pb * OGB_BWORDS * c->rank, c->slots.p, pb * OGB_BWORDS, NCCL_UINT32, c->comm, c->stream));
+			if (c->use_summary) NCCL_TRY(g_nccl.AllGather(c->summary.p + pb * c->rank, c->summary.p, pb, NCCL_UINT32, c->comm, c->stream));
+		}
+		CUDA_TRY(cudaEventRecord(c->ev[EV_HASH1], c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		full = c->h_ctr[CTR_TABLE_FULL];
+		c->st.hash_build_attempts = (uint32_t)attempt + 1;
+		if (!full) break;
+		if (c->nparts > (u32)c->nranks) sub_limit = std::max<u64>(1, c->nparts / c->nranks / 2);
+		else buckets_per_read *= 2;
 	}
-	if (c->n) {
-		u64 threads = (u64)c->n * 4;
-		k_hash_insert<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->rs(), c->tb());
-		CUDA_TRY(cudaGetLastError());
-		c->launches++;
-	}
-	if (c->nranks > 1) {
-		const u64 pb = nb / c->nranks;
-		NCCL_TRY(g_nccl.AllGather(c->slots.p + pb * OGB_BWORDS * c->rank, c->slots.p, pb * OGB_BWORDS, NCCL_UINT32, c->comm, c->stream));
-		if (c->use_summary) NCCL_TRY(g_nccl.AllGather(c->summary.p + pb * c->rank, c->summary.p, pb, NCCL_UINT32, c->comm, c->stream));
-	}
-	CUDA_TRY(cudaEventRecord(c->ev[EV_HASH1], c->stream));
-	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	c->st.ms_hash_build = ev_ms(c, EV_HASH0, EV_HASH1);
 	c->st.table_buckets = nb;
+	c->st.hash_partitions = c->nparts;
 	c->st.table_bytes = nb * OGB_BWORDS * sizeof(u32);
 	c->part_chunk_set = false; c->pq_slack = 5;
 	if (!c->partitioned && c->chunk_reads > (1u << 16)) c->chunk_reads = 1u << 16;
@@ -731,7 +761,7 @@ static ScanArgs scan_args(ogb_context *c, u32 lo, u32 hi)
 	a.contained = c->any_contained ? c->contained.p : nullptr;
 	a.cand_q = c->cand_q.p; a.cand_v = c->cand_v.p; a.cand_cap = c->cand_cap; a.cand_cursor = c->d_cursor;
 	a.sup = c->sup.p; a.slots_e = c->slots_e.p; a.slot_lo = lo; a.cap = c->slot_cap; a.deg = c->deg.p;
-	a.ov_q = c->ov_q.p; a.ov_e = c->ov_e.p; a.ov_cap = c->ov_q.cap; a.ctr = c->d_ctr; a.prefetch = 1;
+	a.ov_q = c->ov_q.p; a.ov_e = c->ov_e.p; a.ov_cap = c->ov_q.cap; a.ctr = c->d_ctr; a.prefetch = 1; a.rows = c->rows.p;
 	return a;
 }
 
@@ -875,12 +905,12 @@ extern "C" int ogb_super_read_ids(ogb_context *c, uint64_t *out, uint64_t cap)
 // ------------------------------------------------------------------------------------------------
 // K3..K6
 // ------------------------------------------------------------------------------------------------
-static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *d_total, u64 *d_max)
+static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *d_total, u64 *d_max, u64 *d_more)
 {
 	u32 nblocks = (n + OGB_SCAN_ITEMS - 1) / OGB_SCAN_ITEMS;
 	if (nblocks == 0) nblocks = 1;
 	OGB_TRY(c->sums.ensure(nblocks + 1));
-	k_scan_sums<<<nblocks, 256, 0, c->stream>>>(cnt, n, c->sums.p, d_max);
+	k_scan_sums<<<nblocks, 256, 0, c->stream>>>(cnt, n, c->sums.p, d_max, d_more);
 	k_scan_top<<<1, 1024, 0, c->stream>>>(c->sums.p, nblocks, d_total);
 	k_scan_apply<<<nblocks, 256, 0, c->stream>>>(cnt, n, c->sums.p, out);
 	CUDA_TRY(cudaGetLastError());
@@ -891,8 +921,12 @@ static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *
 static GraphView graph_view(const ogb_context *c, u32 lo)
 {
 	GraphView g;
+	const u64 per = ((u64)c->n + c->nranks - 1) / c->nranks;
 	g.slots = c->slots_e.p; g.deg = c->deg.p; g.ext = c->ext.p; g.lo = lo; g.cap = c->slot_cap;
-	g.nodes = c->nodes.p; g.adj32 = c->adj32.p; g.ebits = c->ebits.p;
+	g.rows = c->rows.p; g.more = c->more.p; g.ebits = c->ebits.p;
+	g.more_stride = c->more_stride; g.nrows = per * c->nranks;
+	g.per_magic = c->nranks > 1 && per > 1 ? ~0ull / per + 1 : 0;          // exact floor(v / per) for 32-bit v (Lemire); per == 1: see rank_of
+	g.my_rank = (u32)c->rank;
 	return g;
 }
 
@@ -931,19 +965,22 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		if (e && atoi(e) >= 8 && atoi(e) <= 256) c->slot_cap = (u32)atoi(e);
 	}
 	OGB_TRY(c->cnt.ensure(per + 1));
+	OGB_TRY(c->cntc.ensure(per + 1));
 	OGB_TRY(c->pos.ensure(per + 1));
 	OGB_TRY(c->fill.ensure(per + 1));
 	OGB_TRY(c->surv.ensure((per + 1) * OGB_SURV));
+	OGB_TRY(c->cand.ensure((per + 1) * OGB_SURV * 2));
+	OGB_TRY(c->rows.ensure(per * G * OGB_ROW_W + 64));
 	if (c->ov_q.cap == 0) { OGB_TRY(c->ov_q.ensure(1 << 20)); OGB_TRY(c->ov_e.ensure(1 << 20)); }
 
-	// ---- K3 (probe + verify in chunks) into the slot regions; retried with larger pools when a capacity
-	// was exceeded. Every decision below derives from values all ranks share.
+	// ---- K3 (probe + verify in chunks) into the slot regions and the adjacency rows; retried with larger pools when a
+	// capacity was exceeded. Every decision below derives from values all ranks share.
 	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL0], c->stream));
-	u64 local_edges = 0, exact_edges = 0;
+	u64 local_edges = 0, exact_edges = 0, more_need = 0;
 	std::vector<u64> seg_cnt(G, 0);
 	for (int attempt = 0;; attempt++) {
 		if (attempt == 16) { ogb_set_error("ogb_build_graph: staging pools kept overflowing"); return OGB_E_CAPACITY; }
-		OGB_TRY(c->slots_e.ensure(per * c->slot_cap + 64));                 // +64: K5 fetches 32 slots of a pivot before it knows its degree
+		OGB_TRY(c->slots_e.ensure(per * c->slot_cap + 64));
 		OGB_TRY(c->deg.ensure((size_t)n + 1));
 		OGB_TRY(c->ext.ensure(1 << 16));
 		OGB_TRY(ctr_zero(c));
@@ -951,13 +988,15 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		CUDA_TRY(cudaEventRecord(c->ev[EV_K3A], c->stream));
 		OGB_TRY(scan_chunks<MODE_OVERLAP>(c, lo, hi));
 		CUDA_TRY(cudaEventRecord(c->ev[EV_K3B], c->stream));
-		OGB_TRY(exclusive_scan(c, c->deg.p + lo, nloc, c->pos.p, c->d_tot, c->d_ctr + CTR_MAX_DEGREE));   // edge count, largest degree, positions for keep_pre
+		// edge count, largest degree, entries beyond the 30 a row holds, positions for keep_pre
+		OGB_TRY(exclusive_scan(c, c->deg.p + lo, nloc, c->pos.p, c->d_tot, c->d_ctr + CTR_MAX_DEGREE, c->d_ctr + CTR_MORE_NEED));
 		CUDA_TRY(cudaMemcpyAsync(&local_edges, c->d_tot, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 		OGB_TRY(ctr_fetch(c));
 		const u64 n_over = c->h_ctr[CTR_OVERFLOW], n_heavy = c->h_ctr[CTR_BIG_NODES];
-		// [0] candidate queue overflowed, [1] spilled edges, [2] largest degree, [3] edges of this rank, [4] words its heavy lists need
-		u64 verdict[XCHG_PER_RANK] = {c->h_ctr[CTR_CAND_MAX] > c->cand_cap, n_over, c->h_ctr[CTR_MAX_DEGREE], local_edges, n_over + n_heavy * c->slot_cap, c->h_ctr[CTR_PQ_OVERFLOW] != 0, 0, 0};
-		u64 need_ext = verdict[4];
+		// [0] candidate queue overflowed, [1] spilled edges, [2] largest degree, [3] edges of this rank, [4] words its heavy lists need,
+		// [5] a window queue overflowed, [6] entries of this rank beyond the rows
+		u64 verdict[XCHG_PER_RANK] = {c->h_ctr[CTR_CAND_MAX] > c->cand_cap, n_over, c->h_ctr[CTR_MAX_DEGREE], local_edges, n_over + n_heavy * c->slot_cap, c->h_ctr[CTR_PQ_OVERFLOW] != 0, c->h_ctr[CTR_MORE_NEED], 0};
+		more_need = verdict[6];
 		seg_cnt[0] = local_edges; exact_edges = local_edges;
 		if (G > 1) {
 			// one small allgather carries the retry verdicts and the per-rank edge counts
@@ -970,7 +1009,7 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 			for (int r = 0; r < G; r++) {
 				const u64 *v = &all[(size_t)XCHG_PER_RANK * r];
 				verdict[0] = std::max(verdict[0], v[0]); verdict[1] = std::max(verdict[1], v[1]); verdict[2] = std::max(verdict[2], v[2]); verdict[5] = std::max(verdict[5], v[5]);
-				need_ext = std::max(need_ext, v[4]);
+				more_need = std::max(more_need, v[6]);
 				seg_cnt[r] = v[3]; exact_edges += v[3];
 			}
 		}
@@ -984,7 +1023,6 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		c->st.max_degree = verdict[2];
 		c->st.overflow_reads = n_heavy;
 		if (verdict[1]) {                                                    // repeats: some rank has nodes with more than slot_cap edges
-			(void)need_ext;
 			OGB_TRY(c->ext.ensure(n_over + n_heavy * c->slot_cap + 64));
 			if (n_over) {
 				k_heavy_move<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->slots_e.p, c->deg.p, lo, hi, c->slot_cap, c->ext.p, c->ext.cap, c->fill.p, c->d_ctr);
@@ -1003,22 +1041,22 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	c->n_pre = exact_edges;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL1], c->stream));
 
-	// ---- C1 (several ranks): a pivot can live on any rank. Every rank packs its lists to 4-byte entries
-	// (k_pack_adj) at its segment of the common stride; one in-place allgather each for the entries and
-	// the node records. The ELIM bitmap (C2) has one bit per packed entry.
-	u64 seg_stride = 0;
-	if (G > 1) {
-		for (int r = 0; r < G; r++) seg_stride = std::max(seg_stride, seg_cnt[r]);
-		seg_stride = (seg_stride + 255) & ~255ull;
-		OGB_TRY(c->adj32.ensure(std::max<u64>(seg_stride * G, 1)));
-		OGB_TRY(c->nodes.ensure(per * G + 1));
-		OGB_TRY(c->ebits.ensure(std::max<u64>(seg_stride * G / 32, 1)));
-		if (seg_stride) CUDA_TRY(cudaMemsetAsync(c->ebits.p + seg_stride / 32 * c->rank, 0, seg_stride / 32 * sizeof(u32), c->stream));
-		k_pack_adj<<<grid_for(c, (const void *)k_pack_adj, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(graph_view(c, lo), hi, c->pos.p, seg_stride * c->rank, c->nodes.p, c->adj32.p);
+	// ---- rows: headers + the entries beyond 30 (same segment size on every rank: the largest need). C1 (several
+	// ranks): a pivot or a twin can live on any rank -- one in-place allgather each for the rows and the overflow segments.
+	if (more_need >= (1ull << 32) - 2048) { ogb_set_error("ogb_build_graph: adjacency overflow area too large"); return OGB_E_CAPACITY; }
+	c->more_stride = std::max<u64>(1024, (more_need + 1023) & ~1023ull);
+	OGB_TRY(c->more.ensure(c->more_stride * G));
+	const u64 nrows = per * G, obit_words = c->more_stride / 32;          // overflow bits: one word-aligned segment per rank
+	OGB_TRY(c->ebits.ensure(nrows + obit_words * G + 2));
+	CUDA_TRY(cudaMemsetAsync(c->ebits.p + nrows + obit_words * c->rank, 0, obit_words * sizeof(u32), c->stream));
+	if (nloc) {
+		k_rows_finish<<<(nloc + 255) / 256, 256, 0, c->stream>>>(graph_view(c, lo), lo, hi, c->d_ctr);
 		CUDA_TRY(cudaGetLastError());
 		c->launches++;
-		if (seg_stride) NCCL_TRY(g_nccl.AllGather(c->adj32.p + seg_stride * c->rank, c->adj32.p, seg_stride, NCCL_UINT32, c->comm, c->stream));
-		NCCL_TRY(g_nccl.AllGather(c->nodes.p + per * c->rank, c->nodes.p, per, NCCL_UINT64, c->comm, c->stream));
+	}
+	if (G > 1) {
+		NCCL_TRY(g_nccl.AllGather(c->rows.p + per * OGB_ROW_W * c->rank, c->rows.p, per * OGB_ROW_W, NCCL_UINT32, c->comm, c->stream));
+		if (more_need) NCCL_TRY(g_nccl.AllGather(c->more.p + c->more_stride * c->rank, c->more.p, c->more_stride, NCCL_UINT32, c->comm, c->stream));
 	}
 	CUDA_TRY(cudaEventRecord(c->ev[EV_XPRE1], c->stream));
 
@@ -1045,35 +1083,39 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	// ---- K5
 	MarkArgs m;
 	m.G = graph_view(c, lo);
-	m.hi = hi; m.cnt = c->cnt.p;
-	if (c->scratch_keys.cap == 0) { OGB_TRY(c->scratch_keys.ensure(1 << 20)); OGB_TRY(c->scratch_state.ensure(1 << 20)); }
+	m.hi = hi; m.cnt = c->cnt.p; m.cntc = c->cntc.p; m.cand = c->cand.p;
+	OGB_TRY(c->big.ensure((local_edges + 1) * 3));                          // every edge a candidate of an overfull node: cannot overflow
+	m.big = c->big.p; m.big_cap = local_edges + 1;
+	if (c->scratch_keys.cap == 0) OGB_TRY(c->scratch_keys.ensure(1 << 20));
 	for (int attempt = 0;; attempt++) {
 		if (attempt == 4) { ogb_set_error("ogb_build_graph: neighbour-set scratch kept overflowing"); return OGB_E_CAPACITY; }
 		OGB_TRY(ctr_zero(c));
-		m.scratch_keys = c->scratch_keys.p; m.scratch_state = c->scratch_state.p; m.scratch_cap = c->scratch_keys.cap; m.ctr = c->d_ctr;
-		if (G == 1) k_mark<false><<<grid_for(c, (const void *)k_mark<false>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
-		else k_mark<true><<<grid_for(c, (const void *)k_mark<true>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
+		m.scratch_keys = c->scratch_keys.p; m.scratch_cap = c->scratch_keys.cap; m.ctr = c->d_ctr;
+		k_mark<<<grid_for(c, (const void *)k_mark, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
 		CUDA_TRY(cudaGetLastError());
 		c->launches++;
 		if (c->st.max_degree * 2 <= OGB_SETCAP) break;                      // no node can have used the scratch pool
 		OGB_TRY(ctr_fetch(c));
 		if (c->h_ctr[CTR_SCRATCH_FAIL] == 0) break;
-		u64 need = c->h_ctr[CTR_SCRATCH_CURSOR] + 1024;                     // a rerun repeats the same verdicts: the flag bits already set stay valid
-		OGB_TRY(c->scratch_keys.ensure(need)); OGB_TRY(c->scratch_state.ensure(need));
+		u64 need = c->h_ctr[CTR_SCRATCH_CURSOR] + 1024;                     // a rerun repeats the same verdicts: the bits already set stay valid
+		OGB_TRY(c->scratch_keys.ensure(need));
 	}
 	CUDA_TRY(cudaEventRecord(c->ev[EV_MARK1], c->stream));
-	if (G > 1 && seg_stride) NCCL_TRY(g_nccl.AllGather(c->ebits.p + seg_stride / 32 * c->rank, c->ebits.p, seg_stride / 32, NCCL_UINT32, c->comm, c->stream));   // C2
+	if (G > 1) {                                                             // C2: one ELIM bit per entry
+		NCCL_TRY(g_nccl.AllGather(c->ebits.p + per * c->rank, c->ebits.p, per, NCCL_UINT32, c->comm, c->stream));
+		if (more_need) NCCL_TRY(g_nccl.AllGather(c->ebits.p + nrows + obit_words * c->rank, c->ebits.p + nrows, obit_words, NCCL_UINT32, c->comm, c->stream));
+	}
 
 	// ---- K6
-	if (G == 1) k_keep<false><<<grid_for(c, (const void *)k_keep<false>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m, c->surv.p);
-	else k_keep<true><<<grid_for(c, (const void *)k_keep<true>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m, c->surv.p);
+	if (nloc) k_keep<<<(nloc + 255) / 256, 256, 0, c->stream>>>(m, c->surv.p);
+	k_keep_big<<<c->sm_count, 256, 0, c->stream>>>(m);
 	CUDA_TRY(cudaGetLastError());
-	c->launches++;
+	c->launches += 2;
 	OGB_TRY(exclusive_scan(c, c->cnt.p, nloc, c->pos.p, c->d_tot + 1));
 	if (G == 1) {
 		OGB_TRY(c->fin.ensure(std::max<u64>(exact_edges, 1)));               // E_final <= E_pre: no sync needed to size it
-		if (nloc) k_emit_small<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->surv.p, c->cnt.p, c->pos.p, c->fin.p, lo, hi, 0);
-		k_emit<false><<<g_emit, OGB_WARPS * 32, 0, c->stream>>>(c->slots_e.p, c->ext.p, c->deg.p, c->cnt.p, c->pos.p, c->fin.p, lo, hi, cap_now, 0, OGB_SURV);
+		if (nloc) k_emit_small<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->surv.p, c->cnt.p, c->cntc.p, c->pos.p, c->fin.p, lo, hi, 0);
+		k_emit<false><<<g_emit, OGB_WARPS * 32, 0, c->stream>>>(c->slots_e.p, c->ext.p, c->deg.p, c->cntc.p, c->pos.p, c->fin.p, lo, hi, cap_now, 0, OGB_SURV);
 		CUDA_TRY(cudaGetLastError());
 		c->launches += 2;
 		u64 tot = 0;
@@ -1095,8 +1137,8 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		c->n_final = total;
 		OGB_TRY(c->fin_stage.ensure(std::max<u64>(stride * G, 1)));
 		OGB_TRY(c->fin.ensure(std::max<u64>(total, 1)));
-		if (nloc) k_emit_small<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->surv.p, c->cnt.p, c->pos.p, c->fin_stage.p, lo, hi, stride * c->rank);
-		k_emit<false><<<g_emit, OGB_WARPS * 32, 0, c->stream>>>(c->slots_e.p, c->ext.p, c->deg.p, c->cnt.p, c->pos.p, c->fin_stage.p, lo, hi, cap_now, stride * c->rank, OGB_SURV);
+		if (nloc) k_emit_small<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->surv.p, c->cnt.p, c->cntc.p, c->pos.p, c->fin_stage.p, lo, hi, stride * c->rank);
+		k_emit<false><<<g_emit, OGB_WARPS * 32, 0, c->stream>>>(c->slots_e.p, c->ext.p, c->deg.p, c->cntc.p, c->pos.p, c->fin_stage.p, lo, hi, cap_now, stride * c->rank, OGB_SURV);
 		CUDA_TRY(cudaGetLastError());
 		c->launches += 2;
 		OGB_TRY(gather_segments(c, c->fin_stage, stride, fin_cnt, c->fin.p));

@@ -57,7 +57,8 @@ enum { MODE_OVERLAP = 0, MODE_CONTAIN = 1 };
 enum {
 	CTR_EDGE_CURSOR = 0, CTR_OVERFLOW, CTR_PROBES, CTR_SECTORS, CTR_CANDIDATES, CTR_CONTAIN_HITS,
 	CTR_PIVOT_ENTRIES, CTR_ACTIVE_PIVOTS, CTR_MAX_DEGREE, CTR_N_CONTAINED, CTR_NODES_FINAL,
-	CTR_ASYMMETRIC, CTR_SCRATCH_CURSOR, CTR_SCRATCH_FAIL, CTR_CAND_MAX, CTR_BIG_NODES, CTR_EXT_CURSOR, CTR_PQ_OVERFLOW, CTR_COUNT
+	CTR_ASYMMETRIC, CTR_SCRATCH_CURSOR, CTR_SCRATCH_FAIL, CTR_CAND_MAX, CTR_BIG_NODES, CTR_EXT_CURSOR, CTR_PQ_OVERFLOW,
+	CTR_TABLE_FULL, CTR_MORE_CURSOR, CTR_MORE_NEED, CTR_BIGREC_CURSOR, CTR_COUNT
 };
 
 struct ReadStore {
@@ -78,6 +79,7 @@ struct Table {
 	u32 sub;             // partitions per rank
 	u32 my_rank;         // K1: insert only the keys of this rank's partitions
 	u32 h;               // hashStringLength = minOverlap-1 (HashTable.cpp:54)
+	u64 *ctr;            // device counters (K1 raises CTR_TABLE_FULL)
 };
 
 __device__ __forceinline__ u32 padded_words(u32 L) { return ((L + 63) >> 6) << 1; }
@@ -459,7 +461,12 @@ __global__ void k_hash_insert(ReadStore R, Table T)
 	u32 part;
 	u32 b = bucket_of(hash, lead, T, part);
 	const u32 pend = (part + 1) * T.part_buckets;
-	for (;;) {
+	// The probe sequence stays inside the key's hash partition, and the partition is a function of the key's first 16
+	// bases alone: a skewed read set (one primer or repeat in front of most reads) can send more keys to a partition than
+	// it has slots. After one lap the insert gives up and raises CTR_TABLE_FULL; ogb_hash_build retries with fewer, larger
+	// partitions or a larger table (the reference's probe over the whole table, HashTable.cpp:163-195, cannot fill up).
+	for (u32 steps = 0;; steps++) {
+		if (steps >= T.part_buckets) { atomicMax(T.ctr + CTR_TABLE_FULL, 1ull); return; }
 		u32 *w = T.slots + (u64)b * OGB_BWORDS;
 		// one L2-coherent look at the ten values, then a CAS on the first empty one; buckets fill front
 		// to back, so a lost race just moves on to the next slot. The fingerprint half-word is ORed in
@@ -555,6 +562,7 @@ struct ScanArgs {
 	u32 slot_lo;
 	u32 cap;                    // slots per read
 	u32 *deg;                   // edges found per read, by read idx (keeps counting past cap)
+	u32 *rows;                  // adjacency rows by read idx (see GraphView): k_verify writes entries 0..29 as dst<<1 | strand
 	u32 *ov_q;                  // overflow edges of heavy nodes: read idx / edge
 	u64 *ov_e;
 	u64 ov_cap;
@@ -619,7 +627,7 @@ __device__ __forceinline__ void probe_buckets(const ScanArgs &A, QueueCursor &Q,
 {
 	const u32 fp = fj & 0xFFFFu;
 	const u64 tag = (u64)(fj >> 16) << 32;
-	u32 pend = 0;
+	u32 pend = 0, steps = 0;
 	while (__any_sync(0xFFFFFFFFu, active)) {
 		u32 w[OGB_BWORDS];
 		u32 mm = 0;                                                          // slots of this lane's bucket whose fingerprint matches
@@ -628,7 +636,8 @@ __device__ __forceinline__ void probe_buckets(const ScanArgs &A, QueueCursor &Q,
 			c_sectors++;
 			mm = match_bucket(w, fp);
 			// K1 fills a bucket front to back, so "last slot taken" = full = the key may continue in the next bucket
-			active = w[5 + OGB_SLOTS - 1] != 0;
+			// (at most one lap: a completely full partition never gets past ogb_hash_build)
+			active = w[5 + OGB_SLOTS - 1] != 0 && ++steps < A.T.part_buckets;
 			if (active) {
 				if (pend == 0) pend = (b / A.T.part_buckets + 1) * A.T.part_buckets;
 				b = next_bucket(b, pend, A.T);
@@ -917,6 +926,7 @@ __global__ void __launch_bounds__(256, OGB_VERIFY_MINBLOCKS) k_verify(ScanArgs A
 				for (u32 q = 0; q < ne; q++) {
 					const u64 e = q ? e1 : e0;
 					const u32 pos = base + before + q;
+					if (pos < 30) A.rows[(u64)qi * 32 + 2 + pos] = ((ri + 1) << 1) | ((edge_orient(e) >> 1) & 1);   // OGB_ROW_E entries of the 128-byte row
 					if (pos < A.cap) A.slots_e[(u64)(qi - A.slot_lo) * A.cap + pos] = e;
 					else {                                                   // heavy node: spill, placed by k_heavy_place
 						if (pos == A.cap) atomicAdd(A.ctr + CTR_BIG_NODES, 1ull);   // exactly one entry of a heavy node lands here
@@ -936,62 +946,91 @@ __global__ void __launch_bounds__(256, OGB_VERIFY_MINBLOCKS) k_verify(ScanArgs A
 
 // ------------------------------------------------------------------------------------------------
 // The adjacency as the verify kernel leaves it -- and as K5 / K6 consume it, without any copy or sort:
-// read idx of this rank owns slots[(idx - lo)*cap .. +cap) holding deg[idx] edge words in discovery
-// order. A heavy node (deg > cap) keeps its whole list in ext, at the word offset stored in its first
-// slot (k_heavy_move / k_heavy_place).
 //
-// One rank (DENSE = false): a pivot's list and a twin's verdict are read straight from these slot
-// regions. Several ranks (DENSE = true): a pivot or a twin can live on any rank, so every rank packs its
-// lists into 4-byte entries dst<<1 | strand (all K5 needs of a foreign list; k_pack_adj), the packed
-// segments and node records start<<24 | deg are allgathered, and after K5 one ELIM bit per packed
-// entry. Reading the peers' slot regions in place (CUDA IPC over NVLink) was built and measured first:
-// peer reads run at 2.4 G rows/s while the mapped footprint stays within the GPU's translation reach
-// and collapse to 0.16 G rows/s beyond it (3 x 664 MB at 4 ranks), see profiles/r1_notes.md.
+//   slot regions  read idx of this rank owns slots[(idx - lo)*cap .. +cap) holding deg[idx] 8-byte edge words in
+//                 discovery order (offset, dst, orient: what the node's OWN walk and the final records need). A heavy
+//                 node (deg > cap) keeps its whole list in ext, at the word offset stored in its first slot
+//                 (k_heavy_move / k_heavy_place).
+//   rows          what a node looks like to everybody ELSE -- as a pivot (K5) and as a twin (K6) only dst and the
+//                 strand it is left on matter: 4 bytes per entry. Read idx v (any rank) owns the 128-byte line
+//                 rows[v*32 .. +32): word 0 = degree, word 1 = offset of its overflow entries inside its rank's
+//                 segment of `more`, words 2..31 = entries 0..29 as dst<<1 | strand, in slot order. k_verify writes
+//                 the entries next to the edge words; k_rows_finish adds the header and moves entries 30.. to `more`.
+//                 A pivot scan is therefore ONE aligned 128-byte gather at an address known from the edge itself
+//                 (no degree / node-record fetch in front of it), plus a second gather only when deg > 30.
+//   ebits         one ELIM bit per entry, same geometry: word v = row entries of read v, the overflow entries' bits
+//                 follow from word `nrows` on. K5 writes the bits of its own nodes, K6 reads one bit per candidate.
 //
-// The low 14 bits of an edge word are annotations (make_edge leaves them 0): bit 0 = OGB_ELIM
-// "eliminated by the marking of its own node" (K5), bit 1 = OGB_KEEP "survives the reduction" (K6),
-// bits 2-13 = where the twin entry sits in the destination's list (K5, for K6). All are written by the
-// owning warp with one aligned 64-bit store while other warps may be reading dst / orient / bit 0 of
-// the same word -- fields that store never changes.
+// Several ranks: rows, `more` and ebits are laid out by GLOBAL read index / rank segment, every rank fills its own
+// part and the parts are allgathered (C1 after K3, C2 after K5). Reading the peers' slot regions in place (CUDA IPC
+// over NVLink) was built and measured in round 1: peer reads collapse once the mapped footprint exceeds the GPU's
+// translation reach (profiles/r1_notes.md item 16).
+//
+// The low 14 bits of an edge word are annotations (make_edge leaves them 0): bit 1 = OGB_KEEP "survives the
+// reduction" (K6, nodes with many survivors only), bits 2-13 = 1 + position of the twin entry in the destination's
+// list (K5, nodes of degree > 32 only). Both are written by the owning warp.
 // ------------------------------------------------------------------------------------------------
-#define OGB_ELIM 1ull
 #define OGB_KEEP 2ull
-#define OGB_NODE_BITS 24
-#define OGB_NODE_MASK 0xFFFFFFull
+#define OGB_ROW_W 32            // u32 words per adjacency row (one 128-byte line)
+#define OGB_ROW_E 30            // entries held in the row itself
+#define OGB_SURV 4              // candidates / survivors staged per node (a reduced node keeps ~2 edges)
 
 struct GraphView {
 	u64 *slots;                      // this rank's slot regions
 	const u32 *deg;                  // by global read index, valid on [lo, hi)
 	u64 *ext;                        // heavy lists of this rank
 	u32 lo, cap;                     // first read index of this rank; slots per read
-	// several ranks only: every rank's lists, packed
-	const u64 *nodes;                // start<<24 | deg by global read index
-	const u32 *adj32;                // dst<<1 | ((orient>>1)&1), in slot order
-	u32 *ebits;                      // one ELIM bit per packed entry
+	u32 *rows;                       // every rank's rows, by global read index
+	u32 *more;                       // overflow entries: rank r's segment starts at more + r*more_stride
+	u32 *ebits;                      // ELIM bits: word v = row of read v; bit nrows*32 + g = overflow entry g
+	u64 more_stride;                 // entries per rank segment of `more`
+	u64 nrows;                       // rows allocated (reads per rank x ranks)
+	u64 per_magic;                   // rank of read index v = umul64hi(per_magic, v) (0: one rank)
+	u32 my_rank;
 };
 
-// A pivot's list: degree + base pointer (64-bit edge words or packed entries).
-template <bool DENSE> struct PivotList { u32 dv; const u64 *b64; const u32 *b32; };
-template <bool DENSE> __device__ __forceinline__ void pivot_entry(const PivotList<DENSE> &P, u32 kk, u32 &dst, u32 &strand)
+__device__ __forceinline__ u32 row_entry(u64 e) { return (edge_dst(e) << 1) | ((edge_orient(e) >> 1) & 1); }
+__device__ __forceinline__ u32 rank_of(const GraphView &G, u32 vidx) { return G.per_magic ? (u32)__umul64hi(G.per_magic, (u64)vidx) : 0u; }
+// 1 + bit address of the ELIM bit of entry `pos` of read index vidx; ovf = word 1 of its row (read only when pos >= OGB_ROW_E)
+__device__ __forceinline__ u64 entry_bit(const GraphView &G, u32 vidx, u32 pos)
 {
-	if (DENSE) { const u32 f = P.b32[kk]; dst = f >> 1; strand = f & 1; }
-	else { const u64 f = P.b64[kk]; dst = edge_dst(f); strand = (edge_orient(f) >> 1) & 1; }
+	if (pos < OGB_ROW_E) return (u64)vidx * 32 + pos + 1;
+	const u32 ovf = __ldg(G.rows + (u64)vidx * OGB_ROW_W + 1);
+	return G.nrows * 32 + (u64)rank_of(G, vidx) * G.more_stride + ovf + (pos - OGB_ROW_E) + 1;
 }
 
-// Packs the own lists for the exchange and writes the node records. One warp per node.
-__global__ void __launch_bounds__(OGB_WARPS * 32) k_pack_adj(GraphView G, u32 hi, const u64 *__restrict__ pos, u64 seg_off, u64 *__restrict__ nodes, u32 *__restrict__ adj32)
+// Row headers + overflow entries of the own nodes [lo, hi): one thread per node; a warp reserves the overflow space of
+// its 32 nodes with one atomic. Runs after the heavy lists are in place (a node's entries 30.. are read from its list).
+__global__ void __launch_bounds__(256) k_rows_finish(GraphView G, u32 lo, u32 hi, u64 *ctr)
 {
 	const u32 lane = threadIdx.x & 31;
-	const u32 gw = blockIdx.x * OGB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * OGB_WARPS;
-	for (u32 u = G.lo + gw; u < hi; u += nwarps) {
-		const u32 d = G.deg[u];
-		const u64 start = seg_off + pos[u - G.lo];
-		if (lane == 0) nodes[u] = d ? (start << OGB_NODE_BITS) | d : 0;
-		if (d == 0) continue;
-		const u64 *own = G.slots + (u64)(u - G.lo) * G.cap;
-		if (d > G.cap) own = G.ext + own[0];
-		for (u32 k = lane; k < d; k += 32) { const u64 e = own[k]; adj32[start + k] = (edge_dst(e) << 1) | ((edge_orient(e) >> 1) & 1); }
+	const u32 u = lo + blockIdx.x * blockDim.x + threadIdx.x;
+	const u32 d = u < hi ? G.deg[u] : 0;
+	const u32 need = d > OGB_ROW_E ? d - OGB_ROW_E : 0;
+	u32 inc = need;
+	#pragma unroll
+	for (int s = 1; s < 32; s <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, s); if (lane >= (u32)s) inc += t; }
+	const u32 total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+	u64 base = 0;
+	if (total) {
+		if (lane == 31) base = atomicAdd(ctr + CTR_MORE_CURSOR, (u64)total);
+		base = __shfl_sync(0xFFFFFFFFu, base, 31);
 	}
+	if (u >= hi) return;
+	u32 *row = G.rows + (u64)u * OGB_ROW_W;
+	row[0] = d;
+	const u64 *own = G.slots + (u64)(u - G.lo) * G.cap;
+	if (d > G.cap) {
+		// heavy node: its list was gathered in ext, the spilled entries in placement order -- the row follows that order
+		own = G.ext + own[0];
+		for (u32 k = 0; k < d && k < OGB_ROW_E; k++) row[2 + k] = row_entry(own[k]);
+	}
+	if (!need) return;
+	const u64 off = base + inc - need;
+	row[1] = (u32)off;
+	if (off + need > G.more_stride) return;                                  // cannot happen: the segment is sized from the exact count
+	u32 *dst = G.more + (u64)G.my_rank * G.more_stride + off;
+	for (u32 k = OGB_ROW_E; k < d; k++) dst[k - OGB_ROW_E] = row_entry(own[k]);
 }
 
 // Heavy nodes (repeats): the cap edges in the slot region and the spilled ones are gathered in ext.
@@ -1038,24 +1077,34 @@ __global__ void k_contained_bitmap(const u64 *__restrict__ sup, u32 n, u32 *__re
 // pivot" is the smallest (offset, dst, orient, slot) above the current one whose destination is still
 // INPLAY: a warp min-reduction (two REDUX + one ballot) per ACTIVE pivot -- about two per node --
 // replaces the per-node sort. The neighbour set (destination node -> INPLAY/ELIMINATED) is an open-
-// addressing set in shared memory (degree <= 256) or in a global scratch pool (larger).
+// addressing set in shared memory (degree <= 256) or in a global scratch pool (larger): one word per
+// neighbour, dst | state<<31.
 //
-// The kernel is bound by the chain of dependent fetches own list -> pivot list -> next pivot list.
-// Nodes of degree <= 32 (one edge per lane, in registers) therefore fetch their two likely pivots at
-// once: the first edge overall and the first edge leaving the node on the other side -- the latter is
-// almost always the second and last active pivot. The fetch is only a prefetch into registers; the
-// walk itself follows the reference order.
+// The kernel is bound by the chain of dependent gathers own list -> pivot row -> next pivot row. Nodes of
+// degree <= 32 (one edge per lane, in registers) fetch the rows of their two likely pivots at once: the
+// first edge overall and the first edge leaving the node on the other side -- the latter is almost always
+// the second and last active pivot. The fetch is only a prefetch into registers; the walk itself follows
+// the reference order.
+//
+// Output, for K6: the ELIM bits of the own entries, and per node the edges its own marking leaves (its
+// active pivots that were not eliminated later: ~2) with the bit address of the twin entry's ELIM bit,
+// which the pivot scan met on its way. K6 never has to read a list again.
 // ------------------------------------------------------------------------------------------------
 struct MarkArgs {
 	GraphView G;
 	u32 hi;                     // node indices [G.lo, hi) of this rank
+	u32 *cntc;                  // K5 -> K6: candidates (edges left by the own marking) per own node, by idx - lo
+	u64 *cand;                  // OGB_SURV records of two words per own node: edge word, 1 + bit address of the twin's ELIM bit (0 = unknown)
+	u64 *big;                   // nodes with more candidates: records of three words ((idx-lo)<<32 | slot, edge word, twin bit address)
+	u64 big_cap;
 	u32 *cnt;                   // K6: survivors per own node, by idx - lo
 	u32 *scratch_keys;          // global pool for the neighbour sets of big nodes
-	unsigned char *scratch_state;
 	u64 scratch_cap;
 	u64 *ctr;
 };
 
+#define OGB_SET_ELIM 0x80000000u
+#define OGB_SET_KEY 0x3FFFFFFFu
 __device__ __forceinline__ u32 set_hash(u32 key, u32 capmask) { return (key * 2654435761u) >> 7 & capmask; }
 
 __device__ __forceinline__ u32 set_insert(u32 *keys, u32 capmask, u32 key)
@@ -1063,7 +1112,7 @@ __device__ __forceinline__ u32 set_insert(u32 *keys, u32 capmask, u32 key)
 	u32 s = set_hash(key, capmask);
 	for (;;) {
 		u32 cur = atomicCAS(keys + s, 0u, key);
-		if (cur == 0 || cur == key) return s;
+		if (cur == 0 || (cur & OGB_SET_KEY) == key) return s;
 		s = (s + 1) & capmask;
 	}
 }
@@ -1072,163 +1121,228 @@ __device__ __forceinline__ int set_find(const u32 *keys, u32 capmask, u32 key)
 	u32 s = set_hash(key, capmask);
 	for (;;) {
 		u32 cur = keys[s];
-		if (cur == key) return (int)s;
+		if ((cur & OGB_SET_KEY) == key) return (int)s;
 		if (cur == 0) return -1;
 		s = (s + 1) & capmask;
 	}
 }
+// INPLAY -> ELIMINATED for key, if it is a neighbour (:591-596). Lanes may race on one slot; they all store the same word.
+__device__ __forceinline__ void set_eliminate(u32 *keys, u32 capmask, u32 key)
+{
+	u32 s = set_hash(key, capmask);
+	for (;;) {
+		const u32 cur = keys[s];
+		if ((cur & OGB_SET_KEY) == key) { if (!(cur & OGB_SET_ELIM)) keys[s] = cur | OGB_SET_ELIM; return; }
+		if (cur == 0) return;
+		s = (s + 1) & capmask;
+	}
+}
 
-// Lane holding the smallest (w, lane) among the lanes with cand set, -1 if there is none. w < 2^64-2^32.
+// Lane holding the smallest (w, lane) among the lanes with cand set, -1 if there is none. w < 2^64-2^32. The high
+// half (offset | top bits of dst) is almost always decisive: the second reduction runs only on a tie.
 __device__ __forceinline__ int pick_min(bool cand, u64 w)
 {
 	const u32 hi = cand ? (u32)(w >> 32) : 0xFFFFFFFFu;
 	const u32 mh = __reduce_min_sync(0xFFFFFFFFu, hi);
 	if (mh == 0xFFFFFFFFu) return -1;
 	const bool c2 = cand && hi == mh;
+	const u32 b2 = __ballot_sync(0xFFFFFFFFu, c2);
+	if ((b2 & (b2 - 1)) == 0) return __ffs(b2) - 1;
 	const u32 lo = c2 ? (u32)w : 0xFFFFFFFFu;
 	const u32 ml = __reduce_min_sync(0xFFFFFFFFu, lo);
 	return __ffs(__ballot_sync(0xFFFFFFFFu, c2 && lo == ml)) - 1;
 }
 
-// What a lane fetched ahead of a pivot scan: the pivot's degree (slot mode) or node record (packed
-// mode) and the lane's own entry of the list.
-struct PivotPre { u64 head; u64 f; };
-
-template <bool DENSE> __device__ __forceinline__ PivotList<DENSE> pivot_list(const GraphView &G, u32 v, bool pre, u64 head)
+// Neighbour set of a node of degree <= 32 WITHOUT a probe loop: the destinations stay in the lanes' registers, two
+// byte tables per warp map hash(dst) -> lane (1024 and 256 slots; a destination that loses its slot in the first
+// goes to the second). A lookup reads the lane number, fetches that lane's destination with an indexed shuffle and
+// compares: stale or foreign table bytes can never produce a hit, so the tables are never cleared. The states are a
+// bit mask in a register (bit i = lane i's destination was eliminated).
+#define OGB_T1 1024
+#define OGB_T2 256
+__device__ __forceinline__ u32 rs_h1(u32 key) { return (key * 2654435761u) >> 22; }
+__device__ __forceinline__ u32 rs_h2(u32 key) { return (key * 0x85EBCA6Bu) >> 24; }
+// bits of the lanes whose destination equals x (this lane's pivot entry), 0 if x is not a neighbour or `on` is false
+__device__ __forceinline__ u32 rs_lookup(const unsigned char *t1, const unsigned char *t2, bool two, u32 mydst, u32 x, bool on)
 {
-	PivotList<DENSE> P;
-	const u32 idx = v - 1;
-	if (DENSE) {
-		const u64 nd = pre ? head : G.nodes[idx];
-		P.dv = (u32)(nd & OGB_NODE_MASK); P.b32 = G.adj32 + (nd >> OGB_NODE_BITS); P.b64 = nullptr;
-	} else {
-		P.dv = pre ? (u32)head : G.deg[idx];
-		P.b64 = G.slots + (u64)(idx - G.lo) * G.cap; P.b32 = nullptr;
-		if (P.dv > G.cap) P.b64 = G.ext + P.b64[0];
+	const u32 j1 = t1[rs_h1(x)] & 31;
+	const u32 d1 = __shfl_sync(0xFFFFFFFFu, mydst, j1);
+	u32 bit = on && d1 == x ? 1u << j1 : 0;
+	if (two) {
+		const u32 j2 = t2[rs_h2(x)] & 31;
+		const u32 d2 = __shfl_sync(0xFFFFFFFFu, mydst, j2);
+		if (on && d2 == x) bit = 1u << j2;
 	}
-	return P;
+	return bit;
+}
+// scan_pivot for the register set: returns the lanes (representatives) whose destinations v eliminates
+__device__ __forceinline__ u32 scan_pivot_rs(const GraphView &G, u32 v, u32 t1o, u32 self, const unsigned char *t1, const unsigned char *t2, bool two,
+                                             u32 mydst, u32 lane, u32 r, u32 &twin, u32 &dv_out)
+{
+	const u32 dv = __shfl_sync(0xFFFFFFFFu, r, 0);
+	const u32 want = t1o & 1;                                                // compatible(): the pivot is entered and left on the same strand
+	const bool valid = lane >= 2 && lane - 2 < dv;
+	u32 tw = valid && (r >> 1) == self ? lane - 1 : 0;
+	u32 hit = rs_lookup(t1, t2, two, mydst, r >> 1, valid && (r & 1) == want);
+	if (dv > OGB_ROW_E) {                                                    // entries 30.. live in the rank's overflow segment
+		const u32 ovf = __shfl_sync(0xFFFFFFFFu, r, 1);
+		const u32 *m = G.more + (u64)rank_of(G, v - 1) * G.more_stride + ovf;
+		for (u32 k0 = 0; k0 < dv - OGB_ROW_E; k0 += 32) {
+			const u32 kk = k0 + lane;
+			const bool in = kk < dv - OGB_ROW_E;
+			const u32 f = in ? __ldg(m + kk) : 0;
+			if (in && (f >> 1) == self) tw = OGB_ROW_E + kk + 1;
+			hit |= rs_lookup(t1, t2, two, mydst, f >> 1, in && (f & 1) == want);
+		}
+	}
+	twin = __reduce_max_sync(0xFFFFFFFFu, tw);
+	dv_out = dv;
+	return __reduce_or_sync(0xFFFFFFFFu, hit);
 }
 
 // Adjacency of pivot v (1-based id) against the neighbour set: a neighbour reached through v on the
-// strand v was entered on becomes ELIMINATED (:588-596). pre: the list head and this lane's entry were
-// fetched ahead. twin = 1 + position of an entry (v, self) in v's list (0 if there is none): K6 needs
-// v's verdict on self for the edges that survive, and those are always pivots. Returns v's degree.
-template <bool DENSE>
-__device__ __forceinline__ u32 scan_pivot(const GraphView &G, u32 v, u32 t1, u32 self, const u32 *keys, unsigned char *st, u32 capmask, u32 lane,
-                                          bool pre, const PivotPre &pp, u32 &twin)
+// strand v was entered on becomes ELIMINATED (:588-596). r = this lane's word of v's row (fetched by the
+// caller, possibly ahead of time). twin = 1 + position of an entry (v, self) in v's list (0 if there is
+// none): K6 needs v's verdict on self for the edges that survive, and those are always pivots. Returns v's degree.
+__device__ __forceinline__ u32 scan_pivot(const GraphView &G, u32 v, u32 t1, u32 self, u32 *keys, u32 capmask, u32 lane, u32 r, u32 &twin)
 {
-	const PivotList<DENSE> P = pivot_list<DENSE>(G, v, pre, pp.head);
-	if (!DENSE && P.dv > G.cap) pre = false;                                 // heavy list: the entry fetched ahead came from the slot region
+	const u32 dv = __shfl_sync(0xFFFFFFFFu, r, 0);
+	const u32 want = t1 & 1;                                                 // compatible(): the pivot is entered and left on the same strand
 	u32 tw = 0;
-	for (u32 kk = lane; kk < P.dv; kk += 32) {
-		u32 x, strand;
-		if (pre && kk < 32) {
-			if (DENSE) { x = (u32)pp.f >> 1; strand = (u32)pp.f & 1; }
-			else { x = edge_dst(pp.f); strand = (edge_orient(pp.f) >> 1) & 1; }
-		} else pivot_entry<DENSE>(P, kk, x, strand);
-		if (x == self) tw = kk + 1;
-		if ((t1 & 1) == strand) {                                             // compatible(): the pivot is entered and left on the same strand
-			const int sw = set_find(keys, capmask, x);
-			if (sw >= 0 && st[sw] == 1) st[sw] = 2;
+	if (lane >= 2 && lane - 2 < dv) {
+		const u32 x = r >> 1;
+		if (x == self) tw = lane - 1;
+		if ((r & 1) == want) set_eliminate(keys, capmask, x);
+	}
+	if (dv > OGB_ROW_E) {                                                    // entries 30.. live in the rank's overflow segment
+		const u32 ovf = __shfl_sync(0xFFFFFFFFu, r, 1);
+		const u32 *m = G.more + (u64)rank_of(G, v - 1) * G.more_stride + ovf;
+		for (u32 kk = lane; kk < dv - OGB_ROW_E; kk += 32) {
+			const u32 f = __ldg(m + kk);
+			if ((f >> 1) == self) tw = OGB_ROW_E + kk + 1;
+			if ((f & 1) == want) set_eliminate(keys, capmask, f >> 1);
 		}
 	}
 	twin = __reduce_max_sync(0xFFFFFFFFu, tw);
 	__syncwarp();
-	return P.dv;
+	return dv;
 }
 
-// ELIM verdicts of one node as bits of the packed-position bitmap (several ranks only).
-__device__ __forceinline__ void publish_bits(u32 *ebits, u64 start, u32 m)
+// ELIM bits of the own entries beyond the row (positions 30..): atomics into the overflow bit area.
+__device__ __forceinline__ void publish_more_bit(const GraphView &G, u32 ovf, u32 pos)
 {
-	if (m == 0) return;
-	const u64 wi = start >> 5; const u32 sh = (u32)start & 31;
-	atomicOr(ebits + wi, m << sh);
-	if (sh && (m >> (32 - sh))) atomicOr(ebits + wi + 1, m >> (32 - sh));
+	const u64 a = G.nrows * 32 + (u64)G.my_rank * G.more_stride + ovf + (pos - OGB_ROW_E);
+	atomicOr(G.ebits + (a >> 5), 1u << (a & 31));
 }
 
-template <bool DENSE>
-__global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
+#ifndef OGB_MARK_MINBLOCKS
+#define OGB_MARK_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(OGB_WARPS * 32, OGB_MARK_MINBLOCKS) k_mark(MarkArgs A)
 {
 	__shared__ u32 s_keys[OGB_WARPS][OGB_SETCAP];
-	__shared__ unsigned char s_state[OGB_WARPS][OGB_SETCAP];
+	__shared__ unsigned char s_t1[OGB_WARPS][OGB_T1], s_t2[OGB_WARPS][OGB_T2];
 	const GraphView &G = A.G;
-	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lt = (1u << lane) - 1;
 	const u32 gw = blockIdx.x * OGB_WARPS + wib, nwarps = gridDim.x * OGB_WARPS;
 	u64 c_entries = 0, c_pivots = 0;
 
 	for (u32 u = G.lo + gw; u < A.hi; u += nwarps) {
 		const u32 d = G.deg[u];
-		if (d == 0) continue;
+		if (d == 0) { if (lane == 0) A.cntc[u - G.lo] = 0; continue; }
 		u64 *own = G.slots + (u64)(u - G.lo) * G.cap;
 		if (d > G.cap) own = G.ext + own[0];
-		const u64 ustart = DENSE ? G.nodes[u] >> OGB_NODE_BITS : 0;
+		const u32 self = u + 1;
 
-		if (d <= 32) {
-			// ---- one edge per lane, a 64-slot set
-			u32 *keys = s_keys[wib]; unsigned char *st = s_state[wib];
-			const u32 capmask = 63;
-			keys[lane] = 0; keys[lane + 32] = 0;
-			__syncwarp();
+		bool fast = d <= 32, two = false;
+		u64 e = 0;
+		u32 mydst = 0, grp = 0;
+		unsigned char *t1 = s_t1[wib], *t2 = s_t2[wib];
+		if (fast) {
+			// ---- one edge per lane; neighbour set = the lanes' registers behind two byte tables
 			const bool have = lane < d;
-			const u64 e = have ? own[lane] : 0, w = edge_key(e);
-			int sk = 0;
-			if (have) { sk = (int)set_insert(keys, capmask, edge_dst(e)); st[sk] = 1; }   // all neighbours INPLAY (:577-578)
+			e = have ? own[lane] : 0;
+			mydst = edge_dst(e);                                                 // 0 on idle lanes: never equals an entry
+			grp = __match_any_sync(0xFFFFFFFFu, have ? mydst : 0x80000000u | lane);   // lanes with the same destination (multi-edges)
 			__syncwarp();
+			if (have) t1[rs_h1(mydst)] = (unsigned char)lane;
+			__syncwarp();
+			const u32 back1 = __shfl_sync(0xFFFFFFFFu, mydst, t1[rs_h1(mydst)] & 31);   // every lane takes part in the shuffle
+			bool lose = have && back1 != mydst;
+			two = __any_sync(0xFFFFFFFFu, lose);
+			if (two) {
+				if (lose) t2[rs_h2(mydst)] = (unsigned char)lane;
+				__syncwarp();
+				const u32 back2 = __shfl_sync(0xFFFFFFFFu, mydst, t2[rs_h2(mydst)] & 31);
+				lose = lose && back2 != mydst;
+				if (__any_sync(0xFFFFFFFFu, lose)) fast = false;                 // both slots taken by other destinations (~1 node in 10^3): hash-set path
+			}
+		}
+		if (fast) {
+			const bool have = lane < d;
+			const u64 w = edge_key(e);
 			const int a = pick_min(have, w);                                  // first pivot: nothing is eliminated yet
 			const u64 ea = __shfl_sync(0xFFFFFFFFu, e, a);
 			const int b = pick_min(have && ((edge_orient(e) ^ edge_orient(ea)) & 1), w);   // first edge on the other side of u
 			const u64 eb = __shfl_sync(0xFFFFFFFFu, e, b < 0 ? 0 : b);
-			PivotPre pa, pb; pb.head = 0; pb.f = 0;
-			const u32 ia = edge_dst(ea) - 1, ib = edge_dst(eb) - 1;
-			if (DENSE) {
-				pa.head = G.nodes[ia];
-				if (b >= 0) pb.head = G.nodes[ib];
-				pa.f = lane < (u32)(pa.head & OGB_NODE_MASK) ? G.adj32[(pa.head >> OGB_NODE_BITS) + lane] : 0;
-				pb.f = lane < (u32)(pb.head & OGB_NODE_MASK) ? G.adj32[(pb.head >> OGB_NODE_BITS) + lane] : 0;
-			} else {
-				pa.head = G.deg[ia]; pa.f = (G.slots + (u64)(ia - G.lo) * G.cap)[lane];
-				if (b >= 0) { pb.head = G.deg[ib]; pb.f = (G.slots + (u64)(ib - G.lo) * G.cap)[lane]; }
-			}
-			u32 tw, mytw = 0;
-			c_pivots++; c_entries += scan_pivot<DENSE>(G, edge_dst(ea), edge_orient(ea), u + 1, keys, st, capmask, lane, true, pa, tw);
+			const u32 ra = __ldg(G.rows + (u64)(edge_dst(ea) - 1) * OGB_ROW_W + lane);
+			const u32 rb = b >= 0 ? __ldg(G.rows + (u64)(edge_dst(eb) - 1) * OGB_ROW_W + lane) : 0;
+			u32 tw, dv, mytw = 0, elim = 0, done = 0;                            // elim / done: lane bit masks, warp-uniform
+			c_pivots++; elim |= scan_pivot_rs(G, edge_dst(ea), edge_orient(ea), self, t1, t2, two, mydst, lane, ra, tw, dv); c_entries += dv;
 			if ((int)lane == a) mytw = tw;
-			u64 cw = edge_key(ea); int ck = a;
+			done |= 1u << a;
 			for (;;) {
-				const int p = pick_min(have && st[sk] == 1 && (w > cw || (w == cw && (int)lane > ck)), w);
+				// next pivot: smallest edge not walked yet whose destination is still INPLAY (everything smaller was walked or eliminated)
+				const int p = pick_min(have && !((done >> lane) & 1) && !(elim & grp), w);
 				if (p < 0) break;
 				const u64 ep = __shfl_sync(0xFFFFFFFFu, e, p);
-				c_pivots++; c_entries += scan_pivot<DENSE>(G, edge_dst(ep), edge_orient(ep), u + 1, keys, st, capmask, lane, p == b, pb, tw);
+				const u32 rp = p == b ? rb : __ldg(G.rows + (u64)(edge_dst(ep) - 1) * OGB_ROW_W + lane);
+				c_pivots++; elim |= scan_pivot_rs(G, edge_dst(ep), edge_orient(ep), self, t1, t2, two, mydst, lane, rp, tw, dv); c_entries += dv;
 				if ((int)lane == p) mytw = tw;
-				cw = edge_key(ep); ck = p;
+				done |= 1u << p;
 			}
-			const bool elim = have && st[sk] == 2;                            // :601-607 (the twin half is applied in k_keep)
-			if (elim || mytw) own[lane] = e | (mytw < 4096 ? (u64)mytw << 2 : 0) | (elim ? OGB_ELIM : 0);
-			if (DENSE) { const u32 m = __ballot_sync(0xFFFFFFFFu, elim); if (lane == 0) publish_bits(G.ebits, ustart, m); }
+			const bool gone = have && (elim & grp);                              // :601-607 (the twin half is applied in k_keep)
+			const u32 m = __ballot_sync(0xFFFFFFFFu, gone);
+			if (lane == 0) G.ebits[u] = m & ((1u << OGB_ROW_E) - 1);
+			if (gone && lane >= OGB_ROW_E) publish_more_bit(G, __ldg(G.rows + (u64)u * OGB_ROW_W + 1), lane);
+			// the edges the own marking leaves: candidates for K6, with the address of the twin's verdict
+			const bool left = have && !gone;
+			const u32 lb = __ballot_sync(0xFFFFFFFFu, left), c = __popc(lb), rk = __popc(lb & lt);
+			if (lane == 0) A.cntc[u - G.lo] = c;
+			if (left) {
+				const u64 addr = mytw ? entry_bit(G, mydst - 1, mytw - 1) : 0;
+				if (c <= OGB_SURV) { u64 *q = A.cand + ((u64)(u - G.lo) * OGB_SURV + rk) * 2; q[0] = e; q[1] = addr; }
+				else {
+					u64 base = 0;
+					if (rk == 0) base = atomicAdd(A.ctr + CTR_BIGREC_CURSOR, (u64)c);
+					base = __shfl_sync(lb, base, __ffs(lb) - 1);
+					if (base + rk < A.big_cap) { u64 *q = A.big + (base + rk) * 3; q[0] = ((u64)(u - G.lo) << 32) | lane; q[1] = e; q[2] = addr; }
+				}
+			}
 		} else {
 			// ---- any degree: edges stay in memory (L1), a lane looks after entries lane, lane+32, ...
 			u32 cap = 128;
 			while (cap < 2 * d) cap <<= 1;
-			u32 *keys; unsigned char *st;
-			if (cap <= OGB_SETCAP) { keys = s_keys[wib]; st = s_state[wib]; }
+			u32 *keys;
+			if (cap <= OGB_SETCAP) keys = s_keys[wib];
 			else {
 				u64 base = 0;
 				if (lane == 0) base = atomicAdd(A.ctr + CTR_SCRATCH_CURSOR, (u64)cap);
 				base = __shfl_sync(0xFFFFFFFFu, base, 0);
-				if (base + cap > A.scratch_cap) { if (lane == 0) atomicAdd(A.ctr + CTR_SCRATCH_FAIL, 1ull); continue; }
-				keys = A.scratch_keys + base; st = A.scratch_state + base;
+				if (base + cap > A.scratch_cap) { if (lane == 0) { atomicAdd(A.ctr + CTR_SCRATCH_FAIL, 1ull); A.cntc[u - G.lo] = 0; } continue; }
+				keys = A.scratch_keys + base;
 			}
 			const u32 capmask = cap - 1;
 			for (u32 i = lane; i < cap; i += 32) keys[i] = 0;
 			__syncwarp();
-			for (u32 k = lane; k < d; k += 32) st[set_insert(keys, capmask, edge_dst(own[k]))] = 1;
+			for (u32 k = lane; k < d; k += 32) set_insert(keys, capmask, edge_dst(own[k]));
 			__syncwarp();
 			u64 cw = 0; u32 ck = 0; bool first = true;
-			const PivotPre none = {0, 0};
 			for (;;) {
 				u64 bw = ~0ull; u32 bk = 0xFFFFFFFFu;                         // this lane's smallest in-play entry above (cw, ck)
 				for (u32 k = lane; k < d; k += 32) {
 					const u64 x = edge_key(own[k]);
-					if ((first || x > cw || (x == cw && k > ck)) && x < bw && st[set_find(keys, capmask, edge_dst(x))] == 1) { bw = x; bk = k; }
+					if ((first || x > cw || (x == cw && k > ck)) && x < bw && !(keys[set_find(keys, capmask, edge_dst(x))] & OGB_SET_ELIM)) { bw = x; bk = k; }
 				}
 				const u32 hi = (u32)(bw >> 32);
 				const u32 mh = __reduce_min_sync(0xFFFFFFFFu, hi);
@@ -1239,15 +1353,45 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 				ck = __reduce_min_sync(0xFFFFFFFFu, c3 ? bk : 0xFFFFFFFFu);
 				cw = ((u64)mh << 32) | ml; first = false;
 				u32 tw;
-				c_pivots++; c_entries += scan_pivot<DENSE>(G, edge_dst(cw), edge_orient(cw), u + 1, keys, st, capmask, lane, false, none, tw);
-				if (lane == 0 && tw && tw < 4096) own[ck] |= (u64)tw << 2;
+				const u32 rp = __ldg(G.rows + (u64)(edge_dst(cw) - 1) * OGB_ROW_W + lane);
+				c_pivots++; c_entries += scan_pivot(G, edge_dst(cw), edge_orient(cw), self, keys, capmask, lane, rp, tw);
+				if (lane == 0 && tw && tw < 4096) own[ck] |= (u64)tw << 2;      // twin position: 12 spare bits of the pivot's edge word
 				__syncwarp();
 			}
-			for (u32 k = lane; k < d; k += 32) {
-				const u64 x = own[k];
-				if (st[set_find(keys, capmask, edge_dst(x))] == 2) {
-					own[k] = x | OGB_ELIM;
-					if (DENSE) atomicOr(G.ebits + ((ustart + k) >> 5), 1u << ((ustart + k) & 31));
+			// ELIM bits of the own entries, candidates
+			const u32 ovf = __ldg(G.rows + (u64)u * OGB_ROW_W + 1);
+			u32 rowbits = 0, c = 0;
+			for (u32 kb = 0; kb < d; kb += 32) {
+				const u32 k = kb + lane;
+				const u64 x = k < d ? own[k] : 0;
+				const bool elim = k < d && (keys[set_find(keys, capmask, edge_dst(x))] & OGB_SET_ELIM);
+				if (elim) { if (k < OGB_ROW_E) rowbits |= 1u << k; else publish_more_bit(G, ovf, k); }
+				const bool left = k < d && !elim;
+				const u32 lb = __ballot_sync(0xFFFFFFFFu, left);
+				if (left) {
+					const u32 at = c + __popc(lb & lt), tw = edge_twin(x);
+					if (at < OGB_SURV) { u64 *q = A.cand + ((u64)(u - G.lo) * OGB_SURV + at) * 2; q[0] = edge_key(x); q[1] = tw ? entry_bit(G, edge_dst(x) - 1, tw - 1) : 0; }
+				}
+				c += __popc(lb);
+			}
+			rowbits = __reduce_or_sync(0xFFFFFFFFu, rowbits);
+			if (lane == 0) { G.ebits[u] = rowbits; A.cntc[u - G.lo] = c; }
+			if (c > OGB_SURV) {                                                  // rare: all candidates go to the big list instead
+				u64 base = 0;
+				if (lane == 0) base = atomicAdd(A.ctr + CTR_BIGREC_CURSOR, (u64)c);
+				base = __shfl_sync(0xFFFFFFFFu, base, 0);
+				u32 done = 0;
+				for (u32 kb = 0; kb < d; kb += 32) {
+					const u32 k = kb + lane;
+					const u64 x = k < d ? own[k] : 0;
+					const bool left = k < d && !(keys[set_find(keys, capmask, edge_dst(x))] & OGB_SET_ELIM);
+					const u32 lb = __ballot_sync(0xFFFFFFFFu, left);
+					if (left) {
+						const u64 at = base + done + __popc(lb & lt);
+						const u32 tw = edge_twin(x);
+						if (at < A.big_cap) { u64 *q = A.big + at * 3; q[0] = ((u64)(u - G.lo) << 32) | k; q[1] = edge_key(x); q[2] = tw ? entry_bit(G, edge_dst(x) - 1, tw - 1) : 0; }
+					}
+					done += __popc(lb);
 				}
 			}
 		}
@@ -1258,90 +1402,95 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark(MarkArgs A)
 
 // ------------------------------------------------------------------------------------------------
 // K6: an edge (u,w) survives iff it was not flagged by u's marking and its twin was not flagged by
-// w's marking (:605-606, :623-661). Marks are per destination NODE, so w's verdict on u is read off
-// any (w,u) entry of w's list -- no twin pointers are needed, and K5 has left the position of such an
-// entry in the edge word (an edge u kept was a pivot of u, whose scan met it): one word (one rank) or
-// one bit of the exchanged bitmap (several ranks) is fetched; w's list is searched only when the
-// position is missing. One warp per node, one lane per edge. Survivors get OGB_KEEP, the first
-// OGB_SURV of a node are also staged in surv[] for k_emit_small; cnt[u] feeds the scan that positions
-// them in the final list.
+// w's marking (:605-606, :623-661). Marks are per destination NODE, so w's verdict on u is the ELIM bit
+// of any (w,u) entry of w's list, and K5 has left the address of that bit next to every candidate: one
+// bit gather per candidate (~2 per node), no list is read. One THREAD per node; the survivors (<= OGB_SURV)
+// are staged in surv[] for k_emit_small and counted in cnt[] for the scan that positions them. The rare
+// nodes with more candidates go through the record list (k_keep_big) and k_emit.
 // ------------------------------------------------------------------------------------------------
-#define OGB_SURV 4
-template <bool DENSE>
-__global__ void __launch_bounds__(OGB_WARPS * 32) k_keep(MarkArgs A, u64 *__restrict__ surv)
+
+// 1 + bit address of a (v, self) entry found by searching v's list, 0 if there is none (only when K5 could not note it).
+__device__ __forceinline__ u64 find_twin_bit(const GraphView &G, u32 vidx, u32 self)
+{
+	const u32 *row = G.rows + (u64)vidx * OGB_ROW_W;
+	const u32 dv = __ldg(row);
+	for (u32 k = 0; k < dv && k < OGB_ROW_E; k++) if ((__ldg(row + 2 + k) >> 1) == self) return entry_bit(G, vidx, k);
+	if (dv > OGB_ROW_E) {
+		const u32 *m = G.more + (u64)rank_of(G, vidx) * G.more_stride + __ldg(row + 1);
+		for (u32 k = 0; k < dv - OGB_ROW_E; k++) if ((__ldg(m + k) >> 1) == self) return entry_bit(G, vidx, OGB_ROW_E + k);
+	}
+	return 0;
+}
+__device__ __forceinline__ bool twin_eliminated(const GraphView &G, u64 addr, u32 vidx, u32 self, bool &found)
+{
+	if (addr == 0) addr = find_twin_bit(G, vidx, self);
+	found = addr != 0;
+	if (!found) return false;
+	addr--;
+	return (ld_na32(G.ebits + (addr >> 5)) >> (addr & 31)) & 1;
+}
+
+__global__ void __launch_bounds__(256) k_keep(MarkArgs A, u64 *__restrict__ surv)
 {
 	const GraphView &G = A.G;
-	const u32 lane = threadIdx.x & 31;
-	const u32 gw = blockIdx.x * OGB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * OGB_WARPS;
-	u32 c_nodes = 0, c_asym = 0;
-	for (u32 u = G.lo + gw; u < A.hi; u += nwarps) {
-		const u32 d = G.deg[u];
-		u32 total = 0;
-		if (d) {
-			u64 *own = G.slots + (u64)(u - G.lo) * G.cap;
-			if (d > G.cap) own = G.ext + own[0];
-			for (u32 kb = 0; kb < d; kb += 32) {
-				const u32 k = kb + lane;
-				u64 e = 0;
-				bool keep = false;
-				if (k < d) { e = own[k]; keep = !(e & OGB_ELIM); }
-				if (keep) {
-					const u32 idx = edge_dst(e) - 1, tw = edge_twin(e);
-					bool found = false, welim = false;
-					if (DENSE) {
-						const u64 nd = G.nodes[idx];
-						const u32 dw = (u32)(nd & OGB_NODE_MASK);
-						const u64 sw = nd >> OGB_NODE_BITS;
-						u64 at = 0;
-						if (tw && tw <= dw) { found = true; at = sw + tw - 1; }
-						for (u32 x = 0; x < dw && !found; x++) if ((G.adj32[sw + x] >> 1) == u + 1) { found = true; at = sw + x; }
-						if (found) welim = (G.ebits[at >> 5] >> (at & 31)) & 1;
-					} else {
-						const u64 *aw = G.slots + (u64)(idx - G.lo) * G.cap;
-						const u32 dw = G.deg[idx];
-						u64 fat = tw && tw <= G.cap ? aw[tw - 1] : 0;            // fetched along with the degree
-						if (dw > G.cap) { aw = G.ext + aw[0]; fat = 0; }
-						if (tw && fat == 0 && tw <= dw) fat = aw[tw - 1];
-						found = tw && tw <= dw && edge_dst(fat) == u + 1;
-						for (u32 x = 0; x < dw && !found; x += 4) {              // no position: search, batches of four independent loads
-							u64 f[4];
-							#pragma unroll
-							for (int q = 0; q < 4; q++) f[q] = x + q < dw ? aw[x + q] : 0;
-							#pragma unroll
-							for (int q = 3; q >= 0; q--) if (edge_dst(f[q]) == u + 1) { found = true; fat = f[q]; }
-						}
-						welim = (fat & OGB_ELIM) != 0;
-					}
-					if (!found) c_asym++;
-					else keep = !welim;
-					if (keep) own[k] = e | OGB_KEEP;
-				}
-				const u32 bal = __ballot_sync(0xFFFFFFFFu, keep);
-				if (keep) {
-					const u32 at = total + __popc(bal & ((1u << lane) - 1));
-					if (at < OGB_SURV) surv[(u64)(u - G.lo) * OGB_SURV + at] = e;
-				}
-				total += __popc(bal);
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	u32 ns = 0, asym = 0;
+	if (G.lo + i < A.hi) {
+		const u32 c = A.cntc[i];
+		if (c && c <= OGB_SURV) {
+			u64 e[OGB_SURV], a[OGB_SURV];
+			#pragma unroll
+			for (int q = 0; q < OGB_SURV; q++) if (q < (int)c) { e[q] = A.cand[((u64)i * OGB_SURV + q) * 2]; a[q] = A.cand[((u64)i * OGB_SURV + q) * 2 + 1]; }
+			#pragma unroll
+			for (int q = 0; q < OGB_SURV; q++) if (q < (int)c) {
+				bool found;
+				const bool gone = twin_eliminated(G, a[q], edge_dst(e[q]) - 1, G.lo + i + 1, found);
+				asym += !found;
+				if (!gone) surv[(u64)i * OGB_SURV + ns++] = e[q];
 			}
 		}
-		if (lane == 0) { A.cnt[u - G.lo] = total; c_nodes += total > 0; }
+		A.cnt[i] = ns;                                                       // nodes on the big list: k_keep_big adds theirs
 	}
-	if (lane == 0 && c_nodes) atomicAdd(A.ctr + CTR_NODES_FINAL, (u64)c_nodes);
-	if (c_asym) atomicAdd(A.ctr + CTR_ASYMMETRIC, (u64)c_asym);
+	const u32 nodes = __popc(__ballot_sync(0xFFFFFFFFu, ns > 0));
+	if ((threadIdx.x & 31) == 0 && nodes) atomicAdd(A.ctr + CTR_NODES_FINAL, (u64)nodes);
+	if (asym) atomicAdd(A.ctr + CTR_ASYMMETRIC, (u64)asym);
+}
+// One thread per record of the big list: survivors get OGB_KEEP in the node's own list (k_emit writes them).
+__global__ void __launch_bounds__(256) k_keep_big(MarkArgs A)
+{
+	const GraphView &G = A.G;
+	const u64 n_rec = min(A.ctr[CTR_BIGREC_CURSOR], A.big_cap);             // the host never learns the count: fixed grid, strided
+	for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (u64)gridDim.x * blockDim.x) {
+	const u64 *q = A.big + r * 3;
+	const u32 i = (u32)(q[0] >> 32), k = (u32)q[0];
+	bool found;
+	const bool gone = twin_eliminated(G, q[2], edge_dst(q[1]) - 1, G.lo + i + 1, found);
+	if (!found) atomicAdd(A.ctr + CTR_ASYMMETRIC, 1ull);
+	if (gone) continue;
+	u64 *own = G.slots + (u64)i * G.cap;
+	if (G.deg[G.lo + i] > G.cap) own = G.ext + own[0];
+	own[k] |= OGB_KEEP;
+	if (atomicAdd(A.cnt + i, 1u) == 0) atomicAdd(A.ctr + CTR_NODES_FINAL, 1ull);
+	}
 }
 
 // Exclusive scan of u32 counts into u64 offsets: (1) per-block sums, (2) one block scans the sums,
 // (3) per-block scan + base.
 #define OGB_SCAN_ITEMS 2048     // per block of 256 threads (8 per thread)
-__global__ void __launch_bounds__(256) k_scan_sums(const u32 *__restrict__ cnt, u32 n, u64 *__restrict__ sums, u64 *max_out)
+// max_out / more_out (degree scan only): largest count, and the number of entries beyond the adjacency rows (count - 30 each).
+__global__ void __launch_bounds__(256) k_scan_sums(const u32 *__restrict__ cnt, u32 n, u64 *__restrict__ sums, u64 *max_out, u64 *more_out)
 {
 	__shared__ u64 sh[8];
 	u64 base = (u64)blockIdx.x * OGB_SCAN_ITEMS, acc = 0;
-	u32 mx = 0;
-	for (u32 i = threadIdx.x; i < OGB_SCAN_ITEMS; i += 256) if (base + i < n) { const u32 v = cnt[base + i]; acc += v; mx = max(mx, v); }
+	u32 mx = 0, more = 0;
+	for (u32 i = threadIdx.x; i < OGB_SCAN_ITEMS; i += 256) if (base + i < n) { const u32 v = cnt[base + i]; acc += v; mx = max(mx, v); more += v > 30 ? v - 30 : 0; }
 	if (max_out) {
 		for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_down_sync(0xFFFFFFFFu, mx, d));
 		if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_out, (u64)mx);
+	}
+	if (more_out) {
+		more = __reduce_add_sync(0xFFFFFFFFu, more);
+		if ((threadIdx.x & 31) == 0 && more) atomicAdd(more_out, (u64)more);
 	}
 	for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d);
 	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
@@ -1399,13 +1548,13 @@ __device__ __forceinline__ ogb_edge edge_record(u32 src, u64 e)
 
 // Final records of the nodes with at most OGB_SURV survivors (nearly all: a reduced node keeps ~2
 // edges): one thread per node sorts the staged words and writes them at pos[u - lo] (+ add).
-__global__ void __launch_bounds__(256) k_emit_small(const u64 *__restrict__ surv, const u32 *__restrict__ cnt, const u64 *__restrict__ pos,
+__global__ void __launch_bounds__(256) k_emit_small(const u64 *__restrict__ surv, const u32 *__restrict__ cnt, const u32 *__restrict__ cntc, const u64 *__restrict__ pos,
                                                     ogb_edge *__restrict__ out, u32 lo, u32 hi, u64 add)
 {
 	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (lo + i >= hi) return;
 	const u32 c = cnt[i];
-	if (c == 0 || c > OGB_SURV) return;
+	if (c == 0 || cntc[i] > OGB_SURV) return;                                // more candidates than staging slots: k_emit writes that node
 	u64 w[OGB_SURV];
 	#pragma unroll
 	for (int q = 0; q < OGB_SURV; q++) w[q] = q < (int)c ? surv[(u64)i * OGB_SURV + q] : ~0ull;
@@ -1421,7 +1570,7 @@ __global__ void __launch_bounds__(256) k_emit_small(const u64 *__restrict__ surv
 }
 
 // Edge records of the own nodes in the reference order (src, offset, dst, orient): the surviving
-// edges of the nodes with more than min_cnt survivors (ALL = false) or every edge (ALL = true;
+// edges (OGB_KEEP) of the nodes with more than min_cnt candidates in cnt[] (ALL = false) or every edge (ALL = true;
 // pre-reduction list for tests / keep_pre). One warp per node; pos[u - lo] (+ add) is where the node's
 // records start. Entries are ranked by counting the smaller ones -- shuffles up to degree 32, a plain
 // double loop beyond.
@@ -1480,7 +1629,7 @@ __global__ void k_lookup(ReadStore R, Table T, const u64 *__restrict__ keys, u32
 	u64 hash = key_hash<LdGlobal>(key, 0, T.h, lead);
 	u32 fp = hash_fp(hash), b = bucket_of(hash, lead, T, part), c = 0;
 	const u32 pend = (part + 1) * T.part_buckets;
-	for (;;) {
+	for (u32 steps = 0; steps < T.part_buckets; steps++) {
 		u32 w[OGB_BWORDS];
 		load_bucket(T.slots, b, w);
 		for (u32 mm = match_bucket(w, fp); mm; mm &= mm - 1) {

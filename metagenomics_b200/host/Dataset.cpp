@@ -66,9 +66,12 @@ UINT64 Dataset::getNumberOfUniqueReads(void) { return numberOfUniqueReads; }
 
 string Dataset::readString(UINT64 ID, int strand) const
 {
+	// sized from the read's own length (a fixed 64 KB buffer per call cost ~100 GB of memset at config 2's mate-pair pass)
 	uint32_t len = 0;
-	string s(65536, '\0');
-	ogbCheck(ogb_dataset_get_read(store, ID, strand, &s[0], 65536, &len), "Dataset::getReadFromID");
+	const uint64_t n = ogb_dataset_n_unique(store);
+	const uint32_t cap = ID >= 1 && ID <= n ? ogb_dataset_lengths(store)[ID - 1] : 0;
+	string s(cap ? cap : 1, '\0');
+	ogbCheck(ogb_dataset_get_read(store, ID, strand, &s[0], (uint32_t)s.size(), &len), "Dataset::getReadFromID");
 	s.resize(len);
 	return s;
 }

@@ -97,6 +97,21 @@ def one_window(seed=16, min_overlap=40):
     return from_strings(_sample(rng, g, 3000, min_overlap + 1, min_overlap + 1), min_overlap, "one_window")
 
 
+def primer_prefixed(seed=17, min_overlap=30, n_reads=24000):
+    """Amplicon-like reads: every read starts with the same 20-base primer, so one of its four index keys has the same
+    leading bases as everybody else's -- a quarter of all keys falls into ONE hash partition (ADVICE r1 / VERDICT r1 weak #8)."""
+    rng = np.random.default_rng(seed)
+    primer = "GATTACAGGCCTTAGCAATC"
+    g = _rand_seq(rng, 60000)
+    reads = []
+    for _ in range(n_reads):
+        st = int(rng.integers(0, len(g) - 60))
+        s = primer + g[st:st + 60]
+        reads.append(s if rng.integers(0, 2) else rc(s))
+    reads += _sample(rng, g[:20000], 6000, 80, 80)             # plain reads of the same genome: overlaps among themselves and into the amplicons
+    return from_strings(reads, min_overlap, "primer_prefixed")
+
+
 def small_configs():
     return [
         synth.config(1, scale=0.3),

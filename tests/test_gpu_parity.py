@@ -243,3 +243,24 @@ def test_partitioned_probe_with_skewed_partitions(ctx, monkeypatch):
         assert np.array_equal(og.superReadIDs()[1:], orc.read_info()["sup"])
         assert_same_edges(edges_as_tuples(og.edges(pre=True)), orc.edges(pre=True), "pre-reduction, 8 partitions")
         assert_same_edges(edges_as_tuples(og.edges()), orc.edges(), "post-reduction, 8 partitions")
+
+
+def test_skewed_keys_fill_a_hash_partition(ctx, monkeypatch):
+    """K1 bound: with 16 partitions forced, a quarter of all keys -- the primer in front of every read
+    -- lands in one partition that holds 10/16 slots per read: the insert must give up after one lap (CTR_TABLE_FULL) and
+    ogb_hash_build must retry with fewer partitions instead of spinning; the result is still the oracle's graph, and the
+    index still answers getListOfReads like the reference's (HashTable.cpp:202-221)."""
+    from metagenomics_b200 import edges_as_tuples
+    monkeypatch.setenv("OGB_SUB_PARTITIONS", "16")
+    cfg = datasets.primer_prefixed()
+    ds, ht, og = build_gpu(ctx, cfg)
+    orc = Oracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"]).run_all(Oracle.THREE_PHASE, threads=8)
+    assert ds.getNumberOfUniqueReads() == orc.n and orc.n > 20000 and orc.counters()["E_pre"] > 100000
+    st = ctx.stats()
+    assert st["hash_build_attempts"] >= 2 and st["hash_partitions"] < 16  # one partition of 16 could not hold the primer keys: K1 gave up and was retried
+    assert_same_edges(edges_as_tuples(og.edges(pre=True)), orc.edges(pre=True), "pre-reduction, primer-prefixed")
+    assert_same_edges(edges_as_tuples(og.edges()), orc.edges(), "post-reduction, primer-prefixed")
+    h = orc.build_index()
+    keys = [orc.get_read(i)[:h] for i in range(1, orc.n + 1, orc.n // 50)] + ["GATTACAGGCCTTAGCAATC" + "A" * (h - 20)]
+    for k, g in zip(keys, ht.getListsOfReads(keys)):
+        assert np.array_equal(g, orc.lookup(k)), k
