@@ -761,7 +761,7 @@ static ScanArgs scan_args(ogb_context *c, u32 lo, u32 hi)
 	a.contained = c->any_contained ? c->contained.p : nullptr;
 	a.cand_q = c->cand_q.p; a.cand_v = c->cand_v.p; a.cand_cap = c->cand_cap; a.cand_cursor = c->d_cursor;
 	a.sup = c->sup.p; a.slots_e = c->slots_e.p; a.slot_lo = lo; a.cap = c->slot_cap; a.deg = c->deg.p;
-	a.ov_q = c->ov_q.p; a.ov_e = c->ov_e.p; a.ov_cap = c->ov_q.cap; a.ctr = c->d_ctr; a.prefetch = 1; a.rows = c->rows.p;
+	a.ov_q = c->ov_q.p; a.ov_e = c->ov_e.p; a.ov_cap = c->ov_q.cap; a.ctr = c->d_ctr; a.prefetch = 1;
 	return a;
 }
 
@@ -1050,7 +1050,7 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	OGB_TRY(c->ebits.ensure(nrows + obit_words * G + 2));
 	CUDA_TRY(cudaMemsetAsync(c->ebits.p + nrows + obit_words * c->rank, 0, obit_words * sizeof(u32), c->stream));
 	if (nloc) {
-		k_rows_finish<<<(nloc + 255) / 256, 256, 0, c->stream>>>(graph_view(c, lo), lo, hi, c->d_ctr);
+		k_rows_finish<<<grid_for(c, (const void *)k_rows_finish, 256), 256, 0, c->stream>>>(graph_view(c, lo), lo, hi, c->d_ctr);
 		CUDA_TRY(cudaGetLastError());
 		c->launches++;
 	}
@@ -1091,7 +1091,11 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		if (attempt == 4) { ogb_set_error("ogb_build_graph: neighbour-set scratch kept overflowing"); return OGB_E_CAPACITY; }
 		OGB_TRY(ctr_zero(c));
 		m.scratch_keys = c->scratch_keys.p; m.scratch_cap = c->scratch_keys.cap; m.ctr = c->d_ctr;
-		k_mark<<<grid_for(c, (const void *)k_mark, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
+		// degree 1..32, 33..64 (edges in registers), the rest (and the few nodes the fast kernels hand over)
+		k_mark_fast<1><<<grid_for(c, (const void *)k_mark_fast<1>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
+		if (c->st.max_degree > 32) k_mark_fast<2><<<grid_for(c, (const void *)k_mark_fast<2>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
+		c->launches += c->st.max_degree > 32 ? 2 : 1;
+		k_mark_any<<<grid_for(c, (const void *)k_mark_any, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
 		CUDA_TRY(cudaGetLastError());
 		c->launches++;
 		if (c->st.max_degree * 2 <= OGB_SETCAP) break;                      // no node can have used the scratch pool

@@ -562,7 +562,6 @@ struct ScanArgs {
 	u32 slot_lo;
 	u32 cap;                    // slots per read
 	u32 *deg;                   // edges found per read, by read idx (keeps counting past cap)
-	u32 *rows;                  // adjacency rows by read idx (see GraphView): k_verify writes entries 0..29 as dst<<1 | strand
 	u32 *ov_q;                  // overflow edges of heavy nodes: read idx / edge
 	u64 *ov_e;
 	u64 ov_cap;
@@ -926,7 +925,6 @@ __global__ void __launch_bounds__(256, OGB_VERIFY_MINBLOCKS) k_verify(ScanArgs A
 				for (u32 q = 0; q < ne; q++) {
 					const u64 e = q ? e1 : e0;
 					const u32 pos = base + before + q;
-					if (pos < 30) A.rows[(u64)qi * 32 + 2 + pos] = ((ri + 1) << 1) | ((edge_orient(e) >> 1) & 1);   // OGB_ROW_E entries of the 128-byte row
 					if (pos < A.cap) A.slots_e[(u64)(qi - A.slot_lo) * A.cap + pos] = e;
 					else {                                                   // heavy node: spill, placed by k_heavy_place
 						if (pos == A.cap) atomicAdd(A.ctr + CTR_BIG_NODES, 1ull);   // exactly one entry of a heavy node lands here
@@ -954,8 +952,8 @@ __global__ void __launch_bounds__(256, OGB_VERIFY_MINBLOCKS) k_verify(ScanArgs A
 //   rows          what a node looks like to everybody ELSE -- as a pivot (K5) and as a twin (K6) only dst and the
 //                 strand it is left on matter: 4 bytes per entry. Read idx v (any rank) owns the 128-byte line
 //                 rows[v*32 .. +32): word 0 = degree, word 1 = offset of its overflow entries inside its rank's
-//                 segment of `more`, words 2..31 = entries 0..29 as dst<<1 | strand, in slot order. k_verify writes
-//                 the entries next to the edge words; k_rows_finish adds the header and moves entries 30.. to `more`.
+//                 segment of `more`, words 2..31 = entries 0..29 as dst<<1 | strand, in slot order; entries 30.. live in
+//                 `more`. k_rows_finish derives both from the edge words in one streaming pass after K3.
 //                 A pivot scan is therefore ONE aligned 128-byte gather at an address known from the edge itself
 //                 (no degree / node-record fetch in front of it), plus a second gather only when deg > 30.
 //   ebits         one ELIM bit per entry, same geometry: word v = row entries of read v, the overflow entries' bits
@@ -999,38 +997,47 @@ __device__ __forceinline__ u64 entry_bit(const GraphView &G, u32 vidx, u32 pos)
 	return G.nrows * 32 + (u64)rank_of(G, vidx) * G.more_stride + ovf + (pos - OGB_ROW_E) + 1;
 }
 
-// Row headers + overflow entries of the own nodes [lo, hi): one thread per node; a warp reserves the overflow space of
-// its 32 nodes with one atomic. Runs after the heavy lists are in place (a node's entries 30.. are read from its list).
+// Rows of the own nodes [lo, hi) from their edge words: header, entries 0..29, and the entries beyond in the rank's
+// segment of `more`. A warp takes 32 nodes at a time: lane i looks at node i's degree, the overflow space of all 32 is
+// reserved with one atomic, then the warp copies node after node with lane k on entry k (coalesced on both sides).
+// Runs after the heavy lists are in place. (Writing the row entries from k_verify, next to the edge words, was measured
+// first: scattered 4-byte stores cost 2.2 ms at config 3 against 0.7 ms for this pass.)
 __global__ void __launch_bounds__(256) k_rows_finish(GraphView G, u32 lo, u32 hi, u64 *ctr)
 {
 	const u32 lane = threadIdx.x & 31;
-	const u32 u = lo + blockIdx.x * blockDim.x + threadIdx.x;
-	const u32 d = u < hi ? G.deg[u] : 0;
-	const u32 need = d > OGB_ROW_E ? d - OGB_ROW_E : 0;
-	u32 inc = need;
-	#pragma unroll
-	for (int s = 1; s < 32; s <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, s); if (lane >= (u32)s) inc += t; }
-	const u32 total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-	u64 base = 0;
-	if (total) {
-		if (lane == 31) base = atomicAdd(ctr + CTR_MORE_CURSOR, (u64)total);
-		base = __shfl_sync(0xFFFFFFFFu, base, 31);
+	const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (u32 u0 = lo + gw * 32; u0 < hi; u0 += nwarps * 32) {
+		const u32 mine = u0 + lane;
+		const u32 dm = mine < hi ? G.deg[mine] : 0;
+		const u32 need = dm > OGB_ROW_E ? dm - OGB_ROW_E : 0;
+		u32 inc = need;
+		#pragma unroll
+		for (int s = 1; s < 32; s <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, s); if (lane >= (u32)s) inc += t; }
+		const u32 total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+		u64 base = 0;
+		if (total) {
+			if (lane == 31) base = atomicAdd(ctr + CTR_MORE_CURSOR, (u64)total);
+			base = __shfl_sync(0xFFFFFFFFu, base, 31);
+		}
+		const u64 offm = base + inc - need;                                   // this lane's node: start of its overflow entries
+		const u32 cnt = min(32u, hi - u0);
+		for (u32 j = 0; j < cnt; j++) {
+			const u32 u = u0 + j;
+			const u32 d = __shfl_sync(0xFFFFFFFFu, dm, j);
+			const u64 off = __shfl_sync(0xFFFFFFFFu, offm, j);
+			u32 *row = G.rows + (u64)u * OGB_ROW_W;
+			if (d == 0) { if (lane == 0) row[0] = 0; continue; }
+			const u64 *own = G.slots + (u64)(u - G.lo) * G.cap;
+			if (d > G.cap) own = G.ext + own[0];
+			u32 wv = lane == 0 ? d : (u32)off;                                  // header: degree, overflow offset
+			if (lane >= 2) wv = lane - 2 < d ? row_entry(own[lane - 2]) : 0;
+			row[lane] = wv;
+			if (d > OGB_ROW_E && off + (d - OGB_ROW_E) <= G.more_stride) {        // always true: the segment is sized from the exact count
+				u32 *dst = G.more + (u64)G.my_rank * G.more_stride + off;
+				for (u32 k = OGB_ROW_E + lane; k < d; k += 32) dst[k - OGB_ROW_E] = row_entry(own[k]);
+			}
+		}
 	}
-	if (u >= hi) return;
-	u32 *row = G.rows + (u64)u * OGB_ROW_W;
-	row[0] = d;
-	const u64 *own = G.slots + (u64)(u - G.lo) * G.cap;
-	if (d > G.cap) {
-		// heavy node: its list was gathered in ext, the spilled entries in placement order -- the row follows that order
-		own = G.ext + own[0];
-		for (u32 k = 0; k < d && k < OGB_ROW_E; k++) row[2 + k] = row_entry(own[k]);
-	}
-	if (!need) return;
-	const u64 off = base + inc - need;
-	row[1] = (u32)off;
-	if (off + need > G.more_stride) return;                                  // cannot happen: the segment is sized from the exact count
-	u32 *dst = G.more + (u64)G.my_rank * G.more_stride + off;
-	for (u32 k = OGB_ROW_E; k < d; k++) dst[k - OGB_ROW_E] = row_entry(own[k]);
 }
 
 // Heavy nodes (repeats): the cap edges in the slot region and the spilled ones are gathered in ext.
@@ -1153,37 +1160,51 @@ __device__ __forceinline__ int pick_min(bool cand, u64 w)
 	return __ffs(__ballot_sync(0xFFFFFFFFu, c2 && lo == ml)) - 1;
 }
 
-// Neighbour set of a node of degree <= 32 WITHOUT a probe loop: the destinations stay in the lanes' registers, two
-// byte tables per warp map hash(dst) -> lane (1024 and 256 slots; a destination that loses its slot in the first
-// goes to the second). A lookup reads the lane number, fetches that lane's destination with an indexed shuffle and
-// compares: stale or foreign table bytes can never produce a hit, so the tables are never cleared. The states are a
-// bit mask in a register (bit i = lane i's destination was eliminated).
+// Neighbour set of a node of degree <= 32*S WITHOUT a probe loop: the destinations stay in the lanes' registers (S per
+// lane, entry k = lane + 32*slot), two byte tables per warp map hash(dst) -> entry (1024*S and 256 slots; a destination
+// that loses its slot in the first goes to the second). A lookup reads the entry number, fetches that entry's destination
+// with indexed shuffles and compares: stale or foreign table bytes can never produce a hit, so the tables are never
+// cleared. The states are bit masks in registers (bit k = the destination REPRESENTED by entry k was eliminated; every
+// entry knows its representative = the entry the tables return for its destination, which also covers multi-edges).
 #define OGB_T1 1024
 #define OGB_T2 256
-__device__ __forceinline__ u32 rs_h1(u32 key) { return (key * 2654435761u) >> 22; }
+#define OGB_FALLBACK 0xFFFFFFFFu   // cntc value: the fast kernel hands the node to k_mark_any
+template <int S> __device__ __forceinline__ u32 rs_h1(u32 key) { return (key * 2654435761u) >> (S == 1 ? 22 : 21); }
 __device__ __forceinline__ u32 rs_h2(u32 key) { return (key * 0x85EBCA6Bu) >> 24; }
-// bits of the lanes whose destination equals x (this lane's pivot entry), 0 if x is not a neighbour or `on` is false
-__device__ __forceinline__ u32 rs_lookup(const unsigned char *t1, const unsigned char *t2, bool two, u32 mydst, u32 x, bool on)
+// destination held by entry j (every lane of the warp must call this)
+template <int S> __device__ __forceinline__ u32 rs_fetch(const u32 (&dst)[S], u32 j)
 {
-	const u32 j1 = t1[rs_h1(x)] & 31;
-	const u32 d1 = __shfl_sync(0xFFFFFFFFu, mydst, j1);
-	u32 bit = on && d1 == x ? 1u << j1 : 0;
-	if (two) {
-		const u32 j2 = t2[rs_h2(x)] & 31;
-		const u32 d2 = __shfl_sync(0xFFFFFFFFu, mydst, j2);
-		if (on && d2 == x) bit = 1u << j2;
-	}
-	return bit;
+	const u32 v0 = __shfl_sync(0xFFFFFFFFu, dst[0], j & 31);
+	if (S == 1) return v0;
+	const u32 v1 = __shfl_sync(0xFFFFFFFFu, dst[S - 1], j & 31);
+	return (j & 32) ? v1 : v0;
 }
-// scan_pivot for the register set: returns the lanes (representatives) whose destinations v eliminates
-__device__ __forceinline__ u32 scan_pivot_rs(const GraphView &G, u32 v, u32 t1o, u32 self, const unsigned char *t1, const unsigned char *t2, bool two,
-                                             u32 mydst, u32 lane, u32 r, u32 &twin, u32 &dv_out)
+// adds to hit[] the representative entry of x (this lane's pivot entry) if x is a neighbour and `on` is set
+template <int S> __device__ __forceinline__ void rs_lookup(const unsigned char *t1, const unsigned char *t2, bool two, const u32 (&dst)[S], u32 x, bool on, u32 (&hit)[S])
+{
+	const u32 j1 = t1[rs_h1<S>(x)] & (32 * S - 1);
+	const bool m1 = rs_fetch<S>(dst, j1) == x;
+	u32 j = j1; bool m = m1;
+	if (two) {
+		const u32 j2 = t2[rs_h2(x)] & (32 * S - 1);
+		const bool m2 = rs_fetch<S>(dst, j2) == x;
+		if (!m1) { j = j2; m = m2; }
+	}
+	if (on && m) hit[S == 1 ? 0 : (j >> 5)] |= 1u << (j & 31);
+}
+// scan of pivot v's list (row word r of this lane, overflow entries in `more`): returns its degree, ORs the
+// representatives of the destinations it eliminates into elim[], twin = 1 + position of an entry (v, self), 0 if none
+template <int S> __device__ __forceinline__ u32 scan_pivot_rs(const GraphView &G, u32 v, u32 t1o, u32 self, const unsigned char *t1, const unsigned char *t2, bool two,
+                                                              const u32 (&dst)[S], u32 lane, u32 r, u32 &twin, u32 (&elim)[S])
 {
 	const u32 dv = __shfl_sync(0xFFFFFFFFu, r, 0);
 	const u32 want = t1o & 1;                                                // compatible(): the pivot is entered and left on the same strand
 	const bool valid = lane >= 2 && lane - 2 < dv;
 	u32 tw = valid && (r >> 1) == self ? lane - 1 : 0;
-	u32 hit = rs_lookup(t1, t2, two, mydst, r >> 1, valid && (r & 1) == want);
+	u32 hit[S];
+	#pragma unroll
+	for (int q = 0; q < S; q++) hit[q] = 0;
+	rs_lookup<S>(t1, t2, two, dst, r >> 1, valid && (r & 1) == want, hit);
 	if (dv > OGB_ROW_E) {                                                    // entries 30.. live in the rank's overflow segment
 		const u32 ovf = __shfl_sync(0xFFFFFFFFu, r, 1);
 		const u32 *m = G.more + (u64)rank_of(G, v - 1) * G.more_stride + ovf;
@@ -1192,29 +1213,193 @@ __device__ __forceinline__ u32 scan_pivot_rs(const GraphView &G, u32 v, u32 t1o,
 			const bool in = kk < dv - OGB_ROW_E;
 			const u32 f = in ? __ldg(m + kk) : 0;
 			if (in && (f >> 1) == self) tw = OGB_ROW_E + kk + 1;
-			hit |= rs_lookup(t1, t2, two, mydst, f >> 1, in && (f & 1) == want);
+			rs_lookup<S>(t1, t2, two, dst, f >> 1, in && (f & 1) == want, hit);
 		}
 	}
 	twin = __reduce_max_sync(0xFFFFFFFFu, tw);
-	dv_out = dv;
-	return __reduce_or_sync(0xFFFFFFFFu, hit);
+	#pragma unroll
+	for (int q = 0; q < S; q++) elim[q] |= __reduce_or_sync(0xFFFFFFFFu, hit[q]);
+	return dv;
+}
+// Entry with the smallest (key, entry number) among the candidate entries, -1 if there is none
+template <int S> __device__ __forceinline__ int pick_entry(const bool (&cand)[S], const u64 (&w)[S], u32 lane)
+{
+	if (S == 1) return pick_min(cand[0], w[0]);
+	const bool second = cand[S - 1] && (!cand[0] || w[S - 1] < w[0]);          // this lane's better candidate
+	const int l = pick_min(cand[0] || cand[S - 1], second ? w[S - 1] : w[0]);
+	if (l < 0) return -1;
+	return l + (__shfl_sync(0xFFFFFFFFu, (u32)second, l) ? 32 : 0);
+}
+template <int S> __device__ __forceinline__ u64 entry_word(const u64 (&e)[S], int k)
+{
+	const u64 v0 = __shfl_sync(0xFFFFFFFFu, e[0], k & 31);
+	if (S == 1) return v0;
+	const u64 v1 = __shfl_sync(0xFFFFFFFFu, e[S - 1], k & 31);
+	return (k & 32) ? v1 : v0;
+}
+// ELIM bits of the own entries 30.. (`nbits` of them in `bits`, entry 30 first): up to three atomics into the overflow bit area
+__device__ __forceinline__ void publish_more_bits(const GraphView &G, u32 ovf, u64 bits, u32 lane)
+{
+	if (bits == 0) return;
+	const u64 a = G.nrows * 32 + (u64)G.my_rank * G.more_stride + ovf;
+	const u32 sh = (u32)a & 31;
+	u32 *w = G.ebits + (a >> 5);
+	if (lane < 3) {
+		// the bits occupy positions sh .. sh+63 of a 96-bit field starting at word w
+		u32 v;
+		if (lane == 0) v = (u32)(bits << sh);
+		else if (lane == 1) v = (u32)(sh ? bits >> (32 - sh) : bits >> 32);
+		else v = sh ? (u32)(bits >> (64 - sh)) : 0;
+		if (v) atomicOr(w + lane, v);
+	}
 }
 
-// Adjacency of pivot v (1-based id) against the neighbour set: a neighbour reached through v on the
-// strand v was entered on becomes ELIMINATED (:588-596). r = this lane's word of v's row (fetched by the
-// caller, possibly ahead of time). twin = 1 + position of an entry (v, self) in v's list (0 if there is
-// none): K6 needs v's verdict on self for the edges that survive, and those are always pivots. Returns v's degree.
+#ifndef OGB_MARK_MINBLOCKS
+#define OGB_MARK_MINBLOCKS 5
+#endif
+// K5 for the nodes of degree (32*(S-1), 32*S]: one warp per node, S edges per lane in registers. A warp takes 32
+// consecutive nodes, looks at their degrees and walks the ones of its class.
+template <int S>
+__global__ void __launch_bounds__(OGB_WARPS * 32, S == 1 ? OGB_MARK_MINBLOCKS : 4) k_mark_fast(MarkArgs A)
+{
+	__shared__ unsigned char s_t1[OGB_WARPS][OGB_T1 * S], s_t2[OGB_WARPS][OGB_T2];
+	const GraphView &G = A.G;
+	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lt = (1u << lane) - 1;
+	const u32 gw = blockIdx.x * OGB_WARPS + wib, nwarps = gridDim.x * OGB_WARPS;
+	u64 c_entries = 0, c_pivots = 0;
+	unsigned char *t1 = s_t1[wib], *t2 = s_t2[wib];
+
+	for (u32 u0 = G.lo + gw * 32; u0 < A.hi; u0 += nwarps * 32) {
+		const u32 mine = u0 + lane;
+		const u32 dm = mine < A.hi ? G.deg[mine] : 0;
+		if (S == 1 && mine < A.hi && dm == 0) A.cntc[mine - G.lo] = 0;         // nodes without edges
+		for (u32 todo = __ballot_sync(0xFFFFFFFFu, dm > 32 * (S - 1) && dm <= 32 * S); todo; todo &= todo - 1) {
+			const u32 jn = __ffs(todo) - 1, u = u0 + jn, self = u + 1;
+			const u32 d = __shfl_sync(0xFFFFFFFFu, dm, jn);
+			const u64 *own = G.slots + (u64)(u - G.lo) * G.cap;
+			if (d > G.cap) own = G.ext + own[0];
+			u64 e[S], w[S];
+			u32 dst[S], rep[S], mytw[S], elim[S], done[S];
+			bool have[S], lose[S];
+			#pragma unroll
+			for (int q = 0; q < S; q++) {
+				have[q] = lane + 32 * q < d;
+				e[q] = have[q] ? own[lane + 32 * q] : 0;
+				w[q] = edge_key(e[q]);
+				dst[q] = edge_dst(e[q]);                                         // 0 on idle entries: never equals a pivot entry
+				mytw[q] = 0; elim[q] = 0; done[q] = 0;
+			}
+			// ---- tables
+			__syncwarp();
+			#pragma unroll
+			for (int q = 0; q < S; q++) if (have[q]) t1[rs_h1<S>(dst[q])] = (unsigned char)(lane + 32 * q);
+			__syncwarp();
+			bool any_lose = false;
+			#pragma unroll
+			for (int q = 0; q < S; q++) {
+				rep[q] = t1[rs_h1<S>(dst[q])] & (32 * S - 1);
+				lose[q] = rs_fetch<S>(dst, rep[q]) != dst[q] && have[q];
+				any_lose |= lose[q];
+			}
+			const bool two = __any_sync(0xFFFFFFFFu, any_lose);
+			bool fail = false;
+			if (two) {
+				#pragma unroll
+				for (int q = 0; q < S; q++) if (lose[q]) t2[rs_h2(dst[q])] = (unsigned char)(lane + 32 * q);
+				__syncwarp();
+				any_lose = false;
+				#pragma unroll
+				for (int q = 0; q < S; q++) {
+					const u32 j2 = t2[rs_h2(dst[q])] & (32 * S - 1);
+					const bool ok2 = rs_fetch<S>(dst, j2) == dst[q];
+					if (lose[q]) { rep[q] = j2; any_lose |= !ok2; }
+				}
+				fail = __any_sync(0xFFFFFFFFu, any_lose);                        // both slots taken by other destinations: rare
+			}
+			if (fail) { if (lane == 0) A.cntc[u - G.lo] = OGB_FALLBACK; continue; }
+
+			// ---- walk: the first pivot, the first edge on the other side of u (its row is fetched together with the first), then
+			// the smallest edge not walked yet whose destination is still INPLAY (everything smaller was walked or eliminated)
+			const int a = pick_entry<S>(have, w, lane);
+			const u64 ea = entry_word<S>(e, a);
+			bool side[S];
+			#pragma unroll
+			for (int q = 0; q < S; q++) side[q] = have[q] && ((edge_orient(e[q]) ^ edge_orient(ea)) & 1);
+			const int b = pick_entry<S>(side, w, lane);
+			const u64 eb = entry_word<S>(e, b < 0 ? 0 : b);
+			const u32 ra = __ldg(G.rows + (u64)(edge_dst(ea) - 1) * OGB_ROW_W + lane);
+			const u32 rb = b >= 0 ? __ldg(G.rows + (u64)(edge_dst(eb) - 1) * OGB_ROW_W + lane) : 0;
+			int p = a;
+			u64 ep = ea;
+			u32 rp = ra;
+			for (;;) {
+				u32 tw;
+				c_pivots++; c_entries += scan_pivot_rs<S>(G, edge_dst(ep), edge_orient(ep), self, t1, t2, two, dst, lane, rp, tw, elim);
+				#pragma unroll
+				for (int q = 0; q < S; q++) { if ((int)lane + 32 * q == p) mytw[q] = tw; if ((p >> 5) == q) done[q] |= 1u << (p & 31); }
+				bool cand[S];
+				#pragma unroll
+				for (int q = 0; q < S; q++) cand[q] = have[q] && !((done[q] >> lane) & 1) && !((elim[S == 1 ? 0 : (rep[q] >> 5)] >> (rep[q] & 31)) & 1);
+				p = pick_entry<S>(cand, w, lane);
+				if (p < 0) break;
+				ep = entry_word<S>(e, p);
+				rp = p == b ? rb : __ldg(G.rows + (u64)(edge_dst(ep) - 1) * OGB_ROW_W + lane);
+			}
+			// ---- ELIM bits of the own entries (:601-607; the twin half is applied in k_keep), candidates for K6
+			bool left[S];
+			u32 gm[S], lb[S];
+			#pragma unroll
+			for (int q = 0; q < S; q++) {
+				const bool gone = have[q] && ((elim[S == 1 ? 0 : (rep[q] >> 5)] >> (rep[q] & 31)) & 1);
+				left[q] = have[q] && !gone;
+				gm[q] = __ballot_sync(0xFFFFFFFFu, gone);
+				lb[q] = __ballot_sync(0xFFFFFFFFu, left[q]);
+			}
+			if (lane == 0) G.ebits[u] = gm[0] & ((1u << OGB_ROW_E) - 1);
+			if (d > OGB_ROW_E) {
+				u64 bits = gm[0] >> OGB_ROW_E;
+				if (S > 1) bits |= (u64)gm[S - 1] << (32 - OGB_ROW_E);
+				publish_more_bits(G, __ldg(G.rows + (u64)u * OGB_ROW_W + 1), bits, lane);
+			}
+			u32 c = 0;
+			#pragma unroll
+			for (int q = 0; q < S; q++) c += __popc(lb[q]);
+			if (lane == 0) A.cntc[u - G.lo] = c;
+			u64 base = 0;
+			if (c > OGB_SURV) {                                                  // rare: the node's candidates go to the record list
+				if (lane == 0) base = atomicAdd(A.ctr + CTR_BIGREC_CURSOR, (u64)c);
+				base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			}
+			u32 before = 0;
+			#pragma unroll
+			for (int q = 0; q < S; q++) {
+				if (left[q]) {
+					const u32 rk = before + __popc(lb[q] & lt);
+					const u64 addr = mytw[q] ? entry_bit(G, dst[q] - 1, mytw[q] - 1) : 0;
+					if (c <= OGB_SURV) { u64 *o = A.cand + ((u64)(u - G.lo) * OGB_SURV + rk) * 2; o[0] = e[q]; o[1] = addr; }
+					else if (base + rk < A.big_cap) { u64 *o = A.big + (base + rk) * 3; o[0] = ((u64)(u - G.lo) << 32) | (lane + 32 * q); o[1] = e[q]; o[2] = addr; }
+				}
+				before += __popc(lb[q]);
+			}
+		}
+	}
+	if (lane == 0) { atomicAdd(A.ctr + CTR_PIVOT_ENTRIES, c_entries); atomicAdd(A.ctr + CTR_ACTIVE_PIVOTS, c_pivots); }
+}
+
+// Hash-set form of the pivot scan (k_mark_any): adjacency of pivot v (1-based id) against the neighbour set: a neighbour
+// reached through v on the strand v was entered on becomes ELIMINATED (:588-596). r = this lane's word of v's row.
+// twin = 1 + position of an entry (v, self) in v's list (0 if there is none). Returns v's degree.
 __device__ __forceinline__ u32 scan_pivot(const GraphView &G, u32 v, u32 t1, u32 self, u32 *keys, u32 capmask, u32 lane, u32 r, u32 &twin)
 {
 	const u32 dv = __shfl_sync(0xFFFFFFFFu, r, 0);
-	const u32 want = t1 & 1;                                                 // compatible(): the pivot is entered and left on the same strand
+	const u32 want = t1 & 1;
 	u32 tw = 0;
 	if (lane >= 2 && lane - 2 < dv) {
 		const u32 x = r >> 1;
 		if (x == self) tw = lane - 1;
 		if ((r & 1) == want) set_eliminate(keys, capmask, x);
 	}
-	if (dv > OGB_ROW_E) {                                                    // entries 30.. live in the rank's overflow segment
+	if (dv > OGB_ROW_E) {
 		const u32 ovf = __shfl_sync(0xFFFFFFFFu, r, 1);
 		const u32 *m = G.more + (u64)rank_of(G, v - 1) * G.more_stride + ovf;
 		for (u32 kk = lane; kk < dv - OGB_ROW_E; kk += 32) {
@@ -1227,100 +1412,31 @@ __device__ __forceinline__ u32 scan_pivot(const GraphView &G, u32 v, u32 t1, u32
 	__syncwarp();
 	return dv;
 }
-
-// ELIM bits of the own entries beyond the row (positions 30..): atomics into the overflow bit area.
+// ELIM bit of the own entry `pos` >= 30: an atomic into the overflow bit area
 __device__ __forceinline__ void publish_more_bit(const GraphView &G, u32 ovf, u32 pos)
 {
 	const u64 a = G.nrows * 32 + (u64)G.my_rank * G.more_stride + ovf + (pos - OGB_ROW_E);
 	atomicOr(G.ebits + (a >> 5), 1u << (a & 31));
 }
 
-#ifndef OGB_MARK_MINBLOCKS
-#define OGB_MARK_MINBLOCKS 5
-#endif
-__global__ void __launch_bounds__(OGB_WARPS * 32, OGB_MARK_MINBLOCKS) k_mark(MarkArgs A)
+// K5 for everything else (degree > 64, or a node whose destinations did not fit the byte tables): edges stay in memory
+// (L1), a lane looks after entries lane, lane+32, ...; neighbour set = hash set in shared memory or the scratch pool.
+__global__ void __launch_bounds__(OGB_WARPS * 32, 6) k_mark_any(MarkArgs A)
 {
 	__shared__ u32 s_keys[OGB_WARPS][OGB_SETCAP];
-	__shared__ unsigned char s_t1[OGB_WARPS][OGB_T1], s_t2[OGB_WARPS][OGB_T2];
 	const GraphView &G = A.G;
 	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lt = (1u << lane) - 1;
 	const u32 gw = blockIdx.x * OGB_WARPS + wib, nwarps = gridDim.x * OGB_WARPS;
 	u64 c_entries = 0, c_pivots = 0;
 
-	for (u32 u = G.lo + gw; u < A.hi; u += nwarps) {
-		const u32 d = G.deg[u];
-		if (d == 0) { if (lane == 0) A.cntc[u - G.lo] = 0; continue; }
-		u64 *own = G.slots + (u64)(u - G.lo) * G.cap;
-		if (d > G.cap) own = G.ext + own[0];
-		const u32 self = u + 1;
-
-		bool fast = d <= 32, two = false;
-		u64 e = 0;
-		u32 mydst = 0, grp = 0;
-		unsigned char *t1 = s_t1[wib], *t2 = s_t2[wib];
-		if (fast) {
-			// ---- one edge per lane; neighbour set = the lanes' registers behind two byte tables
-			const bool have = lane < d;
-			e = have ? own[lane] : 0;
-			mydst = edge_dst(e);                                                 // 0 on idle lanes: never equals an entry
-			grp = __match_any_sync(0xFFFFFFFFu, have ? mydst : 0x80000000u | lane);   // lanes with the same destination (multi-edges)
-			__syncwarp();
-			if (have) t1[rs_h1(mydst)] = (unsigned char)lane;
-			__syncwarp();
-			const u32 back1 = __shfl_sync(0xFFFFFFFFu, mydst, t1[rs_h1(mydst)] & 31);   // every lane takes part in the shuffle
-			bool lose = have && back1 != mydst;
-			two = __any_sync(0xFFFFFFFFu, lose);
-			if (two) {
-				if (lose) t2[rs_h2(mydst)] = (unsigned char)lane;
-				__syncwarp();
-				const u32 back2 = __shfl_sync(0xFFFFFFFFu, mydst, t2[rs_h2(mydst)] & 31);
-				lose = lose && back2 != mydst;
-				if (__any_sync(0xFFFFFFFFu, lose)) fast = false;                 // both slots taken by other destinations (~1 node in 10^3): hash-set path
-			}
-		}
-		if (fast) {
-			const bool have = lane < d;
-			const u64 w = edge_key(e);
-			const int a = pick_min(have, w);                                  // first pivot: nothing is eliminated yet
-			const u64 ea = __shfl_sync(0xFFFFFFFFu, e, a);
-			const int b = pick_min(have && ((edge_orient(e) ^ edge_orient(ea)) & 1), w);   // first edge on the other side of u
-			const u64 eb = __shfl_sync(0xFFFFFFFFu, e, b < 0 ? 0 : b);
-			const u32 ra = __ldg(G.rows + (u64)(edge_dst(ea) - 1) * OGB_ROW_W + lane);
-			const u32 rb = b >= 0 ? __ldg(G.rows + (u64)(edge_dst(eb) - 1) * OGB_ROW_W + lane) : 0;
-			u32 tw, dv, mytw = 0, elim = 0, done = 0;                            // elim / done: lane bit masks, warp-uniform
-			c_pivots++; elim |= scan_pivot_rs(G, edge_dst(ea), edge_orient(ea), self, t1, t2, two, mydst, lane, ra, tw, dv); c_entries += dv;
-			if ((int)lane == a) mytw = tw;
-			done |= 1u << a;
-			for (;;) {
-				// next pivot: smallest edge not walked yet whose destination is still INPLAY (everything smaller was walked or eliminated)
-				const int p = pick_min(have && !((done >> lane) & 1) && !(elim & grp), w);
-				if (p < 0) break;
-				const u64 ep = __shfl_sync(0xFFFFFFFFu, e, p);
-				const u32 rp = p == b ? rb : __ldg(G.rows + (u64)(edge_dst(ep) - 1) * OGB_ROW_W + lane);
-				c_pivots++; elim |= scan_pivot_rs(G, edge_dst(ep), edge_orient(ep), self, t1, t2, two, mydst, lane, rp, tw, dv); c_entries += dv;
-				if ((int)lane == p) mytw = tw;
-				done |= 1u << p;
-			}
-			const bool gone = have && (elim & grp);                              // :601-607 (the twin half is applied in k_keep)
-			const u32 m = __ballot_sync(0xFFFFFFFFu, gone);
-			if (lane == 0) G.ebits[u] = m & ((1u << OGB_ROW_E) - 1);
-			if (gone && lane >= OGB_ROW_E) publish_more_bit(G, __ldg(G.rows + (u64)u * OGB_ROW_W + 1), lane);
-			// the edges the own marking leaves: candidates for K6, with the address of the twin's verdict
-			const bool left = have && !gone;
-			const u32 lb = __ballot_sync(0xFFFFFFFFu, left), c = __popc(lb), rk = __popc(lb & lt);
-			if (lane == 0) A.cntc[u - G.lo] = c;
-			if (left) {
-				const u64 addr = mytw ? entry_bit(G, mydst - 1, mytw - 1) : 0;
-				if (c <= OGB_SURV) { u64 *q = A.cand + ((u64)(u - G.lo) * OGB_SURV + rk) * 2; q[0] = e; q[1] = addr; }
-				else {
-					u64 base = 0;
-					if (rk == 0) base = atomicAdd(A.ctr + CTR_BIGREC_CURSOR, (u64)c);
-					base = __shfl_sync(lb, base, __ffs(lb) - 1);
-					if (base + rk < A.big_cap) { u64 *q = A.big + (base + rk) * 3; q[0] = ((u64)(u - G.lo) << 32) | lane; q[1] = e; q[2] = addr; }
-				}
-			}
-		} else {
-			// ---- any degree: edges stay in memory (L1), a lane looks after entries lane, lane+32, ...
+	for (u32 u0 = G.lo + gw * 32; u0 < A.hi; u0 += nwarps * 32) {
+		const u32 mine = u0 + lane;
+		const u32 dm = mine < A.hi ? G.deg[mine] : 0;
+		for (u32 todo = __ballot_sync(0xFFFFFFFFu, dm > 64 || (dm && A.cntc[mine - G.lo] == OGB_FALLBACK)); todo; todo &= todo - 1) {
+			const u32 jn = __ffs(todo) - 1, u = u0 + jn, self = u + 1;
+			const u32 d = __shfl_sync(0xFFFFFFFFu, dm, jn);
+			u64 *own = G.slots + (u64)(u - G.lo) * G.cap;
+			if (d > G.cap) own = G.ext + own[0];
 			u32 cap = 128;
 			while (cap < 2 * d) cap <<= 1;
 			u32 *keys;
@@ -1395,7 +1511,6 @@ __global__ void __launch_bounds__(OGB_WARPS * 32, OGB_MARK_MINBLOCKS) k_mark(Mar
 				}
 			}
 		}
-		__syncwarp();
 	}
 	if (lane == 0) { atomicAdd(A.ctr + CTR_PIVOT_ENTRIES, c_entries); atomicAdd(A.ctr + CTR_ACTIVE_PIVOTS, c_pivots); }
 }
