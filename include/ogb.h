@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OGB_VERSION 100
+#define OGB_VERSION 200
 
 enum {
 	OGB_OK = 0,
@@ -54,6 +54,28 @@ typedef struct ogb_edge {
 	uint8_t orient;
 	uint8_t reserved;
 } ogb_edge; /* 12 bytes */
+
+/* Kernel classes of ogb_stats.ms_kernel / n_kernel. */
+enum {
+	OGB_KC_HASH = 0,        /* K1  k_hash_insert */
+	OGB_KC_WINDOW,          /* K3a k_window_part (overlap pass) */
+	OGB_KC_PROBE,           /* K3b k_probe_parts (or the direct probe kernels) */
+	OGB_KC_VERIFY,          /* K3c k_verify */
+	OGB_KC_ROWS,            /*     k_rows_finish */
+	OGB_KC_MARK1,           /* K5  k_mark_fast<1>: degree 1..32 */
+	OGB_KC_MARK2,           /* K5  k_mark_fast<2>: degree 33..64 */
+	OGB_KC_MARKANY,         /* K5  k_mark_any */
+	OGB_KC_KEEP,            /* K6  k_keep + k_keep_big */
+	OGB_KC_EMIT,            /* K6  scan + k_emit_small + k_emit */
+	OGB_KC_CONTAIN_WINDOW,  /* K2  k_window_part (containment pass) */
+	OGB_KC_CONTAIN_PROBE,   /* K2  probe */
+	OGB_KC_CONTAIN_VERIFY,  /* K2  k_verify<CONTAIN> */
+	OGB_KC_EXCH_INDEX,      /* several ranks: allgather of the index slices */
+	OGB_KC_EXCH_ROWS,       /* C1: allgather of the adjacency rows */
+	OGB_KC_EXCH_BITS,       /* C2: allgather of the ELIM bits */
+	OGB_KC_EXCH_FINAL,      /* C3: allgather of the final edges */
+	OGB_KC_COUNT = 20
+};
 
 /* Counters and device timings of the last build (CUDA events on the context's stream). */
 typedef struct ogb_stats {
@@ -89,6 +111,9 @@ typedef struct ogb_stats {
 	float ms_scan_kernel;      /* K3 alone: all probe + verify launches */
 	float ms_probe_launch;     /* average duration of the probe of one chunk (the roofline kernel(s): k_window_part + k_probe_parts, or k_probe), measured in place */
 	float ms_window_launch;    /* of which k_window_part (hash + filter + scatter to the partition queues); 0 on the direct path */
+	float ms_kernel[OGB_KC_COUNT];     /* device time per kernel class (OGB_KC_*), summed over its launches of the last hash_build + mark_contained +
+	                                    * build_graph: CUDA event pairs on the launching stream, recorded in place (kernels of the two K3 streams overlap) */
+	uint32_t n_kernel[OGB_KC_COUNT];   /* launches (event pairs) behind ms_kernel */
 } ogb_stats;
 
 int ogb_version(void);
@@ -167,6 +192,10 @@ int ogb_reads_upload(ogb_context *ctx, const char *bases, const uint64_t *offset
 int ogb_reads_upload_packed(ogb_context *ctx, const uint64_t *words, const uint64_t *word_offsets,
                             const uint16_t *lengths, uint64_t n);
 int ogb_reads_upload_dataset(ogb_context *ctx, const ogb_dataset *ds);
+/* Several ranks, one read length: this rank passes only the reads of its own shard -- reads (per*rank, per*(rank+1)] of
+ * the n_total sorted unique reads, per = ceil(n_total / n_ranks), ceil(read_len/32) tight words each -- and the packed
+ * store is replicated by an allgather over NVLink instead of n_ranks full uploads over PCIe. Collective: every rank calls it. */
+int ogb_reads_upload_packed_sharded(ogb_context *ctx, const uint64_t *shard_words, uint64_t n_total, uint32_t read_len);
 
 /* HashTable::insertDataset(Dataset*, minOverlapLength) (HashTable.cpp:50-80): hashStringLength =
  * minOverlap-1 (:54); 4 keys per read -- prefix/suffix of forward and of reverse complement
@@ -203,6 +232,13 @@ int ogb_graph_edge_count(ogb_context *ctx, int which, uint64_t *n);
 /* Copies the edges, sorted by (src, offset, dst, orient), to host memory. */
 int ogb_graph_edges(ogb_context *ctx, int which, ogb_edge *out, uint64_t cap);
 
+/* The post-reduction edges whose source is in this rank's node range (same order; one rank: the whole list). */
+int ogb_graph_edges_shard(ogb_context *ctx, ogb_edge *out, uint64_t cap, uint64_t *n_out);
+/* Order-independent checksum of the edge list on the device: xor and sum (mod 2^64) over all edges of
+ * mix(src*K1 ^ dst*K2 ^ offset*K3 ^ orient*K4), mix(x) = (x ^ x>>29) * K5, then ^ >>32 -- the figure the oracle's
+ * full-size goldens carry (tests/golden/full_size.json), so a result of GBs can be checked without leaving HBM. */
+int ogb_graph_checksum(ogb_context *ctx, int which, uint64_t *xor_out, uint64_t *sum_out);
+
 int ogb_get_stats(ogb_context *ctx, ogb_stats *out);
 
 /* Measurement helpers: CUDA events on the context's stream (the stream every kernel of this library
@@ -211,6 +247,12 @@ int ogb_get_stats(ogb_context *ctx, ogb_stats *out);
 int ogb_timer_begin(ogb_context *ctx);
 int ogb_timer_end(ogb_context *ctx, float *ms);
 int ogb_l2_flush(ogb_context *ctx, size_t bytes);
+
+/* Random-gather ceiling of this GPU's HBM (the "HBM random-access roofline" the probe / verify / mark kernels are
+ * measured against): every thread keeps four independent, random, aligned loads of gather_bytes (32, 64 or 128) in flight
+ * over a scratch buffer of buffer_bytes (a power of two; use the size of the structure the kernel gathers from -- beyond
+ * ~256 MB the rate is bound by address translation, not by DRAM bandwidth). Returns useful GB/s = bytes requested / time. */
+int ogb_gather_ceiling(ogb_context *ctx, size_t buffer_bytes, uint32_t gather_bytes, double *gb_per_s);
 
 /* Pinned host memory for upload/download staging (released by ogb_free_host). */
 int ogb_alloc_host(void **out, size_t bytes);

@@ -27,10 +27,16 @@ class Stats(C.Structure):
         "active_pivots", "edges_final", "nodes_final", "max_degree", "overflow_reads")] + [
         ("kernel_launches", C.c_uint32), ("probe_launches", C.c_uint32), ("hash_partitions", C.c_uint32), ("hash_build_attempts", C.c_uint32)] + [(n, C.c_float) for n in (
             "ms_pack", "ms_hash_build", "ms_contain", "ms_overlap", "ms_exchange_pre", "ms_mark", "ms_reduce",
-            "ms_total", "ms_scan_kernel", "ms_probe_launch", "ms_window_launch")]
+            "ms_total", "ms_scan_kernel", "ms_probe_launch", "ms_window_launch")] + [
+        ("ms_kernel", C.c_float * 20), ("n_kernel", C.c_uint32 * 20)]
+
+    KERNEL_CLASSES = ("hash_insert", "window_part", "probe_parts", "verify", "rows_finish", "mark_fast1", "mark_fast2", "mark_any", "keep", "emit",
+                      "contain_window", "contain_probe", "contain_verify", "exch_index", "exch_rows", "exch_bits", "exch_final")
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n not in ("ms_kernel", "n_kernel")}
+        d["kernels"] = {k: {"ms": float(self.ms_kernel[i]), "launches": int(self.n_kernel[i])} for i, k in enumerate(self.KERNEL_CLASSES) if self.n_kernel[i]}
+        return d
 
 
 # every symbol include/ogb.h declares: name -> (restype, argtypes)
@@ -64,6 +70,7 @@ PROTOTYPES = {
     "ogb_reads_upload": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
     "ogb_reads_upload_packed": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64]),
     "ogb_reads_upload_dataset": (C.c_int, [_vp, _vp]),
+    "ogb_reads_upload_packed_sharded": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32]),
     "ogb_hash_build": (C.c_int, [_vp, C.c_uint32]),
     "ogb_hash_lookup": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp]),
     "ogb_hash_string_length": (C.c_uint64, [_vp]),
@@ -73,10 +80,13 @@ PROTOTYPES = {
     "ogb_build_graph": (C.c_int, [_vp, C.c_int]),
     "ogb_graph_edge_count": (C.c_int, [_vp, C.c_int, _u64p]),
     "ogb_graph_edges": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
+    "ogb_graph_edges_shard": (C.c_int, [_vp, _vp, C.c_uint64, _u64p]),
+    "ogb_graph_checksum": (C.c_int, [_vp, C.c_int, _u64p, _u64p]),
     "ogb_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "ogb_timer_begin": (C.c_int, [_vp]),
     "ogb_timer_end": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "ogb_l2_flush": (C.c_int, [_vp, C.c_size_t]),
+    "ogb_gather_ceiling": (C.c_int, [_vp, C.c_size_t, C.c_uint32, C.POINTER(C.c_double)]),
     "ogb_alloc_host": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "ogb_free_host": (None, [_vp]),
     "ogb_synth_genome": (C.c_int, [C.c_uint64, C.c_uint64, _vp]),

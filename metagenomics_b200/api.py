@@ -223,6 +223,20 @@ class OverlapGraph:
         check(lib().ogb_graph_edges(self.ctx._h, which, out.ctypes.data, n))
         return out
 
+    def edges_shard(self):
+        """The post-reduction edges whose source lies in this rank's node range (one rank: all of them)."""
+        n = C.c_uint64()
+        cap = self._count(0)
+        out = np.zeros(cap, dtype=EDGE_DTYPE)
+        check(lib().ogb_graph_edges_shard(self.ctx._h, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value]
+
+    def checksum(self, pre=False):
+        """[xor, sum] of the 64-bit mix of every edge tuple, computed on the device (the figure of tests/golden/full_size.json)."""
+        x, t = C.c_uint64(), C.c_uint64()
+        check(lib().ogb_graph_checksum(self.ctx._h, 1 if pre else 0, C.byref(x), C.byref(t)))
+        return [x.value, t.value]
+
 
 def edges_as_tuples(e):
     """structured edge array -> (n,4) uint32 [src, dst, offset, orient] (the oracle's tuple layout)."""

@@ -45,6 +45,8 @@ struct NcclApi {
 	int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	int (*GroupStart)() = nullptr;
 	int (*GroupEnd)() = nullptr;
 	const char *(*GetErrorString)(int) = nullptr;
@@ -58,7 +60,7 @@ static int nccl_load()
 	if (!lib) { ogb_set_error("cannot load libnccl.so.2: %s", dlerror()); return OGB_E_NCCL; }
 #define SYM(field, name) *(void **)(&g_nccl.field) = dlsym(lib, name); if (!g_nccl.field) { ogb_set_error("libnccl: missing %s", name); return OGB_E_NCCL; }
 	SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
-	SYM(AllGather, "ncclAllGather") SYM(AllReduce, "ncclAllReduce") SYM(Broadcast, "ncclBroadcast")
+	SYM(AllGather, "ncclAllGather") SYM(AllReduce, "ncclAllReduce") SYM(Broadcast, "ncclBroadcast") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
 	SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
 	g_nccl.lib = lib;
@@ -116,6 +118,10 @@ struct ogb_context {
 	cudaEvent_t ev_pk[2 * 64] = {};   // timing pairs around the first 64 probe launches of a build
 	cudaEvent_t ev_pm[64] = {};       // ... and between k_window_part and k_probe_parts
 	u32 n_pk = 0;
+	// per-kernel-class device times of a build (ogb_stats.ms_kernel): event pairs on the launching stream, read back at the end
+	struct KEv { cudaEvent_t a = nullptr, b = nullptr; int cls = 0; };
+	std::vector<KEv> kev;
+	u32 n_kev = 0;
 	ncclComm_t comm = nullptr;
 	cudaEvent_t ev[EV_COUNT] = {};
 	// packed reads
@@ -145,8 +151,10 @@ struct ogb_context {
 	Pool<u32> deg;
 	// what a node looks like to the others (pivot scans, twin verdicts): 128-byte rows by global read index, overflow
 	// entries per rank segment, one ELIM bit per entry (GraphView); on several ranks each is allgathered
-	Pool<u32> rows, more, ebits;
-	u64 more_stride = 0;
+	Pool<u32> rows, more, more_own, ebits, hrows;   // more_own: this rank's overflow entries (one rank: the whole of `more`); hrows: heavy-row records
+	u64 more_stride = 0, more_cap = 0;
+	cudaStream_t xs = nullptr;       // several ranks: the rows of a finished chunk travel here while the next chunk is probed
+	cudaEvent_t ev_rows[2] = {}, ev_xs = nullptr;
 	// scan staging: candidate queue of one chunk, spill list of heavy nodes
 	Pool<u32> cand_q, fill, ov_q;    // cand_q / cand_v hold two ping-pong queues of cand_cap entries
 	Pool<u64> cand_v, ov_e;
@@ -164,6 +172,7 @@ struct ogb_context {
 	int probe_blocks_per_sm = 0, verify_blocks_per_sm = 0;   // 0 = as many as fit
 	Pool<char> flush;
 	u64 n_final = 0, n_pre = 0;
+	u64 fin_own_off = 0, fin_own_cnt = 0;   // this rank's node range inside the final list
 	bool have_graph = false, have_pre = false;
 	u64 *d_ctr = nullptr, *h_ctr = nullptr;
 	u64 *d_tot = nullptr;            // [0] scan total of pre-reduction degrees, [1] of surviving edges
@@ -185,6 +194,34 @@ struct ogb_context {
 		hi = (u32)std::min<u64>(n, per * (rank + 1));
 	}
 };
+
+// Brackets one launch (or one NCCL call) of class `cls` on `st` with an event pair; at most OGB_KEV_MAX pairs per build.
+enum { OGB_KEV_MAX = 4096 };
+static int kev_begin(ogb_context *c, int cls, cudaStream_t st)
+{
+	if (c->n_kev >= OGB_KEV_MAX) return -1;
+	if (c->n_kev >= c->kev.size()) {
+		ogb_context::KEv e;
+		if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) { cudaGetLastError(); return -1; }
+		c->kev.push_back(e);
+	}
+	const int i = (int)c->n_kev++;
+	c->kev[i].cls = cls;
+	cudaEventRecord(c->kev[i].a, st);
+	return i;
+}
+static void kev_end(ogb_context *c, int i, cudaStream_t st) { if (i >= 0) cudaEventRecord(c->kev[i].b, st); }
+// after a synchronisation: adds the pairs recorded since the last collection to st.ms_kernel / st.n_kernel
+static void kev_collect(ogb_context *c)
+{
+	for (u32 i = 0; i < c->n_kev; i++) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, c->kev[i].a, c->kev[i].b) == cudaSuccess) { c->st.ms_kernel[c->kev[i].cls] += ms; c->st.n_kernel[c->kev[i].cls]++; }
+		else cudaGetLastError();
+	}
+	c->n_kev = 0;
+}
+#define KEV(cls, stream, launch) do { const int kev_i_ = kev_begin(c, cls, stream); launch; kev_end(c, kev_i_, stream); } while (0)
 
 static int ctr_zero(ogb_context *c) { CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, CTR_COUNT * sizeof(u64), c->stream)); return OGB_OK; }
 static int ctr_fetch(ogb_context *c)
@@ -243,6 +280,9 @@ static int context_create_common(ogb_context **out, int device)
 	CUDA_TRY(cudaMalloc((void **)&c->d_xchg, XCHG_WORDS * sizeof(u64)));
 	CUDA_TRY(cudaMemset(c->d_xchg, 0, XCHG_WORDS * sizeof(u64)));
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+	CUDA_TRY(cudaStreamCreateWithFlags(&c->xs, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_rows[i], cudaEventDisableTiming));
+	CUDA_TRY(cudaEventCreateWithFlags(&c->ev_xs, cudaEventDisableTiming));
 	for (int i = 0; i < 2; i++) { CUDA_TRY(cudaEventCreateWithFlags(&c->ev_probe[i], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&c->ev_verify[i], cudaEventDisableTiming)); }
 	CUDA_TRY(cudaMemset(c->d_tot, 0, 2 * sizeof(u64)));
 	CUDA_TRY(cudaMallocHost((void **)&c->h_ctr, CTR_COUNT * sizeof(u64)));
@@ -286,6 +326,7 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	if (c->stream2) cudaStreamSynchronize(c->stream2);
+	if (c->xs) cudaStreamSynchronize(c->xs);
 	if (c->comm) g_nccl.CommDestroy(c->comm);
 	c->words.release(); c->meta.release(); c->stage_bytes.release(); c->stage_offs.release(); c->stage_lens.release();
 	c->slots.release(); c->summary.release(); c->sup.release(); c->contained.release(); c->pos.release();
@@ -298,12 +339,16 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	c->pq_b.release(); c->pq_f.release(); c->pq_q.release();
 	if (c->d_xchg) cudaFree(c->d_xchg);
 	c->cand_q.release(); c->deg.release(); c->fill.release(); c->ov_q.release();
-	c->cand_v.release(); c->slots_e.release(); c->ext.release(); c->ov_e.release(); c->rows.release(); c->more.release(); c->ebits.release();
+	c->cand_v.release(); c->slots_e.release(); c->ext.release(); c->ov_e.release(); c->rows.release(); c->more.release(); c->more_own.release(); c->hrows.release(); c->ebits.release();
 	if (c->h_ctr) cudaFreeHost(c->h_ctr);
 	for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 128; i++) if (c->ev_pk[i]) cudaEventDestroy(c->ev_pk[i]);
 	for (int i = 0; i < 64; i++) if (c->ev_pm[i]) cudaEventDestroy(c->ev_pm[i]);
+	for (auto &e : c->kev) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
 	for (int i = 0; i < 2; i++) { if (c->ev_probe[i]) cudaEventDestroy(c->ev_probe[i]); if (c->ev_verify[i]) cudaEventDestroy(c->ev_verify[i]); }
+	for (int i = 0; i < 2; i++) if (c->ev_rows[i]) cudaEventDestroy(c->ev_rows[i]);
+	if (c->ev_xs) cudaEventDestroy(c->ev_xs);
+	if (c->xs) cudaStreamDestroy(c->xs);
 	if (c->stream2) cudaStreamDestroy(c->stream2);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -465,6 +510,42 @@ extern "C" int ogb_reads_upload_dataset(ogb_context *c, const ogb_dataset *ds)
 	return ogb_reads_upload_packed(c, w, ogb_dataset_word_offsets(ds), ogb_dataset_lengths(ds), ogb_dataset_n_unique(ds));
 }
 
+// Several ranks, one read length: every rank uploads only the reads of its own shard (tight forward words) over PCIe,
+// K0 packs them into its segment of the read store and one in-place allgather over NVLink replicates the store --
+// instead of G copies of the whole read set crossing PCIe at once.
+extern "C" int ogb_reads_upload_packed_sharded(ogb_context *c, const uint64_t *shard_words, uint64_t n_total, uint32_t read_len)
+{
+	if (!c || (n_total && !shard_words)) { ogb_set_error("ogb_reads_upload_packed_sharded: NULL argument"); return OGB_E_ARG; }
+	if (n_total >= (1ull << 30)) { ogb_set_error("ogb_reads_upload_packed_sharded: at most 2^30-1 reads per context"); return OGB_E_CAPACITY; }
+	if (read_len < 2 || read_len > 65535) { ogb_set_error("ogb_reads_upload_packed_sharded: read length %u (allowed 2..65535)", read_len); return OGB_E_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	const int G = c->nranks;
+	c->n = (u32)n_total; c->min_len = c->max_len = read_len; c->uniform_len = read_len; c->uniform_pw = ((read_len + 63) >> 6) << 1;
+	const u64 per = (n_total + G - 1) / G, stride = 2ull * c->uniform_pw, nw = (read_len + 31) / 32;
+	const u64 total_words = per * G * stride;                               // the last rank's segment is padded to the common size
+	std::vector<u64> none;
+	OGB_TRY(upload_common(c, total_words, none));
+	if (n_total == 0) return OGB_OK;
+	u32 lo, hi;
+	c->shard(lo, hi);
+	const u64 nloc = hi - lo;
+	OGB_TRY(c->stage_bytes.ensure(std::max<u64>(nloc * nw, 1) * sizeof(u64)));
+	CUDA_TRY(cudaEventRecord(c->ev[EV_PACK0], c->stream));
+	if (nloc) {
+		CUDA_TRY(cudaMemcpyAsync(c->stage_bytes.p, shard_words, nloc * nw * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+		const u64 threads = nloc * c->uniform_pw;
+		k_pack_words<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>((const u64 *)c->stage_bytes.p, nullptr, nullptr, c->words.p + (u64)lo * stride, nullptr,
+		                                                                      (u32)nloc, c->uniform_len, c->uniform_pw, c->uniform_pw);
+		CUDA_TRY(cudaGetLastError());
+	}
+	if (G > 1) NCCL_TRY(g_nccl.AllGather(c->words.p + per * stride * c->rank, c->words.p, per * stride, NCCL_UINT64, c->comm, c->stream));
+	CUDA_TRY(cudaEventRecord(c->ev[EV_PACK1], c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->st.ms_pack = ev_ms(c, EV_PACK0, EV_PACK1);
+	c->st.n_reads = n_total;
+	return OGB_OK;
+}
+
 static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *d_total, u64 *d_max = nullptr, u64 *d_more = nullptr);
 
 // ------------------------------------------------------------------------------------------------
@@ -624,6 +705,8 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 		c->partitioned = e ? atoi(e) != 0 : true;
 	}
 	c->launches = 0;
+	c->n_kev = 0;
+	memset(c->st.ms_kernel, 0, sizeof c->st.ms_kernel); memset(c->st.n_kernel, 0, sizeof c->st.n_kernel);
 	CUDA_TRY(cudaEventRecord(c->ev[EV_HASH0], c->stream));
 	// One hash partition per rank: every rank inserts only the keys of its own partition (a slice of
 	// nb/G buckets that stays L2- and TLB-friendly), then the slices are allgathered. A replicated build
@@ -659,7 +742,7 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 		CUDA_TRY(cudaMemsetAsync(c->d_ctr + CTR_TABLE_FULL, 0, sizeof(u64), c->stream));
 		if (c->n) {
 			u64 threads = (u64)c->n * 4;
-			k_hash_insert<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->rs(), c->tb());
+			KEV(OGB_KC_HASH, c->stream, (k_hash_insert<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->rs(), c->tb())));
 			CUDA_TRY(cudaGetLastError());
 			c->launches++;
 		}
@@ -669,11 +752,14 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 		CUDA_TRY(cudaMemcpyAsync(c->h_ctr + CTR_TABLE_FULL, c->d_ctr + CTR_TABLE_FULL, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 		if (c->nranks > 1) {
 			const u64 pb = nb / c->nranks;
+			const int ke = kev_begin(c, OGB_KC_EXCH_INDEX, c->stream);
 			NCCL_TRY(g_nccl.AllGather(c->slots.p + pb * OGB_BWORDS * c->rank, c->slots.p, pb * OGB_BWORDS, NCCL_UINT32, c->comm, c->stream));
 			if (c->use_summary) NCCL_TRY(g_nccl.AllGather(c->summary.p + pb * c->rank, c->summary.p, pb, NCCL_UINT32, c->comm, c->stream));
+			kev_end(c, ke, c->stream);
 		}
 		CUDA_TRY(cudaEventRecord(c->ev[EV_HASH1], c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		kev_collect(c);
 		full = c->h_ctr[CTR_TABLE_FULL];
 		c->st.hash_build_attempts = (uint32_t)attempt + 1;
 		if (!full) break;
@@ -765,6 +851,33 @@ static ScanArgs scan_args(ogb_context *c, u32 lo, u32 hi)
 	return a;
 }
 
+static GraphView graph_view(const ogb_context *c, u32 lo);
+
+// Several ranks: chunk `ci` of every rank's rows (reads [lo_r + ci*chunk, lo_r + (ci+1)*chunk) of rank r) goes to every other
+// rank, as one group of point-to-point sends / receives on the exchange stream. Every rank calls this for the same chunk
+// grid; a rank whose chunk is empty only receives.
+static int exchange_chunk_rows(ogb_context *c, u32 ci, cudaStream_t st)
+{
+	const int G = c->nranks;
+	const u64 per = ((u64)c->n + G - 1) / G;
+	auto range = [&](int r, u64 &a, u64 &b) {
+		const u64 lo = std::min<u64>(c->n, per * r), hi = std::min<u64>(c->n, per * (r + 1));
+		a = std::min(hi, lo + (u64)ci * c->chunk_reads); b = std::min(hi, a + c->chunk_reads);
+	};
+	u64 ma, mb;
+	range(c->rank, ma, mb);
+	NCCL_TRY(g_nccl.GroupStart());
+	for (int p = 0; p < G; p++) {
+		if (p == c->rank) continue;
+		u64 pa, pb;
+		range(p, pa, pb);
+		if (mb > ma) NCCL_TRY(g_nccl.Send(c->rows.p + ma * OGB_ROW_W, (mb - ma) * OGB_ROW_W, NCCL_UINT32, p, c->comm, st));
+		if (pb > pa) NCCL_TRY(g_nccl.Recv(c->rows.p + pa * OGB_ROW_W, (pb - pa) * OGB_ROW_W, NCCL_UINT32, p, c->comm, st));
+	}
+	NCCL_TRY(g_nccl.GroupEnd());
+	return OGB_OK;
+}
+
 // k_probe + k_verify over [lo,hi) in chunks of c->chunk_reads reads, so that the candidate queue of a
 // chunk (and the partner strands its probe prefetched) stay L2-resident. The probe of chunk i+1 runs
 // on the main stream while the verify of chunk i runs on stream2 (ping-pong queues): the former is
@@ -779,17 +892,20 @@ template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 	{
 		const char *e = getenv("OGB_CHUNK_READS");                           // experiment knob
 		if (e && atoll(e) >= 256 && !part_mode) c->chunk_reads = (u32)std::min<long long>(atoll(e), 1ll << 16);
-		const u64 want = part_mode ? 32ull << 20 : 8ull << 20;
-		if (c->cand_cap < want) { OGB_TRY(c->cand_q.ensure(2 * want)); OGB_TRY(c->cand_v.ensure(2 * want)); c->cand_cap = want; }
 	}
 	if (part_mode) {
-		if (!c->part_chunk_set) { const char *e = getenv("OGB_CHUNK_READS"); c->chunk_reads = e && atoll(e) >= 256 ? (u32)std::min<long long>(atoll(e), 1ll << 20) : 1u << 18; c->part_chunk_set = true; }
+		if (!c->part_chunk_set) { const char *e = getenv("OGB_CHUNK_READS"); c->chunk_reads = e && atoll(e) >= 256 ? (u32)std::min<long long>(atoll(e), 1ll << 23) : 1u << 18; c->part_chunk_set = true; }
 		c->chunk_reads = (u32)std::max<u64>(256, std::min<u64>(c->chunk_reads, (64ull << 20) / std::max<u32>(nwin_u, 1)));   // <= 64 M windows per chunk (reads up to ~300 bp: the full 256 k reads)
 		const u64 pcap = std::min<u64>(c->chunk_reads, hi - lo) * nwin_u / c->nparts * std::min<u64>(c->pq_slack, 4ull * c->nparts) / 4 + 4096;   // a quarter of slack over a perfectly even split at first
 		OGB_TRY(c->pq_b.ensure(pcap * c->nparts)); OGB_TRY(c->pq_f.ensure(pcap * c->nparts)); OGB_TRY(c->pq_q.ensure(pcap * c->nparts));
 		c->pq_cap = pcap;
 	} else
 	if (c->chunk_reads > (1u << 16)) c->chunk_reads = 1u << 16;             // k_probe_uniform indexes windows with 32 bits
+	{
+		// candidate queues (two, ping-pong): ~25 candidates per read at 30x coverage; an overflow halves the chunk and retries
+		const u64 want = part_mode ? std::max<u64>(32ull << 20, (u64)c->chunk_reads * 40) : 8ull << 20;
+		if (c->cand_cap < want) { OGB_TRY(c->cand_q.ensure(2 * want)); OGB_TRY(c->cand_v.ensure(2 * want)); c->cand_cap = want; }
+	}
 	int gp = grid_for(c, (const void *)k_probe<MODE>, 256), gv = grid_for(c, (const void *)k_verify<MODE>, 256);
 	int gu = grid_for(c, (const void *)k_probe_uniform<MODE>, 256);
 	{
@@ -804,9 +920,21 @@ template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 	cudaStream_t sv = overlap_streams ? c->stream2 : c->stream;
 	ScanArgs a = scan_args(c, lo, hi);
 	u32 i = 0;
-	for (u32 b0 = lo; b0 < hi; b0 += c->chunk_reads, i++) {
+	// several ranks (overlap pass): every rank walks the same chunk grid -- ceil(reads per rank / chunk) chunks -- so that the row
+	// exchanges pair up; the chunks a shorter last shard does not have are empty here
+	const bool xchg = MODE == MODE_OVERLAP && c->nranks > 1;
+	const u64 per_rank = ((u64)c->n + c->nranks - 1) / c->nranks;
+	const u32 n_chunks = (u32)(((xchg ? per_rank : (u64)(hi - lo)) + c->chunk_reads - 1) / c->chunk_reads);
+	const GraphView gv_rows = graph_view(c, lo);
+	const int g_rows = grid_for(c, (const void *)k_rows_finish<false>, 256);
+	for (; i < n_chunks; i++) {
+		const u64 b0 = (u64)lo + (u64)i * c->chunk_reads;
 		const int q = i & 1;
-		a.lo = b0; a.hi = (u32)std::min<u64>(hi, (u64)b0 + c->chunk_reads);
+		if (b0 >= hi) {                                                        // no reads of this rank in the chunk: only its part of the exchange
+			if (xchg) { const int ke = kev_begin(c, OGB_KC_EXCH_ROWS, c->xs); OGB_TRY(exchange_chunk_rows(c, i, c->xs)); kev_end(c, ke, c->xs); }
+			continue;
+		}
+		a.lo = (u32)b0; a.hi = (u32)std::min<u64>(hi, b0 + c->chunk_reads);
 		a.cand_q = c->cand_q.p + q * c->cand_cap; a.cand_v = c->cand_v.p + q * c->cand_cap; a.cand_cursor = c->d_cursor + q;
 		if (overlap_streams && i >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_verify[q], 0));   // queue q is free again
 		CUDA_TRY(cudaMemsetAsync(a.cand_cursor, 0, sizeof(u64), c->stream));
@@ -821,28 +949,43 @@ template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 			const u64 tiles = ((u64)warps * nwin_u + 256 * OGB_WPT - 1) / (256 * OGB_WPT);
 			const bool uni = c->uniform_len && !a.contained;
 			const int gw = grid_for(c, uni ? (const void *)k_window_part<MODE, true> : (const void *)k_window_part<MODE, false>, 256), gb = grid_for(c, (const void *)k_probe_parts<MODE>, 256);
-			if (uni) k_window_part<MODE, true><<<(unsigned)std::min<u64>(gw, tiles), 256, 0, c->stream>>>(a, nwin_u, ~0ull / nwin_u + 1, pq);
-			else k_window_part<MODE, false><<<(unsigned)std::min<u64>(gw, tiles), 256, 0, c->stream>>>(a, nwin_u, ~0ull / nwin_u + 1, pq);
+			const int kc = MODE == MODE_OVERLAP ? 0 : OGB_KC_CONTAIN_WINDOW - OGB_KC_WINDOW;
+			if (uni) KEV(OGB_KC_WINDOW + kc, c->stream, (k_window_part<MODE, true><<<(unsigned)std::min<u64>(gw, tiles), 256, 0, c->stream>>>(a, nwin_u, ~0ull / nwin_u + 1, pq)));
+			else KEV(OGB_KC_WINDOW + kc, c->stream, (k_window_part<MODE, false><<<(unsigned)std::min<u64>(gw, tiles), 256, 0, c->stream>>>(a, nwin_u, ~0ull / nwin_u + 1, pq)));
 			if (timed) CUDA_TRY(cudaEventRecord(c->ev_pm[i], c->stream));
-			k_probe_parts<MODE><<<gb, 256, 0, c->stream>>>(a, pq);
+			KEV(OGB_KC_PROBE + kc, c->stream, (k_probe_parts<MODE><<<gb, 256, 0, c->stream>>>(a, pq)));
 			c->launches++;
 		} else if (c->uniform_len && !a.contained) {
 			const u32 nwin = c->uniform_len - c->h - 1;
 			const u64 rounds = ((u64)warps * nwin + 31) / 32;
-			k_probe_uniform<MODE><<<(unsigned)std::min<u64>(gu, (rounds * 32 + 255) / 256), 256, 0, c->stream>>>(a, nwin, ~0ull / nwin + 1);
+			KEV(MODE == MODE_OVERLAP ? OGB_KC_PROBE : OGB_KC_CONTAIN_PROBE, c->stream, (k_probe_uniform<MODE><<<(unsigned)std::min<u64>(gu, (rounds * 32 + 255) / 256), 256, 0, c->stream>>>(a, nwin, ~0ull / nwin + 1)));
 		} else
-			k_probe<MODE><<<(unsigned)std::min<u64>(gp, ((u64)warps * 32 + 255) / 256), 256, 0, c->stream>>>(a);
+			KEV(MODE == MODE_OVERLAP ? OGB_KC_PROBE : OGB_KC_CONTAIN_PROBE, c->stream, (k_probe<MODE><<<(unsigned)std::min<u64>(gp, ((u64)warps * 32 + 255) / 256), 256, 0, c->stream>>>(a)));
 		if (timed) { CUDA_TRY(cudaEventRecord(c->ev_pk[2 * i + 1], c->stream)); c->n_pk = i + 1; }
 		if (overlap_streams) {
 			CUDA_TRY(cudaEventRecord(c->ev_probe[q], c->stream));
 			CUDA_TRY(cudaStreamWaitEvent(sv, c->ev_probe[q], 0));
 		}
-		k_verify<MODE><<<gv, 256, 0, sv>>>(a);
+		KEV(MODE == MODE_OVERLAP ? OGB_KC_VERIFY : OGB_KC_CONTAIN_VERIFY, sv, (k_verify<MODE><<<gv, 256, 0, sv>>>(a)));
+		if (MODE == MODE_OVERLAP) {
+			// rows of the chunk's nodes right behind their verification (slot regions still in L2); nodes with more edges than
+			// slots wait for the heavy pass after K3. Several ranks: the finished rows leave on the exchange stream.
+			KEV(OGB_KC_ROWS, sv, (k_rows_finish<false><<<std::min<int>(g_rows, (int)((a.hi - a.lo + 255) / 256)), 256, 0, sv>>>(gv_rows, a.lo, a.hi, c->more_own.p, c->more_cap, c->d_ctr, nullptr, 0)));
+			c->launches++;
+			if (xchg) {
+				CUDA_TRY(cudaEventRecord(c->ev_rows[q], sv));
+				CUDA_TRY(cudaStreamWaitEvent(c->xs, c->ev_rows[q], 0));
+				const int ke = kev_begin(c, OGB_KC_EXCH_ROWS, c->xs);
+				OGB_TRY(exchange_chunk_rows(c, i, c->xs));
+				kev_end(c, ke, c->xs);
+			}
+		}
 		if (overlap_streams) CUDA_TRY(cudaEventRecord(c->ev_verify[q], sv));
 		c->launches += 2;
 	}
 	if (overlap_streams)                                                     // the main stream continues after every verify
 		for (int q = 0; q < 2 && q < (int)i; q++) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_verify[q], 0));
+	if (xchg) { CUDA_TRY(cudaEventRecord(c->ev_xs, c->xs)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_xs, 0)); }
 	CUDA_TRY(cudaGetLastError());
 	return OGB_OK;
 }
@@ -883,6 +1026,7 @@ extern "C" int ogb_mark_contained(ogb_context *c)
 	c->launches++;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_CONT1], c->stream));
 	OGB_TRY(ctr_fetch(c));
+	kev_collect(c);
 	c->st.ms_contain = ev_ms(c, EV_CONT0, EV_CONT1);
 	c->st.n_contained = c->h_ctr[CTR_N_CONTAINED];
 	c->any_contained = c->st.n_contained > 0;
@@ -923,7 +1067,7 @@ static GraphView graph_view(const ogb_context *c, u32 lo)
 	GraphView g;
 	const u64 per = ((u64)c->n + c->nranks - 1) / c->nranks;
 	g.slots = c->slots_e.p; g.deg = c->deg.p; g.ext = c->ext.p; g.lo = lo; g.cap = c->slot_cap;
-	g.rows = c->rows.p; g.more = c->more.p; g.ebits = c->ebits.p;
+	g.rows = c->rows.p; g.more = c->nranks > 1 ? c->more.p : c->more_own.p; g.ebits = c->ebits.p;
 	g.more_stride = c->more_stride; g.nrows = per * c->nranks;
 	g.per_magic = c->nranks > 1 && per > 1 ? ~0ull / per + 1 : 0;          // exact floor(v / per) for 32-bit v (Lemire); per == 1: see rank_of
 	g.my_rank = (u32)c->rank;
@@ -976,13 +1120,15 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	// ---- K3 (probe + verify in chunks) into the slot regions and the adjacency rows; retried with larger pools when a
 	// capacity was exceeded. Every decision below derives from values all ranks share.
 	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL0], c->stream));
-	u64 local_edges = 0, exact_edges = 0, more_need = 0;
-	std::vector<u64> seg_cnt(G, 0);
+	u64 local_edges = 0, exact_edges = 0, more_need = 0, heavy_max = 0;
+	std::vector<u64> seg_cnt(G, 0), hrow_cnt(G, 0);
 	for (int attempt = 0;; attempt++) {
 		if (attempt == 16) { ogb_set_error("ogb_build_graph: staging pools kept overflowing"); return OGB_E_CAPACITY; }
 		OGB_TRY(c->slots_e.ensure(per * c->slot_cap + 64));
 		OGB_TRY(c->deg.ensure((size_t)n + 1));
 		OGB_TRY(c->ext.ensure(1 << 16));
+		if (c->more_cap == 0) c->more_cap = per * 8 + 1024;                  // entries beyond the rows; grows with the need (same value on every rank)
+		OGB_TRY(c->more_own.ensure((c->more_cap + 1023) & ~1023ull));      // rounded like the exchange stride: never reallocated after K3 has filled it
 		OGB_TRY(ctr_zero(c));
 		if (nloc) CUDA_TRY(cudaMemsetAsync(c->deg.p + lo, 0, (size_t)nloc * sizeof(u32), c->stream));
 		CUDA_TRY(cudaEventRecord(c->ev[EV_K3A], c->stream));
@@ -994,10 +1140,11 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		OGB_TRY(ctr_fetch(c));
 		const u64 n_over = c->h_ctr[CTR_OVERFLOW], n_heavy = c->h_ctr[CTR_BIG_NODES];
 		// [0] candidate queue overflowed, [1] spilled edges, [2] largest degree, [3] edges of this rank, [4] words its heavy lists need,
-		// [5] a window queue overflowed, [6] entries of this rank beyond the rows
-		u64 verdict[XCHG_PER_RANK] = {c->h_ctr[CTR_CAND_MAX] > c->cand_cap, n_over, c->h_ctr[CTR_MAX_DEGREE], local_edges, n_over + n_heavy * c->slot_cap, c->h_ctr[CTR_PQ_OVERFLOW] != 0, c->h_ctr[CTR_MORE_NEED], 0};
-		more_need = verdict[6];
+		// [5] a window queue overflowed, [6] entries of this rank beyond the rows, [7] its heavy nodes
+		u64 verdict[XCHG_PER_RANK] = {c->h_ctr[CTR_CAND_MAX] > c->cand_cap, n_over, c->h_ctr[CTR_MAX_DEGREE], local_edges, n_over + n_heavy * c->slot_cap, c->h_ctr[CTR_PQ_OVERFLOW] != 0, c->h_ctr[CTR_MORE_NEED], n_heavy};
+		more_need = verdict[6]; heavy_max = n_heavy;
 		seg_cnt[0] = local_edges; exact_edges = local_edges;
+		hrow_cnt.assign(G, 0); hrow_cnt[0] = n_heavy;
 		if (G > 1) {
 			// one small allgather carries the retry verdicts and the per-rank edge counts
 			CUDA_TRY(cudaMemcpyAsync(c->d_xchg + XCHG_PER_RANK * c->rank, verdict, sizeof verdict, cudaMemcpyHostToDevice, c->stream));
@@ -1009,11 +1156,12 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 			for (int r = 0; r < G; r++) {
 				const u64 *v = &all[(size_t)XCHG_PER_RANK * r];
 				verdict[0] = std::max(verdict[0], v[0]); verdict[1] = std::max(verdict[1], v[1]); verdict[2] = std::max(verdict[2], v[2]); verdict[5] = std::max(verdict[5], v[5]);
-				more_need = std::max(more_need, v[6]);
-				seg_cnt[r] = v[3]; exact_edges += v[3];
+				more_need = std::max(more_need, v[6]); heavy_max = std::max(heavy_max, v[7]);
+				seg_cnt[r] = v[3]; exact_edges += v[3]; hrow_cnt[r] = v[7];
 			}
 		}
 		if (verdict[5]) { c->pq_slack *= 2; continue; }                      // a partition's window queue overflowed (skewed keys): more slack, up to everything in one partition
+		if (more_need > c->more_cap) { c->more_cap = more_need + more_need / 8 + 1024; continue; }   // the overflow segment was too small for some rank
 		if (verdict[0]) { c->chunk_reads = std::max<u32>(256, c->chunk_reads / 2); continue; }
 		if (verdict[1] > c->ov_q.cap) {                                      // many heavy nodes: more slots per read, bigger spill list
 			if (c->slot_cap < 256) c->slot_cap *= 2;
@@ -1041,22 +1189,38 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	c->n_pre = exact_edges;
 	CUDA_TRY(cudaEventRecord(c->ev[EV_OVL1], c->stream));
 
-	// ---- rows: headers + the entries beyond 30 (same segment size on every rank: the largest need). C1 (several
-	// ranks): a pivot or a twin can live on any rank -- one in-place allgather each for the rows and the overflow segments.
+	// ---- rows of the heavy nodes (their lists are complete only now), then what is left of C1 on several ranks: the heavy
+	// rows as (node, row) records and the overflow segments at a common stride. The rows of all other nodes were built and
+	// sent chunk by chunk behind k_verify (scan_chunks).
 	if (more_need >= (1ull << 32) - 2048) { ogb_set_error("ogb_build_graph: adjacency overflow area too large"); return OGB_E_CAPACITY; }
-	c->more_stride = std::max<u64>(1024, (more_need + 1023) & ~1023ull);
-	OGB_TRY(c->more.ensure(c->more_stride * G));
+	c->more_stride = G > 1 ? std::max<u64>(1024, (more_need + 1023) & ~1023ull) : ((c->more_cap + 1023) & ~1023ull);
+	if (G > 1) OGB_TRY(c->more.ensure(c->more_stride * G));                  // more_own already holds >= more_stride entries (more_need <= more_cap)
 	const u64 nrows = per * G, obit_words = c->more_stride / 32;          // overflow bits: one word-aligned segment per rank
 	OGB_TRY(c->ebits.ensure(nrows + obit_words * G + 2));
 	CUDA_TRY(cudaMemsetAsync(c->ebits.p + nrows + obit_words * c->rank, 0, obit_words * sizeof(u32), c->stream));
-	if (nloc) {
-		k_rows_finish<<<grid_for(c, (const void *)k_rows_finish, 256), 256, 0, c->stream>>>(graph_view(c, lo), lo, hi, c->d_ctr);
+	if (heavy_max) {
+		const u64 hstride = heavy_max;
+		if (G > 1) OGB_TRY(c->hrows.ensure(hstride * G * OGB_HROW_W));
+		u32 *my_h = G > 1 ? c->hrows.p + hstride * c->rank * OGB_HROW_W : nullptr;
+		if (nloc && hrow_cnt[c->rank])
+			KEV(OGB_KC_ROWS, c->stream, (k_rows_finish<true><<<grid_for(c, (const void *)k_rows_finish<true>, 256), 256, 0, c->stream>>>(graph_view(c, lo), lo, hi, c->more_own.p, c->more_cap, c->d_ctr, my_h, hstride)));
 		CUDA_TRY(cudaGetLastError());
 		c->launches++;
+		if (G > 1) {
+			const int ke = kev_begin(c, OGB_KC_EXCH_ROWS, c->stream);
+			NCCL_TRY(g_nccl.AllGather(c->hrows.p + hstride * c->rank * OGB_HROW_W, c->hrows.p, hstride * OGB_HROW_W, NCCL_UINT32, c->comm, c->stream));
+			kev_end(c, ke, c->stream);
+			OGB_TRY(c->sums.ensure(G + 8));
+			CUDA_TRY(cudaMemcpyAsync(c->sums.p, hrow_cnt.data(), (size_t)G * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+			k_scatter_hrows<<<c->sm_count, 256, 0, c->stream>>>(c->hrows.p, hstride, c->sums.p, (u32)G, (u32)c->rank, c->rows.p);
+			CUDA_TRY(cudaGetLastError());
+			c->launches++;
+		}
 	}
-	if (G > 1) {
-		NCCL_TRY(g_nccl.AllGather(c->rows.p + per * OGB_ROW_W * c->rank, c->rows.p, per * OGB_ROW_W, NCCL_UINT32, c->comm, c->stream));
-		if (more_need) NCCL_TRY(g_nccl.AllGather(c->more.p + c->more_stride * c->rank, c->more.p, c->more_stride, NCCL_UINT32, c->comm, c->stream));
+	if (G > 1 && more_need) {
+		const int ke = kev_begin(c, OGB_KC_EXCH_ROWS, c->stream);
+		NCCL_TRY(g_nccl.AllGather(c->more_own.p, c->more.p, c->more_stride, NCCL_UINT32, c->comm, c->stream));
+		kev_end(c, ke, c->stream);
 	}
 	CUDA_TRY(cudaEventRecord(c->ev[EV_XPRE1], c->stream));
 
@@ -1092,10 +1256,10 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		OGB_TRY(ctr_zero(c));
 		m.scratch_keys = c->scratch_keys.p; m.scratch_cap = c->scratch_keys.cap; m.ctr = c->d_ctr;
 		// degree 1..32, 33..64 (edges in registers), the rest (and the few nodes the fast kernels hand over)
-		k_mark_fast<1><<<grid_for(c, (const void *)k_mark_fast<1>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
-		if (c->st.max_degree > 32) k_mark_fast<2><<<grid_for(c, (const void *)k_mark_fast<2>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
+		KEV(OGB_KC_MARK1, c->stream, (k_mark_fast<1><<<grid_for(c, (const void *)k_mark_fast<1>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m)));
+		if (c->st.max_degree > 32) KEV(OGB_KC_MARK2, c->stream, (k_mark_fast<2><<<grid_for(c, (const void *)k_mark_fast<2>, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m)));
 		c->launches += c->st.max_degree > 32 ? 2 : 1;
-		k_mark_any<<<grid_for(c, (const void *)k_mark_any, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m);
+		KEV(OGB_KC_MARKANY, c->stream, (k_mark_any<<<grid_for(c, (const void *)k_mark_any, OGB_WARPS * 32), OGB_WARPS * 32, 0, c->stream>>>(m)));
 		CUDA_TRY(cudaGetLastError());
 		c->launches++;
 		if (c->st.max_degree * 2 <= OGB_SETCAP) break;                      // no node can have used the scratch pool
@@ -1106,13 +1270,18 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	}
 	CUDA_TRY(cudaEventRecord(c->ev[EV_MARK1], c->stream));
 	if (G > 1) {                                                             // C2: one ELIM bit per entry
+		const int ke = kev_begin(c, OGB_KC_EXCH_BITS, c->stream);
 		NCCL_TRY(g_nccl.AllGather(c->ebits.p + per * c->rank, c->ebits.p, per, NCCL_UINT32, c->comm, c->stream));
 		if (more_need) NCCL_TRY(g_nccl.AllGather(c->ebits.p + nrows + obit_words * c->rank, c->ebits.p + nrows, obit_words, NCCL_UINT32, c->comm, c->stream));
+		kev_end(c, ke, c->stream);
 	}
 
 	// ---- K6
+	const int ke_keep = kev_begin(c, OGB_KC_KEEP, c->stream);
 	if (nloc) k_keep<<<(nloc + 255) / 256, 256, 0, c->stream>>>(m, c->surv.p);
 	k_keep_big<<<c->sm_count, 256, 0, c->stream>>>(m);
+	kev_end(c, ke_keep, c->stream);
+	const int ke_emit = kev_begin(c, OGB_KC_EMIT, c->stream);
 	CUDA_TRY(cudaGetLastError());
 	c->launches += 2;
 	OGB_TRY(exclusive_scan(c, c->cnt.p, nloc, c->pos.p, c->d_tot + 1));
@@ -1121,11 +1290,12 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		if (nloc) k_emit_small<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->surv.p, c->cnt.p, c->cntc.p, c->pos.p, c->fin.p, lo, hi, 0);
 		k_emit<false><<<g_emit, OGB_WARPS * 32, 0, c->stream>>>(c->slots_e.p, c->ext.p, c->deg.p, c->cntc.p, c->pos.p, c->fin.p, lo, hi, cap_now, 0, OGB_SURV);
 		CUDA_TRY(cudaGetLastError());
+		kev_end(c, ke_emit, c->stream);
 		c->launches += 2;
 		u64 tot = 0;
 		CUDA_TRY(cudaMemcpyAsync(&tot, c->d_tot + 1, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 		OGB_TRY(ctr_fetch(c));
-		c->n_final = tot;
+		c->n_final = tot; c->fin_own_off = 0; c->fin_own_cnt = tot;
 	} else {
 		// C3: the final edges of every rank's node range (the exchange north_star names). Segment sizes
 		// travel first (one word per rank); the segments are emitted at a common stride so that the
@@ -1138,14 +1308,17 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 		u64 stride = 0, total = 0;
 		for (int r = 0; r < G; r++) { stride = std::max(stride, fin_cnt[r]); total += fin_cnt[r]; }
 		stride = (stride + 63) & ~63ull;
-		c->n_final = total;
+		c->n_final = total; c->fin_own_off = 0; for (int r = 0; r < c->rank; r++) c->fin_own_off += fin_cnt[r]; c->fin_own_cnt = fin_cnt[c->rank];
 		OGB_TRY(c->fin_stage.ensure(std::max<u64>(stride * G, 1)));
 		OGB_TRY(c->fin.ensure(std::max<u64>(total, 1)));
 		if (nloc) k_emit_small<<<(nloc + 255) / 256, 256, 0, c->stream>>>(c->surv.p, c->cnt.p, c->cntc.p, c->pos.p, c->fin_stage.p, lo, hi, stride * c->rank);
 		k_emit<false><<<g_emit, OGB_WARPS * 32, 0, c->stream>>>(c->slots_e.p, c->ext.p, c->deg.p, c->cntc.p, c->pos.p, c->fin_stage.p, lo, hi, cap_now, stride * c->rank, OGB_SURV);
 		CUDA_TRY(cudaGetLastError());
+		kev_end(c, ke_emit, c->stream);
 		c->launches += 2;
+		const int ke_fin = kev_begin(c, OGB_KC_EXCH_FINAL, c->stream);
 		OGB_TRY(gather_segments(c, c->fin_stage, stride, fin_cnt, c->fin.p));
+		kev_end(c, ke_fin, c->stream);
 		NCCL_TRY(g_nccl.AllReduce(c->d_ctr + CTR_NODES_FINAL, c->d_xchg + XCHG_SCRATCH + 2, 1, NCCL_UINT64, 0 /*ncclSum*/, c->comm, c->stream));
 		OGB_TRY(ctr_fetch(c));
 		CUDA_TRY(cudaMemcpyAsync(&c->h_ctr[CTR_NODES_FINAL], c->d_xchg + XCHG_SCRATCH + 2, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
@@ -1153,6 +1326,7 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	}
 	CUDA_TRY(cudaEventRecord(c->ev[EV_RED1], c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	kev_collect(c);
 	if (c->h_ctr[CTR_ASYMMETRIC]) { ogb_set_error("ogb_build_graph: %llu edges without a twin (internal error)", (unsigned long long)c->h_ctr[CTR_ASYMMETRIC]); return OGB_E_STATE; }
 	// next build on these reads: slots sized to the largest degree seen (a collective value: same decision on every rank)
 	{
@@ -1205,6 +1379,37 @@ extern "C" int ogb_graph_edges(ogb_context *c, int which, ogb_edge *out, uint64_
 	return OGB_OK;
 }
 
+// The final edges whose source lies in this rank's node range (one rank: all of them): what a rank hands back to its
+// host when the ranks' hosts each continue with their own part.
+extern "C" int ogb_graph_edges_shard(ogb_context *c, ogb_edge *out, uint64_t cap, uint64_t *n_out)
+{
+	if (!c || !n_out) { ogb_set_error("ogb_graph_edges_shard: NULL argument"); return OGB_E_ARG; }
+	if (!c->have_graph) { ogb_set_error("ogb_graph_edges_shard: build the graph first"); return OGB_E_STATE; }
+	*n_out = c->fin_own_cnt;
+	if (c->fin_own_cnt == 0) return OGB_OK;
+	if (!out || cap < c->fin_own_cnt) { ogb_set_error("ogb_graph_edges_shard: need room for %llu edges", (unsigned long long)c->fin_own_cnt); return OGB_E_CAPACITY; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	CUDA_TRY(cudaMemcpyAsync(out, c->fin.p + c->fin_own_off, c->fin_own_cnt * sizeof(ogb_edge), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return OGB_OK;
+}
+
+extern "C" int ogb_graph_checksum(ogb_context *c, int which, uint64_t *xor_out, uint64_t *sum_out)
+{
+	uint64_t n = 0;
+	OGB_TRY(ogb_graph_edge_count(c, which, &n));
+	if (!xor_out || !sum_out) { ogb_set_error("ogb_graph_checksum: NULL argument"); return OGB_E_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	CUDA_TRY(cudaMemsetAsync(c->d_xchg + XCHG_SCRATCH + 4, 0, 2 * sizeof(u64), c->stream));
+	if (n) k_edge_checksum<<<c->sm_count * 8, 256, 0, c->stream>>>(which ? c->pre.p : c->fin.p, n, c->d_xchg + XCHG_SCRATCH + 4);
+	CUDA_TRY(cudaGetLastError());
+	u64 h[2] = {0, 0};
+	CUDA_TRY(cudaMemcpyAsync(h, c->d_xchg + XCHG_SCRATCH + 4, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	*xor_out = h[0]; *sum_out = h[1];
+	return OGB_OK;
+}
+
 extern "C" int ogb_get_stats(ogb_context *c, ogb_stats *out)
 {
 	if (!c || !out) { ogb_set_error("ogb_get_stats: NULL argument"); return OGB_E_ARG; }
@@ -1237,5 +1442,33 @@ extern "C" int ogb_l2_flush(ogb_context *c, size_t bytes)
 	OGB_TRY(c->flush.ensure(bytes));
 	CUDA_TRY(cudaMemsetAsync(c->flush.p, 0x5a, bytes, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return OGB_OK;
+}
+
+extern "C" int ogb_gather_ceiling(ogb_context *c, size_t buffer_bytes, uint32_t gather_bytes, double *gb_per_s)
+{
+	if (!c || !gb_per_s) { ogb_set_error("ogb_gather_ceiling: NULL argument"); return OGB_E_ARG; }
+	if (gather_bytes != 32 && gather_bytes != 64 && gather_bytes != 128) { ogb_set_error("ogb_gather_ceiling: gather_bytes must be 32, 64 or 128"); return OGB_E_ARG; }
+	if (buffer_bytes < (1u << 20) || (buffer_bytes & (buffer_bytes - 1))) { ogb_set_error("ogb_gather_ceiling: buffer_bytes must be a power of two >= 1 MiB"); return OGB_E_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	OGB_TRY(c->flush.ensure(buffer_bytes));
+	CUDA_TRY(cudaMemsetAsync(c->flush.p, 1, buffer_bytes, c->stream));
+	const u64 nblocks = buffer_bytes / gather_bytes;
+	const u32 per_thread = 256;
+	const int grid = c->sm_count * 8;
+	float best = 1e30f;
+	for (int rep = 0; rep < 4; rep++) {
+		CUDA_TRY(cudaEventRecord(c->ev[EV_T0], c->stream));
+		if (gather_bytes == 32) k_gather_ceiling<32><<<grid, 256, 0, c->stream>>>((const u64 *)c->flush.p, nblocks, per_thread, c->d_tot);
+		else if (gather_bytes == 64) k_gather_ceiling<64><<<grid, 256, 0, c->stream>>>((const u64 *)c->flush.p, nblocks, per_thread, c->d_tot);
+		else k_gather_ceiling<128><<<grid, 256, 0, c->stream>>>((const u64 *)c->flush.p, nblocks, per_thread, c->d_tot);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaEventRecord(c->ev[EV_T1], c->stream));
+		CUDA_TRY(cudaEventSynchronize(c->ev[EV_T1]));
+		float ms = 0;
+		CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[EV_T0], c->ev[EV_T1]));
+		if (rep && ms < best) best = ms;                                      // the first run warms the TLBs
+	}
+	*gb_per_s = (double)grid * 256 * per_thread * gather_bytes / (best * 1e-3) / 1e9;
 	return OGB_OK;
 }

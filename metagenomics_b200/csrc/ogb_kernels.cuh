@@ -58,7 +58,7 @@ enum {
 	CTR_EDGE_CURSOR = 0, CTR_OVERFLOW, CTR_PROBES, CTR_SECTORS, CTR_CANDIDATES, CTR_CONTAIN_HITS,
 	CTR_PIVOT_ENTRIES, CTR_ACTIVE_PIVOTS, CTR_MAX_DEGREE, CTR_N_CONTAINED, CTR_NODES_FINAL,
 	CTR_ASYMMETRIC, CTR_SCRATCH_CURSOR, CTR_SCRATCH_FAIL, CTR_CAND_MAX, CTR_BIG_NODES, CTR_EXT_CURSOR, CTR_PQ_OVERFLOW,
-	CTR_TABLE_FULL, CTR_MORE_CURSOR, CTR_MORE_NEED, CTR_BIGREC_CURSOR, CTR_COUNT
+	CTR_TABLE_FULL, CTR_MORE_CURSOR, CTR_MORE_NEED, CTR_BIGREC_CURSOR, CTR_HROW_CURSOR, CTR_COUNT
 };
 
 struct ReadStore {
@@ -997,19 +997,28 @@ __device__ __forceinline__ u64 entry_bit(const GraphView &G, u32 vidx, u32 pos)
 	return G.nrows * 32 + (u64)rank_of(G, vidx) * G.more_stride + ovf + (pos - OGB_ROW_E) + 1;
 }
 
-// Rows of the own nodes [lo, hi) from their edge words: header, entries 0..29, and the entries beyond in the rank's
-// segment of `more`. A warp takes 32 nodes at a time: lane i looks at node i's degree, the overflow space of all 32 is
-// reserved with one atomic, then the warp copies node after node with lane k on entry k (coalesced on both sides).
-// Runs after the heavy lists are in place. (Writing the row entries from k_verify, next to the edge words, was measured
-// first: scattered 4-byte stores cost 2.2 ms at config 3 against 0.7 ms for this pass.)
-__global__ void __launch_bounds__(256) k_rows_finish(GraphView G, u32 lo, u32 hi, u64 *ctr)
+// Rows of the own nodes [lo, hi) from their edge words: header, entries 0..29, and the entries beyond in this rank's
+// overflow segment `more_own` (more_cap entries; the running cursor CTR_MORE_CURSOR hands out space, so the pass can run
+// chunk by chunk right behind k_verify, while the chunk's slot regions are still in L2 -- and, on several ranks, the
+// finished rows of a chunk travel to the peers while the next chunk is probed). A warp takes 32 nodes at a time: lane i
+// looks at node i's degree, the overflow space of all 32 is reserved with one atomic, then the warp copies node after
+// node with lane k on entry k (coalesced on both sides). HEAVY = false: nodes with more edges than slots are left for
+// the HEAVY = true pass, which runs once their lists have been gathered in ext (k_heavy_move / k_heavy_place) and also
+// appends (node, row) records to hrows for the peers. (Writing the row entries from k_verify, next to the edge words, was
+// measured first: scattered 4-byte stores cost 2.2 ms at config 3 against 0.7-0.9 ms for this pass.)
+#define OGB_HROW_W 34           // u32 words per heavy-row record: node index, pad, 32 row words
+template <bool HEAVY>
+__global__ void __launch_bounds__(256) k_rows_finish(GraphView G, u32 lo, u32 hi, u32 *__restrict__ more_own, u64 more_cap, u64 *ctr,
+                                                     u32 *__restrict__ hrows, u64 hrows_cap)
 {
 	const u32 lane = threadIdx.x & 31;
 	const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 	for (u32 u0 = lo + gw * 32; u0 < hi; u0 += nwarps * 32) {
 		const u32 mine = u0 + lane;
-		const u32 dm = mine < hi ? G.deg[mine] : 0;
-		const u32 need = dm > OGB_ROW_E ? dm - OGB_ROW_E : 0;
+		u32 dm = mine < hi ? G.deg[mine] : 0;
+		const bool heavy = dm > G.cap;
+		if (heavy != HEAVY) dm = HEAVY ? 0 : 0xFFFFFFFFu;                     // not this pass's node (0: nothing to do; ~0: skip, keep the row)
+		const u32 need = dm != 0xFFFFFFFFu && dm > OGB_ROW_E ? dm - OGB_ROW_E : 0;
 		u32 inc = need;
 		#pragma unroll
 		for (int s = 1; s < 32; s <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, s); if (lane >= (u32)s) inc += t; }
@@ -1026,16 +1035,34 @@ __global__ void __launch_bounds__(256) k_rows_finish(GraphView G, u32 lo, u32 hi
 			const u32 d = __shfl_sync(0xFFFFFFFFu, dm, j);
 			const u64 off = __shfl_sync(0xFFFFFFFFu, offm, j);
 			u32 *row = G.rows + (u64)u * OGB_ROW_W;
-			if (d == 0) { if (lane == 0) row[0] = 0; continue; }
+			if (d == 0xFFFFFFFFu) continue;
+			if (d == 0) { if (!HEAVY && lane == 0) row[0] = 0; continue; }
 			const u64 *own = G.slots + (u64)(u - G.lo) * G.cap;
-			if (d > G.cap) own = G.ext + own[0];
+			if (HEAVY) own = G.ext + own[0];
 			u32 wv = lane == 0 ? d : (u32)off;                                  // header: degree, overflow offset
 			if (lane >= 2) wv = lane - 2 < d ? row_entry(own[lane - 2]) : 0;
 			row[lane] = wv;
-			if (d > OGB_ROW_E && off + (d - OGB_ROW_E) <= G.more_stride) {        // always true: the segment is sized from the exact count
-				u32 *dst = G.more + (u64)G.my_rank * G.more_stride + off;
-				for (u32 k = OGB_ROW_E + lane; k < d; k += 32) dst[k - OGB_ROW_E] = row_entry(own[k]);
+			if (HEAVY && hrows) {
+				u64 at = 0;
+				if (lane == 0) at = atomicAdd(ctr + CTR_HROW_CURSOR, 1ull);
+				at = __shfl_sync(0xFFFFFFFFu, at, 0);
+				if (at < hrows_cap) { u32 *r = hrows + at * OGB_HROW_W; if (lane == 0) { r[0] = u; r[1] = 0; } r[2 + lane] = wv; }
 			}
+			if (d > OGB_ROW_E && off + (d - OGB_ROW_E) <= more_cap)             // beyond the capacity: the host sees the cursor and retries with more
+				for (u32 k = OGB_ROW_E + lane; k < d; k += 32) more_own[off + k - OGB_ROW_E] = row_entry(own[k]);
+		}
+	}
+}
+// Heavy-row records of the other ranks (allgathered at a common stride) into the local rows
+__global__ void __launch_bounds__(256) k_scatter_hrows(const u32 *__restrict__ hrows, u64 stride, const u64 *__restrict__ counts, u32 nranks, u32 my_rank, u32 *__restrict__ rows)
+{
+	const u32 lane = threadIdx.x & 31;
+	const u64 gw = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+	for (u32 r = 0; r < nranks; r++) {
+		if (r == my_rank) continue;
+		for (u64 i = gw; i < counts[r]; i += nwarps) {
+			const u32 *rec = hrows + (r * stride + i) * OGB_HROW_W;
+			rows[(u64)rec[0] * OGB_ROW_W + lane] = rec[2 + lane];
 		}
 	}
 }
@@ -1761,4 +1788,48 @@ __global__ void k_lookup(ReadStore R, Table T, const u64 *__restrict__ keys, u32
 		b = next_bucket(b, pend, T);
 	}
 	if (pass == 0) cnt[k] = c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Measurement helper (ogb_gather_ceiling): random, aligned, non-allocating gathers of BYTES from a buffer of
+// nblocks * BYTES bytes (nblocks a power of two), four independent ones in flight per thread -- the access
+// pattern of the index probes, the partner-strand fetches and the pivot-row fetches, with nothing else around it.
+// ------------------------------------------------------------------------------------------------
+template <int BYTES>
+__global__ void __launch_bounds__(256) k_gather_ceiling(const u64 *__restrict__ buf, u64 nblocks, u32 per_thread, u64 *out)
+{
+	const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	u64 acc = 0;
+	for (u32 it = 0; it < per_thread; it += 4) {
+		u64 v[4][BYTES / 8];
+		#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			u64 x = tid * 0x9E3779B97F4A7C15ULL + it + u;
+			x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+			const u64 *p = buf + (x & (nblocks - 1)) * (BYTES / 8);
+			#pragma unroll
+			for (int q = 0; q < BYTES / 32; q++)
+				asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[u][4 * q]), "=l"(v[u][4 * q + 1]), "=l"(v[u][4 * q + 2]), "=l"(v[u][4 * q + 3]) : "l"(p + 4 * q));
+		}
+		#pragma unroll
+		for (int u = 0; u < 4; u++)
+			#pragma unroll
+			for (int q = 0; q < BYTES / 8; q++) acc ^= v[u][q];
+	}
+	if (acc == 0x1234567) out[0] = acc;
+}
+
+// Order-independent checksum of a list of edge records (xor and sum of a 64-bit mix of every tuple): the bench and
+// the full-size tests compare it with the oracle's figure without moving GBs of edges to the host.
+__global__ void __launch_bounds__(256) k_edge_checksum(const ogb_edge *__restrict__ e, u64 n, u64 *out)
+{
+	u64 x_or = 0, x_sum = 0;
+	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+		const ogb_edge r = e[i];
+		u64 x = (u64)r.src * 0x9E3779B97F4A7C15ULL ^ (u64)r.dst * 0xC2B2AE3D27D4EB4FULL ^ (u64)r.offset * 0x165667B19E3779F9ULL ^ (u64)r.orient * 0x27D4EB2F165667C5ULL;
+		x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 32;
+		x_or ^= x; x_sum += x;
+	}
+	for (int d = 16; d > 0; d >>= 1) { x_or ^= __shfl_down_sync(0xFFFFFFFFu, x_or, d); x_sum += __shfl_down_sync(0xFFFFFFFFu, x_sum, d); }
+	if ((threadIdx.x & 31) == 0) { atomicXor(out, x_or); atomicAdd(out + 1, x_sum); }
 }

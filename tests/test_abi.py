@@ -23,13 +23,13 @@ def test_every_declared_symbol_is_exported_and_bound():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/ogb.h but not exported by libogb.so"
     assert set(names) == set(PROTOTYPES), set(names) ^ set(PROTOTYPES)
-    assert lib().ogb_version() == 100
+    assert lib().ogb_version() == 200
 
 
 def test_struct_layout():
     from metagenomics_b200._lib import Edge, Stats
     assert C.sizeof(Edge) == 12 and Edge.offset.offset == 8 and Edge.orient.offset == 10
-    assert C.sizeof(Stats) == 17 * 8 + 4 * 4 + 11 * 4 + 4      # 11 floats, padded to the 8-byte alignment of the struct
+    assert C.sizeof(Stats) == 17 * 8 + 4 * 4 + 11 * 4 + 20 * 4 + 20 * 4 + 4      # 11 + 20 floats, 20 counters, padded to the 8-byte alignment of the struct
 
 
 def test_device_calls_fail_loudly_without_gpu():

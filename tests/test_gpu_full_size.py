@@ -12,7 +12,9 @@ from oracle_lib import sort_tuples
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-GOLD = json.load(open(os.path.join(HERE, "golden", "full_size.json")))
+# one GPU: the entries up to ~10 M reads (the larger ones -- config 3 x 2/4/8, config 4 at full size -- are the multi-GPU cases of
+# tests/test_multi_gpu.py and the bench's own parity check)
+GOLD = [g for g in json.load(open(os.path.join(HERE, "golden", "full_size.json"))) if g["n_unique"] <= 11_000_000 and (g["config"], g["scale"]) != (2, 4.0)]
 
 
 def checksum(e):

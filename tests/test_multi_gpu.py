@@ -11,7 +11,29 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world", [2, 4])
+def _torchrun(world, script, *args, timeout=1800):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29500 + world), os.path.join(ROOT, "tests", script)] + [str(a) for a in args]
+    return subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+
+
+# (world, config, scale): the weak-scaled bench workloads (config 3 x world) and config 2 x world -- sub-partitioned index,
+# rows of hundreds of MB through C1, the retry paths -- and, on 8 GPUs, BASELINE.json configs[3] at full size (50 M x 150 bp)
+BIG = [(2, 2, 2.0), (2, 3, 2.0), (4, 2, 4.0), (4, 3, 4.0), (8, 2, 8.0), (8, 3, 8.0), (8, 4, 1.0)]
+
+
+@pytest.mark.parametrize("world,config,scale", BIG, ids=[f"{w}gpu-config{c}@{s}" for w, c, s in BIG])
+def test_sharded_build_matches_golden_at_scale(world, config, scale):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    r = _torchrun(world, "dist_worker_big.py", config, scale, timeout=3000)
+    assert r.returncode == 0, r.stdout[-4000:]
+    assert r.stdout.count("identical to the golden") == world, r.stdout[-2000:]
+    print(r.stdout[-1500:])
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_build_matches_oracle(world):
     import torch
     if torch.cuda.device_count() < world:
