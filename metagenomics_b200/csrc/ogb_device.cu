@@ -714,9 +714,10 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 	// Partitions per rank: 1 while a rank's slice fits L2; beyond that the slice is cut into pieces of <= 48 MB, the
 	// unit the partitioned probe (k_window_part / k_probe_parts) works through at a time.
 	// A partition is chosen by the key's first 16 bases alone and linear probing wraps inside it, so a skewed read set can
-	// fill one up (K1 raises CTR_TABLE_FULL after a whole lap): the build is then repeated with half as many partitions per
+	// fill one up (K1 raises CTR_TABLE_FULL after a whole lap; a key queue that overflows raises it to 2): the build is then repeated with half as many partitions per
 	// rank and, once there is one per rank, with twice the buckets -- a collective decision, all ranks see the same flag.
 	u64 sub_limit = OGB_MAXPART / c->nranks, nb = 0;
+	bool k1_direct = false;
 	for (int attempt = 0;; attempt++) {
 		if (attempt == 12) { ogb_set_error("ogb_hash_build: a hash partition kept filling up (%u partitions, %.1f buckets per read)", c->nparts, buckets_per_read); return OGB_E_CAPACITY; }
 		nb = std::max<u64>((u64)(buckets_per_read * c->n) + 1, 512);
@@ -742,9 +743,31 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 		CUDA_TRY(cudaMemsetAsync(c->d_ctr + CTR_TABLE_FULL, 0, sizeof(u64), c->stream));
 		if (c->n) {
 			u64 threads = (u64)c->n * 4;
-			KEV(OGB_KC_HASH, c->stream, (k_hash_insert<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->rs(), c->tb())));
-			CUDA_TRY(cudaGetLastError());
-			c->launches++;
+			// Several partitions per rank (index beyond L2): the keys go through per-partition queues and are inserted one
+			// L2-resident partition at a time. A skewed set that overflows a queue (checked below) is rebuilt by the direct kernel.
+			const u32 sub = c->nparts / c->nranks;
+			const char *eq = getenv("OGB_K1_QUEUES");                            // experiment knob: 0 = always the direct kernel
+			const bool queued = sub > 1 && !k1_direct && !(eq && atoi(eq) == 0);
+			if (queued) {
+				const u64 qcap = threads / c->nparts * 5 / 4 + 4096;             // 25 % slack over an even split of the 4N keys over the partitions
+				OGB_TRY(c->pq_b.ensure(qcap * sub)); OGB_TRY(c->pq_f.ensure(qcap * sub)); OGB_TRY(c->pq_q.ensure(qcap * sub));
+				KeyQueue kq;
+				kq.b = c->pq_b.p; kq.f = c->pq_f.p; kq.v = c->pq_q.p; kq.cursor = c->d_pq_cursor; kq.cap = qcap;
+				kq.nparts = c->nparts; kq.first = (u32)c->rank * sub; kq.count = sub;
+				CUDA_TRY(cudaMemsetAsync(c->d_pq_cursor, 0, OGB_MAXPART * sizeof(u64), c->stream));
+				const u64 tiles = (threads + 256 * OGB_KPT - 1) / (256 * OGB_KPT);
+				const int ke = kev_begin(c, OGB_KC_HASH, c->stream);
+				k_key_part<<<(unsigned)std::min<u64>(grid_for(c, (const void *)k_key_part, 256), tiles), 256, 0, c->stream>>>(c->rs(), c->tb(), kq);
+				k_insert_parts<<<grid_for(c, (const void *)k_insert_parts, 256), 256, 0, c->stream>>>(c->tb(), kq);
+				kev_end(c, ke, c->stream);
+				CUDA_TRY(cudaGetLastError());
+				c->launches += 2;
+			}
+			if (!queued) {
+				KEV(OGB_KC_HASH, c->stream, (k_hash_insert<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->rs(), c->tb())));
+				CUDA_TRY(cudaGetLastError());
+				c->launches++;
+			}
 		}
 		// the verdict travels with the slices: on several ranks it is max-reduced first (tiny), then every rank decides alike
 		u64 full = 0;
@@ -763,6 +786,7 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 		full = c->h_ctr[CTR_TABLE_FULL];
 		c->st.hash_build_attempts = (uint32_t)attempt + 1;
 		if (!full) break;
+		if (full >= 2 && !k1_direct) { k1_direct = true; continue; }         // a key queue overflowed: same geometry, direct kernel
 		if (c->nparts > (u32)c->nranks) sub_limit = std::max<u64>(1, c->nparts / c->nranks / 2);
 		else buckets_per_read *= 2;
 	}

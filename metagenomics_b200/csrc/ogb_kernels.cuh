@@ -486,6 +486,92 @@ __global__ void k_hash_insert(ReadStore R, Table T)
 	}
 }
 
+// K1 through partition queues (index beyond L2): random read-modify-writes into hundreds of MB run at the DRAM row /
+// translation rate, so the keys are first hashed and SCATTERED into one queue per hash partition (k_key_part: a block
+// counts its tile's keys per partition in shared memory, reserves queue space with one atomic per partition and tile,
+// then writes bucket / fingerprint / value records), and the queues are inserted one partition at a time
+// (k_insert_parts): while a partition is being filled its <= 48 MB of buckets are L2-resident.
+struct KeyQueue {
+	u32 *b, *f, *v;             // nparts regions of cap records: home bucket, fingerprint, value id<<2|o
+	u64 *cursor;                // records appended per partition (may exceed cap: the build falls back to k_hash_insert)
+	u64 cap;
+	u32 nparts;                 // partitions of the index; this rank fills [first, first + count)
+	u32 first, count;
+};
+#define OGB_KPT 4               // keys per thread and tile in k_key_part
+__global__ void __launch_bounds__(256, 6) k_key_part(ReadStore R, Table T, KeyQueue Q)
+{
+	__shared__ u32 s_cnt[64];
+	__shared__ u64 s_base[64];
+	const u64 total = (u64)R.n * 4;
+	const u32 tile_keys = 256 * OGB_KPT;
+	const u64 tiles = (total + tile_keys - 1) / tile_keys;
+	for (u64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+		if (threadIdx.x < Q.nparts) s_cnt[threadIdx.x] = 0;
+		__syncthreads();
+		u32 eb[OGB_KPT], ef[OGB_KPT], ev[OGB_KPT], ep[OGB_KPT];
+		#pragma unroll
+		for (int r = 0; r < OGB_KPT; r++) {
+			const u64 x = tile * tile_keys + r * 256 + threadIdx.x;
+			ep[r] = 0xFFFFFFFFu; eb[r] = ef[r] = ev[r] = 0;
+			if (x >= total) continue;
+			const u32 idx = (u32)(x >> 2), o = (u32)(x & 3);
+			u64 off; u32 L;
+			read_geom(R, idx, off, L);
+			const u64 *w = R.words + off + (o >> 1) * padded_words(L);
+			const u32 p = (o & 1) ? L - T.h : 0;
+			u32 lead;
+			const u64 hash = key_hash<LdGlobal>(w, p, T.h, lead);
+			u32 part;
+			eb[r] = bucket_of(hash, lead, T, part);
+			if (T.nparts > T.sub && part / T.sub != T.my_rank) continue;          // another rank builds that partition
+			ef[r] = hash_fp(hash); ev[r] = ((idx + 1) << 2) | o;
+			ep[r] = (part << 16) | atomicAdd(&s_cnt[part], 1u);
+		}
+		__syncthreads();
+		if (threadIdx.x < Q.nparts) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(Q.cursor + threadIdx.x, (u64)s_cnt[threadIdx.x]) : 0;
+		__syncthreads();
+		#pragma unroll
+		for (int r = 0; r < OGB_KPT; r++)
+			if (ep[r] != 0xFFFFFFFFu) {
+				const u32 part = ep[r] >> 16;
+				const u64 at = s_base[part] + (ep[r] & 0xFFFFu);
+				if (at < Q.cap) { const u64 i = (part - Q.first) * Q.cap + at; Q.b[i] = eb[r]; Q.f[i] = ef[r]; Q.v[i] = ev[r]; }
+			}
+		__syncthreads();
+	}
+}
+// One insert: claims the first empty slot along the probe sequence (see k_hash_insert)
+__device__ __forceinline__ void insert_record(const Table &T, u32 b, u32 fp, u32 val)
+{
+	const u32 part = b / T.part_buckets, pend = (part + 1) * T.part_buckets;
+	for (u32 steps = 0;; steps++) {
+		if (steps >= T.part_buckets) { atomicMax(T.ctr + CTR_TABLE_FULL, 1ull); return; }
+		u32 *w = T.slots + (u64)b * OGB_BWORDS;
+		u32 cur[12];
+		#pragma unroll
+		for (int q = 0; q < 12; q += 4)
+			asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(cur[q]), "=r"(cur[q + 1]), "=r"(cur[q + 2]), "=r"(cur[q + 3]) : "l"(w + 4 + q) : "memory");
+		int s = OGB_SLOTS;
+		#pragma unroll
+		for (int q = OGB_SLOTS - 1; q >= 0; q--) s = cur[1 + q] == 0 ? q : s;
+		bool done = false;
+		for (; s < OGB_SLOTS && !done; s++) done = atomicCAS(w + 5 + s, 0u, val) == 0;
+		if (done) { atomicOr(w + ((s - 1) >> 1), fp << (16 * ((s - 1) & 1))); if (T.summary) atomicOr(T.summary + b, summary_bits(fp)); return; }
+		if (T.summary) atomicOr(T.summary + b, OGB_SPILLED);
+		b = next_bucket(b, pend, T);
+	}
+}
+__global__ void __launch_bounds__(256, 6) k_insert_parts(Table T, KeyQueue Q)
+{
+	const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (u64)gridDim.x * blockDim.x;
+	for (u32 part = Q.first; part < Q.first + Q.count; part++) {
+		const u64 n = min(Q.cursor[part], Q.cap), base = (part - Q.first) * Q.cap;
+		if (Q.cursor[part] > Q.cap && g == 0) atomicMax(T.ctr + CTR_TABLE_FULL, 2ull);   // a queue dropped keys (skewed leads): the host rebuilds with the direct kernel
+		for (u64 i = g; i < n; i += nthreads) insert_record(T, Q.b[base + i], Q.f[base + i], Q.v[base + i]);
+	}
+}
+
 // One bucket = 64 bytes = two 256-bit non-allocating loads. w[0..4] fingerprint pairs, w[5..14] values.
 __device__ __forceinline__ void load_bucket(const u32 *__restrict__ slots, u32 b, u32 (&w)[OGB_BWORDS])
 {

@@ -1,10 +1,10 @@
 """CPU, world_size 2 over gloo: the host-side logic of the N > 1 path -- shard bounds, the unique-id
 broadcast, max-over-ranks timing -- and a Python model of the sharded algorithm exactly as the CUDA/NCCL
-path runs it (csrc/ogb_device.cu ogb_build_graph, csrc/ogb_kernels.cuh k_pack_adj / k_mark / k_keep /
-k_emit): every rank keeps its own lists UNSORTED (discovery order), packs them to (dst, strand) entries
-that are allgathered (C1), walks the pivots of its own nodes by repeated minimum of (offset, dst, orient,
-slot) among the in-play entries, records where the scan of a pivot met the twin entry, publishes one
-ELIM bit per packed entry (C2), keeps an edge iff the bit at the recorded twin position is clear (K6),
+path runs it (csrc/ogb_device.cu ogb_build_graph, csrc/ogb_kernels.cuh k_rows_finish / k_mark_fast / k_mark_any /
+k_keep / k_emit): every rank keeps its own lists UNSORTED (discovery order), packs them to (dst, strand) entries
+-- the adjacency rows -- that reach every rank (C1), walks the pivots of its own nodes by repeated minimum of
+(offset, dst, orient, slot) among the in-play entries, records where the scan of a pivot met the twin entry, publishes
+one ELIM bit per row entry (C2), keeps an edge iff the bit at the recorded twin position is clear (K6),
 and the sorted survivors of all shards are allgathered (C3). The result must be the oracle's
 post-reduction graph; the model also checks the claim K6 relies on: every edge a node keeps was one of
 its pivots, so its twin position is always known."""
@@ -75,7 +75,7 @@ def worker(rank, world, port, q):
             own = {}
             for s_, d, off, o in mine[rng.permutation(len(mine))].tolist():   # ... in discovery order, i.e. unsorted
                 own.setdefault(s_, []).append((off, d, o))
-            mypacked = {u: [(d << 1) | ((o >> 1) & 1) for _, d, o in g] for u, g in own.items()}   # k_pack_adj
+            mypacked = {u: [(d << 1) | ((o >> 1) & 1) for _, d, o in g] for u, g in own.items()}   # k_rows_finish
             gathered = [None] * world
             dist.all_gather_object(gathered, mypacked)                 # C1: packed lists (+ node records)
             packed = {}
