@@ -262,3 +262,91 @@ bool OverlapGraph::isEdgePresent(UINT64 source, UINT64 destination)
 		if (graph->at(source)->at(i)->getDestinationRead()->getReadNumber() == destination) return true;
 	return false;
 }
+
+// OverlapGraph.cpp:1219-1259 -- the reference's .unitig format: one decimal number per line; for every edge with
+// source < destination (a self-edge: one of the twin pair), source, destination, orientation, overlapOffset, the number
+// of reads inside the edge and, for each of them, read number, overlap offset, orientation. The reference picks the
+// self-edge twin with the lower heap address; here it is the one that sits first in the node's list (the same edge for a
+// graph that came out of readGraphFromFile, where the forward edge is created and inserted first).
+bool OverlapGraph::saveGraphToFile(string fileName)
+{
+	FILE *f = fopen(fileName.c_str(), "w");
+	if (!f) throw OgbFailure(OGB_E_IO, "Unable to open file: " + fileName);
+	for (UINT64 i = 1; i < graph->size(); i++) {
+		vector<Edge *> *l = graph->at(i);
+		for (UINT64 j = 0; j < l->size(); j++) {
+			Edge *e = l->at(j);
+			const UINT64 source = e->getSourceRead()->getReadNumber(), destination = e->getDestinationRead()->getReadNumber();
+			bool write = source < destination;
+			if (source == destination) {											// the twin is in the same list: keep the first of the two
+				write = true;
+				for (UINT64 k = 0; k < j; k++) if (l->at(k) == e->getReverseEdge()) { write = false; break; }
+			}
+			if (!write) continue;
+			fprintf(f, "%llu\n%llu\n%llu\n%llu\n%llu\n", (unsigned long long)source, (unsigned long long)destination, (unsigned long long)e->getOrientation(),
+			        (unsigned long long)e->getOverlapOffset(), (unsigned long long)e->getListOfReads()->size());
+			for (UINT64 k = 0; k < e->getListOfReads()->size(); k++)
+				fprintf(f, "%llu\n%llu\n%llu\n", (unsigned long long)e->getListOfReads()->at(k), (unsigned long long)e->getListOfOverlapOffsets()->at(k),
+				        (unsigned long long)e->getListOfOrientations()->at(k));
+		}
+	}
+	if (fclose(f) != 0) throw OgbFailure(OGB_E_IO, "Unable to write file: " + fileName);
+	return true;
+}
+
+// OverlapGraph.cpp:1267-1367 -- rebuilds the graph (every edge together with its reverse edge, whose read list, offsets and
+// orientations are derived as in :1321-1341) from a .unitig file; the Dataset must be the one the file was written for.
+bool OverlapGraph::readGraphFromFile(string fileName)
+{
+	FILE *f = fopen(fileName.c_str(), "r");
+	if (!f) throw OgbFailure(OGB_E_IO, "Unable to open file: " + fileName);
+	vector<UINT64> list;
+	unsigned long long t;
+	while (fscanf(f, "%llu", &t) == 1) list.push_back(t);
+	fclose(f);
+	for (size_t i = 0; i < graph->size(); i++) {
+		for (size_t j = 0; j < graph->at(i)->size(); j++) delete graph->at(i)->at(j);
+		delete graph->at(i);
+	}
+	graph->clear();
+	numberOfNodes = numberOfEdges = 0;
+	for (UINT64 i = 0; i <= dataSet->getNumberOfUniqueReads(); i++) graph->push_back(new vector<Edge *>);
+	for (size_t i = 0; i + 5 <= list.size();) {
+		const UINT64 source = list[i++], destination = list[i++], orientation = list[i++], overlapOffset = list[i++], nReads = list[i++];
+		if (i + 3 * nReads > list.size()) throw OgbFailure(OGB_E_IO, "Truncated unitig file: " + fileName);
+		vector<UINT64> *listReads = new vector<UINT64>;
+		vector<UINT16> *listOverlapOffsets = new vector<UINT16>;
+		vector<UINT8> *listOrientations = new vector<UINT8>;
+		UINT64 length = 0;
+		for (UINT64 j = 0; j < 3 * nReads; j += 3) {
+			listReads->push_back(list[i + j]);
+			listOverlapOffsets->push_back((UINT16)list[i + j + 1]);
+			listOrientations->push_back((UINT8)list[i + j + 2]);
+			length += list[i + j + 1];
+		}
+		Read *read1 = dataSet->getReadFromID(source), *read2 = dataSet->getReadFromID(destination);
+		vector<UINT64> *listReadsReverse = new vector<UINT64>;
+		vector<UINT16> *listOverlapOffsetsReverse = new vector<UINT16>;
+		vector<UINT8> *listOrientationsReverse = new vector<UINT8>;
+		const UINT64 size = listReads->size();
+		for (UINT64 j = 0; j < size; j++) {											// :1321-1341
+			listReadsReverse->push_back(listReads->at(size - j - 1));
+			UINT64 length1, overlapOffsetForward;
+			if (j == 0) { length1 = read2->getReadLength(); overlapOffsetForward = overlapOffset - length; }
+			else { length1 = dataSet->getReadFromID(listReads->at(size - j))->getReadLength(); overlapOffsetForward = listOverlapOffsets->at(size - j); }
+			const UINT64 length2 = dataSet->getReadFromID(listReads->at(size - j - 1))->getReadLength();
+			listOverlapOffsetsReverse->push_back((UINT16)(length1 + overlapOffsetForward - length2));
+			listOrientationsReverse->push_back(!(listOrientations->at(size - j - 1)));
+		}
+		const UINT64 reverseOverlapOffset = overlapOffset + read2->getReadLength() - read1->getReadLength();
+		Edge *edgeForward = new Edge(), *edgeReverse = new Edge();
+		edgeForward->makeEdge(read1, read2, orientation, overlapOffset, listReads, listOverlapOffsets, listOrientations);
+		edgeReverse->makeEdge(read2, read1, twinEdgeOrientation((UINT8)orientation), reverseOverlapOffset, listReadsReverse, listOverlapOffsetsReverse, listOrientationsReverse);
+		edgeForward->setReverseEdge(edgeReverse);
+		edgeReverse->setReverseEdge(edgeForward);
+		insertEdge(edgeForward);
+		insertEdge(edgeReverse);
+		i += nReads * 3;
+	}
+	return true;
+}

@@ -54,6 +54,8 @@ class OverlapGraph
 		UINT64 getNumberOfNodes(void) { return numberOfNodes; }
 		bool setDataset(Dataset *dataset) { dataSet = dataset; dataset->readMatePairsFromFile(); return true; }
 		void sortEdges();
+		bool saveGraphToFile(string fileName);			// OverlapGraph.cpp:1219-1259: the reference's .unitig text format
+		bool readGraphFromFile(string fileName);		// OverlapGraph.cpp:1267-1367 (resume path, main.cpp:36-42)
 		Edge *findEdge(UINT64 source, UINT64 destination);
 		bool isEdgePresent(UINT64 source, UINT64 destination);
 		vector<vector<Edge *> *> *getGraph(void) { return graph; }

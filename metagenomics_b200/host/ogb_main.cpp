@@ -61,7 +61,8 @@ int main(int argc, char **argv)
 	UINT64 minimumOverlapLength = 0;
 	vector<string> pairedEndFileNames, singleEndFileNames;
 	string allFileName = "";
-	const char *dumpPath = NULL;
+	const char *dumpPath = NULL, *resavePath = NULL;
+	bool startFromUnitigGraph = false;
 	for (int i = 1; i < argc; i++) {
 		string a = argv[i];
 		if ((a == "-pe" || a == "-se") && i + 1 < argc) {
@@ -70,8 +71,10 @@ int main(int argc, char **argv)
 		} else if (a == "-f" && i + 1 < argc) allFileName = argv[++i];
 		else if (a == "-l" && i + 1 < argc) minimumOverlapLength = atoi(argv[++i]);
 		else if (a == "--dump" && i + 1 < argc) dumpPath = argv[++i];
+		else if (a == "-s") startFromUnitigGraph = true;												// main.cpp: resume from <prefix>.unitig
+		else if (a == "--resave" && i + 1 < argc) resavePath = argv[++i];
 		else {
-			cerr << "Usage: ogb_overlap -l minOverlap [-pe n files...] [-se n files...] [-f prefix] [--dump file]" << endl;
+			cerr << "Usage: ogb_overlap -l minOverlap [-pe n files...] [-se n files...] [-f prefix] [-s] [--dump file] [--resave file]" << endl;
 			return a == "-h" || a == "--help" ? 0 : 1;
 		}
 	}
@@ -82,12 +85,26 @@ int main(int argc, char **argv)
 	try {
 		Dataset *dataSet = new Dataset(pairedEndFileNames, singleEndFileNames, minimumOverlapLength);	// main.cpp:33
 		OverlapGraph *overlapGraph;
+		if (startFromUnitigGraph) {																		// main.cpp:36-42: no GPU involved
+			overlapGraph = new OverlapGraph();
+			overlapGraph->setDataset(dataSet);
+			overlapGraph->readGraphFromFile(allFileName + ".unitig");
+			overlapGraph->sortEdges();
+			if (dumpPath) dumpGraph(dumpPath, dataSet, overlapGraph, minimumOverlapLength);
+			if (resavePath) overlapGraph->saveGraphToFile(resavePath);
+			cout << "reads: " << dataSet->getNumberOfReads() << " unique: " << dataSet->getNumberOfUniqueReads()
+			     << " nodes: " << overlapGraph->getNumberOfNodes() << " edges: " << overlapGraph->getNumberOfEdges() << " (from " << allFileName << ".unitig)" << endl;
+			delete dataSet;
+			delete overlapGraph;
+			return 0;
+		}
 		HashTable *hashTable = new HashTable();															// main.cpp:45
 		hashTable->insertDataset(dataSet, minimumOverlapLength);										// main.cpp:46
 		overlapGraph = new OverlapGraph(hashTable); //hashTable deleted by this function after building the graph (main.cpp:47)
 		if (allFileName != "") dataSet->saveReads(allFileName + "_sortedReads.fasta");					// main.cpp:48
 		if (dumpPath) dumpGraph(dumpPath, dataSet, overlapGraph, minimumOverlapLength);
 		overlapGraph->sortEdges();																		// main.cpp:49
+		if (allFileName != "") overlapGraph->saveGraphToFile(allFileName + ".unitig");					// main.cpp:50 (the graph at :210; the reference contracts first)
 		const ogb_stats &st = overlapGraph->getBuildStats();
 		cout << "reads: " << dataSet->getNumberOfReads() << " unique: " << dataSet->getNumberOfUniqueReads()
 		     << " nodes: " << overlapGraph->getNumberOfNodes() << " edges: " << overlapGraph->getNumberOfEdges()

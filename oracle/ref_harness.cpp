@@ -66,6 +66,7 @@ static Dataset *g_dataset = 0;
 static const char *g_dump_path = 0;
 static const char *g_json_path = 0;
 static const char *g_dump2_path = 0;
+static const char *g_unitig_path = 0;	// --unitig: the reference's own saveGraphToFile after sortEdges (main.cpp:49-50), needs --dump2
 static double g_t_dataset = 0, g_t_insert = 0, g_t_build0 = 0, g_t_mate = 0;
 static streambuf *g_cout_buf = 0;
 
@@ -199,6 +200,7 @@ int main(int argc, char **argv)
 		else if (a == "--dump" && i + 1 < argc) g_dump_path = argv[++i];
 		else if (a == "--json" && i + 1 < argc) g_json_path = argv[++i];
 		else if (a == "--dump2" && i + 1 < argc) g_dump2_path = argv[++i];
+		else if (a == "--unitig" && i + 1 < argc) g_unitig_path = argv[++i];
 		else if (a == "--table" && i + 1 < argc) table_path = argv[++i];
 		else if (a == "--verbose") quiet = false;
 		else { fprintf(stderr, "usage: ref_overlap -l minOverlap [-se f]... [-pe f]... [--dump f] [--json f] [--table f] [--verbose]\n"); return 2; }
@@ -226,7 +228,11 @@ int main(int argc, char **argv)
 	if (quiet) sink.str("");
 	g_t_build0 = now_s();
 	new (mem) OverlapGraph(hashTable);
-	if (g_dump2_path) { dump_contracted(g_graph, dataSet, g_dump2_path); fflush(0); _exit(0); }
+	if (g_dump2_path) {
+		dump_contracted(g_graph, dataSet, g_dump2_path);
+		if (g_unitig_path) { g_graph->sortEdges(); g_graph->saveGraphToFile(g_unitig_path); }	// main.cpp:49-50, the unmodified writer
+		fflush(0); _exit(0);
+	}
 	fprintf(stderr, "ref_harness: constructor returned without reaching OverlapGraph.cpp:210\n");
 	return 5;
 }

@@ -39,7 +39,8 @@ def main():
         with tempfile.TemporaryDirectory() as td:
             fa = os.path.join(td, "in.fa")
             synth.write_fasta(fa, cfg["bases"], cfg["offsets"])
-            d, t, _ = run_reference([fa], cfg["min_overlap"], paired=cfg["paired"], contracted=True)
+            # the .unitig file the unmodified reference writes for this graph (small text; fixture of the reader / writer test)
+            d, t, _ = run_reference([fa], cfg["min_overlap"], paired=cfg["paired"], contracted=True, unitig=os.path.join(HERE, name + ".unitig"))
         out = os.path.join(HERE, name + ".npz")
         np.savez_compressed(out, bases=cfg["bases"], offsets=cfg["offsets"], min_overlap=np.int64(cfg["min_overlap"]),
                             edges=d["edges"], sup=d["reads"]["sup"], freq=d["reads"]["freq"], len=d["reads"]["len"],

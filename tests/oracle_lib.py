@@ -253,14 +253,17 @@ def sort_tuples(e):
     return np.ascontiguousarray(e[idx])
 
 
-def run_reference(fasta_paths, min_overlap, paired=False, want_table=False, binary=REF_BIN, timeout=3600, contracted=False):
+def run_reference(fasta_paths, min_overlap, paired=False, want_table=False, binary=REF_BIN, timeout=3600, contracted=False, unitig=None):
     """Runs the unmodified reference on FASTA files; returns (dump dict, timing json, table lists|None). contracted=True:
-    the dump dict gets a "contracted" entry (read_dump2: the graph after OverlapGraph.cpp:211-215)."""
+    the dump dict gets a "contracted" entry (read_dump2: the graph after OverlapGraph.cpp:211-215). unitig=path (with
+    contracted): the reference's own sortEdges + saveGraphToFile (main.cpp:49-50) writes its .unitig file there."""
     with tempfile.TemporaryDirectory() as td:
         dump, js, tab = os.path.join(td, "d.bin"), os.path.join(td, "t.json"), os.path.join(td, "tab.bin")
         cmd = [binary, "-l", str(min_overlap), "--dump", dump, "--json", js]
         if contracted:
             cmd += ["--dump2", os.path.join(td, "d2.bin")]
+            if unitig:
+                cmd += ["--unitig", os.path.abspath(unitig)]
         for p in fasta_paths:
             cmd += ["-pe" if paired else "-se", p]
         if want_table:

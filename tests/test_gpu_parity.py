@@ -172,8 +172,14 @@ def test_cpp_dropin_matches_reference_dump(ctx, tmp_path):
         fa, dump = str(tmp_path / (name + ".fa")), str(tmp_path / (name + ".bin"))
         synth.write_fasta(fa, z["bases"], z["offsets"])
         kind = "-pe" if name == "config2_small" else "-se"          # paired input also fills the mate-pair lists
-        subprocess.run([exe, "-l", str(int(z["min_overlap"])), kind, "1", fa, "--dump", dump], check=True, timeout=120)
+        prefix = str(tmp_path / name)
+        subprocess.run([exe, "-l", str(int(z["min_overlap"])), kind, "1", fa, "-f", prefix, "--dump", dump], check=True, timeout=120)
         d = read_dump(dump)
+        # main.cpp:48-50: the sorted reads and the .unitig file of the GPU-built graph; the resume path (main.cpp:36-42) reads it back
+        assert os.path.exists(prefix + "_sortedReads.fasta") and os.path.exists(prefix + ".unitig")
+        subprocess.run([exe, "-l", str(int(z["min_overlap"])), kind, "1", fa, "-f", prefix, "-s", "--dump", dump + "2"], check=True, timeout=120)
+        d2 = read_dump(dump + "2")
+        assert np.array_equal(d2["edges"], d["edges"]) and d2["number_of_nodes"] == d["number_of_nodes"] and d2["number_of_edges"] == d["number_of_edges"], name
         assert d["n"] == len(z["sup"]) and np.array_equal(d["reads"]["fnv"], z["fnv"]), name
         assert np.array_equal(d["reads"]["sup"], z["sup"]) and np.array_equal(d["reads"]["freq"], z["freq"]), name
         assert np.array_equal(d["edges"], z["edges"]), name
