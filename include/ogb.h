@@ -219,6 +219,15 @@ int ogb_mark_contained(ogb_context *ctx);
 /* Read::superReadID (Read.h:50) for ids 0..n (entry 0 unused, = 0). */
 int ogb_super_read_ids(ogb_context *ctx, uint64_t *out, uint64_t cap);
 
+/* Dataset::storeMatePairInformation (Dataset.cpp:208-310; called at OverlapGraph.cpp:142, after markContainedReads) for a
+ * batch: sequence i = bases[offsets[i] .. offsets[i+1]) as sequenced (ASCII; sequences 2k and 2k+1 are mates). For each:
+ * the filter of :268 (length > minOverlap, testRead), getReadFromString (:421-455) as one verified index lookup, the
+ * redirection of a contained read to its super read (:280-284) and the orientation bit -- 1 iff the sequence is a substring
+ * of that read's forward strand (:291-292). out_id[i] = ID of the read that stands for sequence i (0: filtered out; a pair
+ * is good when both are non-zero), out_orient[i] = the bit. Sequences longer than 960 bases are reported as 0 (host loop). */
+int ogb_mate_lookup(ogb_context *ctx, const char *bases, const uint64_t *offsets, uint64_t n_seqs, uint32_t min_overlap,
+                    uint32_t *out_id, uint8_t *out_orient);
+
 /* OverlapGraph::buildOverlapGraphFromHashTable (OverlapGraph.cpp:107-210, up to `delete hashTable`)
  * minus markContainedReads/readMatePairsFromFile: insertAllEdgesOfRead + checkOverlap (K3, :354-383,
  * :529-565), the per-node order by offset (:563, produced on the fly by K5/K6), markTransitiveEdges (K5, :574-615),

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "ogb_hash_table_size": (C.c_uint64, [_vp]),
     "ogb_mark_contained": (C.c_int, [_vp]),
     "ogb_super_read_ids": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "ogb_mate_lookup": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, _vp, _vp]),
     "ogb_build_graph": (C.c_int, [_vp, C.c_int]),
     "ogb_graph_edge_count": (C.c_int, [_vp, C.c_int, _u64p]),
     "ogb_graph_edges": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),

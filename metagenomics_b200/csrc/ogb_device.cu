@@ -1496,3 +1496,37 @@ extern "C" int ogb_gather_ceiling(ogb_context *c, size_t buffer_bytes, uint32_t 
 	*gb_per_s = (double)grid * 256 * per_thread * gather_bytes / (best * 1e-3) / 1e9;
 	return OGB_OK;
 }
+
+// Dataset::storeMatePairInformation for a batch of sequences (see k_mate_lookup). Needs the reads, the index and the
+// containment marks of the same context (the reference calls it at OverlapGraph.cpp:142, between markContainedReads and the
+// edge build, for that reason).
+extern "C" int ogb_mate_lookup(ogb_context *c, const char *bases, const uint64_t *offsets, uint64_t n_seqs, uint32_t min_overlap, uint32_t *out_id, uint8_t *out_orient)
+{
+	if (!c || (n_seqs && (!bases || !offsets || !out_id || !out_orient))) { ogb_set_error("ogb_mate_lookup: NULL argument"); return OGB_E_ARG; }
+	if (!c->have_table || !c->contain_done) { ogb_set_error("ogb_mate_lookup: build the hash table and mark contained reads first"); return OGB_E_STATE; }
+	if (n_seqs == 0) return OGB_OK;
+	CUDA_TRY(cudaSetDevice(c->device));
+	const u64 nbytes = offsets[n_seqs] - offsets[0];
+	Tmp<char> d_bases;
+	Tmp<u64> d_offs;
+	Tmp<u32> d_id;
+	Tmp<unsigned char> d_or;
+	std::vector<u64> rel;
+	const u64 *offs_src = (const u64 *)offsets;
+	if (offsets[0] != 0) { rel.resize(n_seqs + 1); for (u64 i = 0; i <= n_seqs; i++) rel[i] = offsets[i] - offsets[0]; offs_src = rel.data(); }
+	auto run = [&]() -> int {
+		OGB_TRY(d_bases.ensure(nbytes + 1, c->stream)); OGB_TRY(d_offs.ensure(n_seqs + 1, c->stream));
+		OGB_TRY(d_id.ensure(n_seqs, c->stream)); OGB_TRY(d_or.ensure(n_seqs, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(d_bases.p, bases + offsets[0], nbytes, cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(d_offs.p, offs_src, (n_seqs + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+		k_mate_lookup<<<(unsigned)((n_seqs + 127) / 128), 128, 0, c->stream>>>(c->rs(), c->tb(), c->any_contained ? c->sup.p : nullptr, d_bases.p, d_offs.p, n_seqs, min_overlap, d_id.p, d_or.p);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpyAsync(out_id, d_id.p, n_seqs * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(out_orient, d_or.p, n_seqs, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		return OGB_OK;
+	};
+	const int rc = run();
+	d_bases.release(); d_offs.release(); d_id.release(); d_or.release();
+	return rc;
+}

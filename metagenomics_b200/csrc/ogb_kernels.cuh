@@ -1919,3 +1919,81 @@ __global__ void __launch_bounds__(256) k_edge_checksum(const ogb_edge *__restric
 	for (int d = 16; d > 0; d >>= 1) { x_or ^= __shfl_down_sync(0xFFFFFFFFu, x_or, d); x_sum += __shfl_down_sync(0xFFFFFFFFu, x_sum, d); }
 	if ((threadIdx.x & 31) == 0) { atomicXor(out, x_or); atomicAdd(out + 1, x_sum); }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Mate-pair pass (Dataset::storeMatePairInformation, Dataset.cpp:208-310), batched: one thread per sequence as
+// sequenced. Filter like Dataset.cpp:268 (length > minOverlap, ACGT only, testRead :398-413), canonical strand,
+// getReadFromString (:421-455) as ONE index lookup -- the read's own prefix key is in the table with o = 0 -- verified
+// against the whole stored strand, redirection to the super read (:280-284; sup[] still holds K2's packed maximum),
+// and the orientation bit: 1 iff the sequence is a substring of that read's forward strand (:291-292).
+// out_id = ID of the read that stands for the sequence (0: filtered out or not in the data set), out_or = the bit.
+// ------------------------------------------------------------------------------------------------
+#define OGB_MATE_MAXW 32         // sequences up to 1024 bases on this path (longer ones: the caller's host loop)
+__global__ void __launch_bounds__(128) k_mate_lookup(ReadStore R, Table T, const u64 *__restrict__ sup, const char *__restrict__ bases, const u64 *__restrict__ offsets,
+                                                     u64 n_seqs, u32 min_overlap, u32 *__restrict__ out_id, unsigned char *__restrict__ out_or)
+{
+	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_seqs) return;
+	out_id[i] = 0; out_or[i] = 0;
+	const char *s = bases + offsets[i];
+	const u32 L = (u32)(offsets[i + 1] - offsets[i]);
+	if (L <= min_overlap || L > 32 * (OGB_MATE_MAXW - 2)) return;               // :268 (strict); overlong: left to the host
+	u64 fw[OGB_MATE_MAXW], rc[OGB_MATE_MAXW];
+	const u32 nw = (L + 31) >> 5;
+	for (u32 k = 0; k < nw + 2; k++) { fw[k] = 0; rc[k] = 0; }
+	u32 cnt[4] = {0, 0, 0, 0};
+	for (u32 p = 0; p < L; p++) {
+		const u32 ch = (u32)(unsigned char)s[p] & ~0x20u;                       // toupper (:262-266)
+		if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') return;           // testRead :403-406
+		u32 c = (ch >> 1) & 3;
+		cnt[c]++;
+		c ^= c >> 1;                                                          // A C G T -> 0 1 2 3
+		fw[p >> 5] |= (u64)c << (62 - 2 * (p & 31));
+		const u32 q = L - 1 - p;
+		rc[q >> 5] |= (u64)(3 - c) << (62 - 2 * (q & 31));
+	}
+	const u32 thr = (u32)(L * .8);                                            // :409
+	if (cnt[0] >= thr || cnt[1] >= thr || cnt[2] >= thr || cnt[3] >= thr) return;
+	int pick = 0;                                                             // canonical strand = min(read, reverse complement) (:161-164)
+	for (u32 k = 0; k < nw && pick == 0; k++) if (fw[k] != rc[k]) pick = fw[k] < rc[k] ? 1 : 2;
+	const u64 *can = pick == 2 ? rc : fw;
+	// getReadFromString: the canonical strand's prefix key, o = 0 entries, whole-strand compare
+	u32 lead;
+	const u64 hash = key_hash<LdShared>(can, 0, T.h, lead);
+	u32 part;
+	u32 b = bucket_of(hash, lead, T, part);
+	const u32 fp = hash_fp(hash), pend = (part + 1) * T.part_buckets;
+	u32 found = 0;
+	for (u32 steps = 0; steps < T.part_buckets && !found; steps++) {
+		u32 w[OGB_BWORDS];
+		load_bucket(T.slots, b, w);
+		for (u32 mm = match_bucket(w, fp); mm && !found; mm &= mm - 1) {
+			const u32 val = bucket_value(w, __ffs(mm) - 1);
+			if (val == 0 || (val & 3) != 0) continue;
+			const u32 ri = (val >> 2) - 1;
+			u64 off; u32 L2;
+			read_geom(R, ri, off, L2);
+			if (L2 != L) continue;
+			const u64 *t = R.words + off;
+			bool same = true;
+			for (u32 k = 0; k < nw && same; k++) same = __ldg(t + k) == can[k];  // both zero-padded behind the last base
+			if (same) found = ri + 1;
+		}
+		if (w[5 + OGB_SLOTS - 1] == 0) break;
+		b = next_bucket(b, pend, T);
+	}
+	if (!found) return;
+	u32 id = found;
+	bool forward = pick != 2;                                                 // the stored strand IS the sequence (or the sequence is its own reverse complement)
+	const u64 sv = sup ? sup[found - 1] : 0;
+	if (sv) {                                                                 // contained: the super read stands for it (:280-284)
+		id = (0xFFFFFFFFu - (u32)(sv & 0xFFFFFFFFull)) + 1;
+		u64 off; u32 LR;
+		read_geom(R, id - 1, off, LR);
+		const u64 *t = R.words + off;                                         // forward strand of the super read
+		forward = false;
+		for (u32 sh = 0; sh + L <= LR && !forward; sh++) forward = region_equal<LdGlobal, LdShared>(t, sh, fw, 0, L);   // string::find (:291-292)
+	}
+	out_id[i] = id;
+	out_or[i] = forward ? 1 : 0;
+}

@@ -4,13 +4,13 @@
 
 
 Dataset::Dataset(void)
-	: numberOfReads(0), numberOfUniqueReads(0), minimumOverlapLength(0), reads(new vector<Read *>), store(NULL),
+	: numberOfReads(0), numberOfUniqueReads(0), minimumOverlapLength(0), reads(new vector<Read *>), store(NULL), mateContext(NULL),
 	  shortestReadLength(0XFFFFFFFFFFFFFFFF), longestReadLength(0)
 {
 }
 
 Dataset::Dataset(vector<string> pairedEndFileNames, vector<string> singleEndFileNames, UINT64 minOverlap)
-	: numberOfReads(0), numberOfUniqueReads(0), minimumOverlapLength(minOverlap), reads(new vector<Read *>), store(NULL),
+	: numberOfReads(0), numberOfUniqueReads(0), minimumOverlapLength(minOverlap), reads(new vector<Read *>), store(NULL), mateContext(NULL),
 	  shortestReadLength(0XFFFFFFFFFFFFFFFF), longestReadLength(0)
 {
 	pairedEndDatasetFileNames = pairedEndFileNames;
@@ -24,7 +24,7 @@ Dataset::Dataset(vector<string> pairedEndFileNames, vector<string> singleEndFile
 }
 
 Dataset::Dataset(const char *bases, const uint64_t *offsets, UINT64 n, UINT64 minOverlap)
-	: numberOfReads(0), numberOfUniqueReads(0), minimumOverlapLength(minOverlap), reads(new vector<Read *>), store(NULL),
+	: numberOfReads(0), numberOfUniqueReads(0), minimumOverlapLength(minOverlap), reads(new vector<Read *>), store(NULL), mateContext(NULL),
 	  shortestReadLength(0XFFFFFFFFFFFFFFFF), longestReadLength(0)
 {
 	ogbCheck(ogb_dataset_create(&store), "Dataset");
@@ -130,7 +130,28 @@ bool Dataset::storeMatePairInformation(string fileName, UINT64 minOverlap, UINT6
 		}
 	}
 	ogb_dataset *probe = store;
+	// Device path: every sequence of the file in one ogb_mate_lookup call (filter, getReadFromString, super-read redirection and
+	// orientation bit on the GPU); the host only appends to the lists, in file order like the reference.
+	vector<uint32_t> ids;
+	vector<uint8_t> orients;
+	if (mateContext != NULL && !seqs.empty()) {
+		vector<uint64_t> offs(seqs.size() + 1, 0);
+		for (size_t i = 0; i < seqs.size(); i++) offs[i + 1] = offs[i] + seqs[i].size();
+		string flat;
+		flat.reserve(offs.back());
+		for (size_t i = 0; i < seqs.size(); i++) flat += seqs[i];
+		ids.assign(seqs.size(), 0); orients.assign(seqs.size(), 0);
+		ogbCheck(ogb_mate_lookup(mateContext, flat.data(), offs.data(), seqs.size(), (uint32_t)minOverlap, ids.data(), orients.data()), "storeMatePairInformation");
+	}
 	for (size_t p = 0; p + 1 < seqs.size(); p += 2) {
+		if (!ids.empty() && seqs[p].size() <= 960 && seqs[p + 1].size() <= 960) {
+			if (ids[p] == 0 || ids[p + 1] == 0) continue;							// one mate failed the quality filter
+			Read *r1 = reads->at(ids[p] - 1), *r2 = reads->at(ids[p + 1] - 1);
+			const UINT16 o1 = orients[p], o2 = orients[p + 1];
+			r1->addMatePair(r2, o1 * 2 + o2, datasetNumber);
+			r2->addMatePair(r1, o1 + o2 * 2, datasetNumber);
+			continue;
+		}
 		string a = seqs[p], b = seqs[p + 1];
 		for (size_t k = 0; k < a.size(); k++) a[k] = (char)toupper(a[k]);
 		for (size_t k = 0; k < b.size(); k++) b[k] = (char)toupper(b[k]);

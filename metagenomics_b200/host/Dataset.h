@@ -15,6 +15,7 @@ class Dataset
 		UINT64 minimumOverlapLength;
 		vector<Read *> *reads;
 		ogb_dataset *store;								// packed, sorted, unique reads (host)
+		ogb_context *mateContext;						// device context for the batched mate-pair pass (NULL: host loop)
 		bool storeMatePairInformation(string fileName, UINT64 minOverlap, UINT64 datasetNumber);
 		void adopt(UINT64 minOverlap);					// finalize `store` and create the Read objects
 
@@ -35,6 +36,9 @@ class Dataset
 		Read *getReadFromString(const string &read);
 		Read *getReadFromID(UINT64 ID);
 		void readMatePairsFromFile(void);
+		// Not in the reference: the mate-pair pass (storeMatePairInformation) runs as one batched lookup on this context's GPU,
+		// which must hold this data set's reads, index and containment marks (OverlapGraph sets it before OverlapGraph.cpp:142).
+		void setMatePairContext(ogb_context *ctx) { mateContext = ctx; }
 		void saveReads(string fileName);
 
 		string readString(UINT64 ID, int strand) const;	// used by Read

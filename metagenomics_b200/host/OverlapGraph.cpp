@@ -1,6 +1,7 @@
 // OverlapGraph.cpp -- see OverlapGraph.h.
 #include "OverlapGraph.h"
 
+#include <cstdlib>
 #include <cstring>
 
 static bool byDestination(Edge *a, Edge *b) { return a->getDestinationRead()->getReadNumber() < b->getDestinationRead()->getReadNumber(); }
@@ -54,7 +55,9 @@ bool OverlapGraph::buildOverlapGraphFromHashTable(HashTable *ht)
 	for (UINT64 i = 0; i <= dataSet->getNumberOfUniqueReads(); i++) graph->push_back(new vector<Edge *>);	// :131-138
 
 	markContainedReads();													// :140
+	if (getenv("OGB_MATES_ON_HOST") == NULL) dataSet->setMatePairContext(ht->getContext());	// batched lookup on the GPU (ogb_mate_lookup)
 	dataSet->readMatePairsFromFile();										// :142 (needs superReadID)
+	dataSet->setMatePairContext(NULL);
 
 	ogb_context *ctx = ht->getContext();
 	ogbCheck(ogb_build_graph(ctx, 0), "OverlapGraph::buildOverlapGraphFromHashTable");	// :144-204

@@ -56,12 +56,31 @@ static void dumpGraph(const char *path, Dataset *dataSet, OverlapGraph *overlapG
 	fclose(f);
 }
 
+// the format of oracle/ref_harness.cpp --mates: every read's mate-pair list, in list order
+static void dumpMates(const char *path, Dataset *dataSet)
+{
+	FILE *f = fopen(path, "wb");
+	if (!f) throw OgbFailure(OGB_E_IO, string("cannot open ") + path);
+	unsigned long long magic = 0x31534554414d474fULL, n = dataSet->getNumberOfUniqueReads();
+	fwrite(&magic, 8, 1, f); fwrite(&n, 8, 1, f);
+	for (UINT64 i = 1; i <= n; i++) {
+		vector<MPlist> *l = dataSet->getReadFromID(i)->getMatePairList();
+		unsigned int c = (unsigned int)l->size();
+		fwrite(&c, 4, 1, f);
+		for (size_t k = 0; k < l->size(); k++) {
+			unsigned int v[3] = {(unsigned int)l->at(k).matePairID, (unsigned int)l->at(k).matePairOrientation, (unsigned int)l->at(k).datasetNumber};
+			fwrite(v, 4, 3, f);
+		}
+	}
+	fclose(f);
+}
+
 int main(int argc, char **argv)
 {
 	UINT64 minimumOverlapLength = 0;
 	vector<string> pairedEndFileNames, singleEndFileNames;
 	string allFileName = "";
-	const char *dumpPath = NULL, *resavePath = NULL;
+	const char *dumpPath = NULL, *resavePath = NULL, *matesPath = NULL;
 	bool startFromUnitigGraph = false;
 	for (int i = 1; i < argc; i++) {
 		string a = argv[i];
@@ -73,6 +92,7 @@ int main(int argc, char **argv)
 		else if (a == "--dump" && i + 1 < argc) dumpPath = argv[++i];
 		else if (a == "-s") startFromUnitigGraph = true;												// main.cpp: resume from <prefix>.unitig
 		else if (a == "--resave" && i + 1 < argc) resavePath = argv[++i];
+		else if (a == "--mates" && i + 1 < argc) matesPath = argv[++i];
 		else {
 			cerr << "Usage: ogb_overlap -l minOverlap [-pe n files...] [-se n files...] [-f prefix] [-s] [--dump file] [--resave file]" << endl;
 			return a == "-h" || a == "--help" ? 0 : 1;
@@ -103,6 +123,7 @@ int main(int argc, char **argv)
 		overlapGraph = new OverlapGraph(hashTable); //hashTable deleted by this function after building the graph (main.cpp:47)
 		if (allFileName != "") dataSet->saveReads(allFileName + "_sortedReads.fasta");					// main.cpp:48
 		if (dumpPath) dumpGraph(dumpPath, dataSet, overlapGraph, minimumOverlapLength);
+		if (matesPath) dumpMates(matesPath, dataSet);
 		overlapGraph->sortEdges();																		// main.cpp:49
 		if (allFileName != "") overlapGraph->saveGraphToFile(allFileName + ".unitig");					// main.cpp:50 (the graph at :210; the reference contracts first)
 		const ogb_stats &st = overlapGraph->getBuildStats();

@@ -66,6 +66,7 @@ static Dataset *g_dataset = 0;
 static const char *g_dump_path = 0;
 static const char *g_json_path = 0;
 static const char *g_dump2_path = 0;
+static const char *g_mates_path = 0;	// --mates: every read's mate-pair list as left by Dataset::storeMatePairInformation (OverlapGraph.cpp:142)
 static const char *g_unitig_path = 0;	// --unitig: the reference's own saveGraphToFile after sortEdges (main.cpp:49-50), needs --dump2
 static double g_t_dataset = 0, g_t_insert = 0, g_t_build0 = 0, g_t_mate = 0;
 static streambuf *g_cout_buf = 0;
@@ -121,6 +122,23 @@ extern "C" void __wrap__ZN9HashTableD1Ev(HashTable *self)
 				put<unsigned int>(f, (unsigned int)e->getOverlapOffset());
 				put<unsigned int>(f, (unsigned int)e->getOrientation());
 			}
+		fclose(f);
+	}
+	if (g_mates_path) {
+		// u64 magic, u64 n, then per read: u32 count, count x (u32 matePairID, u32 matePairOrientation, u32 datasetNumber), in list order
+		FILE *f = fopen(g_mates_path, "wb");
+		if (!f) { fprintf(stderr, "ref_harness: cannot open %s\n", g_mates_path); _exit(3); }
+		put<unsigned long long>(f, 0x31534554414d474fULL);
+		put<unsigned long long>(f, n);
+		for (UINT64 i = 1; i <= n; i++) {
+			vector<MPlist> *l = ds->getReadFromID(i)->getMatePairList();
+			put<unsigned int>(f, (unsigned int)l->size());
+			for (size_t k = 0; k < l->size(); k++) {
+				put<unsigned int>(f, (unsigned int)l->at(k).matePairID);
+				put<unsigned int>(f, (unsigned int)l->at(k).matePairOrientation);
+				put<unsigned int>(f, (unsigned int)l->at(k).datasetNumber);
+			}
+		}
 		fclose(f);
 	}
 	if (g_cout_buf && !g_dump2_path) cout.rdbuf(g_cout_buf);
@@ -201,6 +219,7 @@ int main(int argc, char **argv)
 		else if (a == "--json" && i + 1 < argc) g_json_path = argv[++i];
 		else if (a == "--dump2" && i + 1 < argc) g_dump2_path = argv[++i];
 		else if (a == "--unitig" && i + 1 < argc) g_unitig_path = argv[++i];
+		else if (a == "--mates" && i + 1 < argc) g_mates_path = argv[++i];
 		else if (a == "--table" && i + 1 < argc) table_path = argv[++i];
 		else if (a == "--verbose") quiet = false;
 		else { fprintf(stderr, "usage: ref_overlap -l minOverlap [-se f]... [-pe f]... [--dump f] [--json f] [--table f] [--verbose]\n"); return 2; }

@@ -112,6 +112,14 @@ def primer_prefixed(seed=17, min_overlap=30, n_reads=24000):
     return from_strings(reads, min_overlap, "primer_prefixed")
 
 
+def paired_mixed(seed=18, min_overlap=30):
+    """Paired reads of mixed lengths at high coverage: most reads are contained in longer ones, so the mate-pair pass has to
+    redirect mates to super reads and decide their orientation by substring search (Dataset.cpp:280-292)."""
+    g = [synth.genome(seed, 5000)]
+    b, o = synth.sample_reads(seed, g, 3000, 50, 110, paired=True, insert_mean=260.0, insert_sd=25.0)
+    return dict(name="paired_mixed", bases=b, offsets=o, min_overlap=min_overlap, paired=True)
+
+
 def small_configs():
     return [
         synth.config(1, scale=0.3),

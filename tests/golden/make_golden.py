@@ -34,20 +34,22 @@ def main():
         "repeats": datasets.repeats(),
         "palindromes": datasets.palindromes(),
         "filtered": datasets.filtered(),
+        "paired_mixed": datasets.paired_mixed(),
     }
     for name, cfg in sets.items():
         with tempfile.TemporaryDirectory() as td:
             fa = os.path.join(td, "in.fa")
             synth.write_fasta(fa, cfg["bases"], cfg["offsets"])
             # the .unitig file the unmodified reference writes for this graph (small text; fixture of the reader / writer test)
-            d, t, _ = run_reference([fa], cfg["min_overlap"], paired=cfg["paired"], contracted=True, unitig=os.path.join(HERE, name + ".unitig"))
+            d, t, _ = run_reference([fa], cfg["min_overlap"], paired=cfg["paired"], contracted=True, unitig=os.path.join(HERE, name + ".unitig"), mates=True)
         out = os.path.join(HERE, name + ".npz")
         np.savez_compressed(out, bases=cfg["bases"], offsets=cfg["offsets"], min_overlap=np.int64(cfg["min_overlap"]),
                             edges=d["edges"], sup=d["reads"]["sup"], freq=d["reads"]["freq"], len=d["reads"]["len"],
                             fnv=d["reads"]["fnv"], number_of_nodes=np.int64(d["number_of_nodes"]),
                             number_of_edges=np.int64(d["number_of_edges"]), n_good=np.int64(t["n_reads"]),
                             c_edges=d["contracted"]["edges"], c_list_start=d["contracted"]["list_start"], c_lists=d["contracted"]["lists"],
-                            c_number_of_nodes=np.int64(d["contracted"]["number_of_nodes"]), c_number_of_edges=np.int64(d["contracted"]["number_of_edges"]))
+                            c_number_of_nodes=np.int64(d["contracted"]["number_of_nodes"]), c_number_of_edges=np.int64(d["contracted"]["number_of_edges"]),
+                            mate_start=d["mates"][0], mate_lists=d["mates"][1], paired=np.int64(1 if cfg["paired"] else 0))
         print(f"{name}: {d['n']} unique reads, {len(d['edges'])} edges, {len(d['contracted']['edges'])} after contraction -> {os.path.getsize(out)} bytes")
 
 

@@ -223,6 +223,24 @@ def read_dump(path):
                 edges=sort_tuples(edges))
 
 
+def read_mates(path):
+    """Mate-pair lists dumped by oracle/ref_harness.cpp --mates or metagenomics_b200/host/ogb_overlap --mates:
+    (start (n+1,) int64, triples (m,3) uint32 [matePairID, matePairOrientation, datasetNumber]) in list order, reads 1..n."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    hdr = np.frombuffer(raw[:16].tobytes(), dtype="<u8")
+    assert hdr[0] == 0x31534554414d474f, "bad mates magic"
+    n = int(hdr[1])
+    w = np.frombuffer(raw[16:].tobytes(), dtype="<u4")
+    start = np.zeros(n + 1, np.int64)
+    out, p = [], 0
+    for i in range(n):
+        c = int(w[p]); p += 1
+        out.append(w[p:p + 3 * c].reshape(c, 3)); p += 3 * c
+        start[i + 1] = start[i] + c
+    assert p == len(w)
+    return start, (np.concatenate(out) if out else np.zeros((0, 3), np.uint32))
+
+
 def read_dump2(path):
     """Second dump of oracle/ref_harness.cpp (--dump2): the reference graph after its contractCompositePaths /
     removeDeadEndNodes fix-point (OverlapGraph.cpp:211-215). Returns edges (n,5) [src,dst,orient,nlist,offset] (uint64),
@@ -253,7 +271,7 @@ def sort_tuples(e):
     return np.ascontiguousarray(e[idx])
 
 
-def run_reference(fasta_paths, min_overlap, paired=False, want_table=False, binary=REF_BIN, timeout=3600, contracted=False, unitig=None):
+def run_reference(fasta_paths, min_overlap, paired=False, want_table=False, binary=REF_BIN, timeout=3600, contracted=False, unitig=None, mates=False):
     """Runs the unmodified reference on FASTA files; returns (dump dict, timing json, table lists|None). contracted=True:
     the dump dict gets a "contracted" entry (read_dump2: the graph after OverlapGraph.cpp:211-215). unitig=path (with
     contracted): the reference's own sortEdges + saveGraphToFile (main.cpp:49-50) writes its .unitig file there."""
@@ -268,8 +286,12 @@ def run_reference(fasta_paths, min_overlap, paired=False, want_table=False, bina
             cmd += ["-pe" if paired else "-se", p]
         if want_table:
             cmd += ["--table", tab]
+        if mates:
+            cmd += ["--mates", os.path.join(td, "m.bin")]
         subprocess.run(cmd, check=True, timeout=timeout, cwd=td)
         d = read_dump(dump)
+        if mates:
+            d["mates"] = read_mates(os.path.join(td, "m.bin"))
         if contracted:
             d["contracted"] = read_dump2(os.path.join(td, "d2.bin"))
         with open(js) as f:

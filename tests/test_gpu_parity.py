@@ -270,3 +270,45 @@ def test_skewed_keys_fill_a_hash_partition(ctx, monkeypatch):
     keys = [orc.get_read(i)[:h] for i in range(1, orc.n + 1, orc.n // 50)] + ["GATTACAGGCCTTAGCAATC" + "A" * (h - 20)]
     for k, g in zip(keys, ht.getListsOfReads(keys)):
         assert np.array_equal(g, orc.lookup(k)), k
+
+
+@pytest.mark.parametrize("name", ["config2_small", "paired_mixed"])
+@pytest.mark.parametrize("where", ["device", "host"])
+def test_mate_pair_lists_match_reference(ctx, tmp_path, name, where):
+    """Dataset::storeMatePairInformation (Dataset.cpp:208-310, called at OverlapGraph.cpp:142): every read's mate-pair list --
+    mate ID after super-read redirection, the two orientation bits, data set number, in list order -- as the UNMODIFIED reference
+    leaves it (fixture dumped through oracle/ref_harness.cpp --mates). `device`: the batched lookup kernel (ogb_mate_lookup:
+    filter, getReadFromString as one verified index lookup, redirection, substring test); `host`: the per-pair loop of the
+    drop-in class. paired_mixed has 81 % contained reads, i.e. most mates are redirected."""
+    import subprocess
+    from metagenomics_b200 import synth
+    from oracle_lib import read_dump, read_mates
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "metagenomics_b200", "host", "ogb_overlap")
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    fa, dump, mates = str(tmp_path / "in.fa"), str(tmp_path / "d.bin"), str(tmp_path / "m.bin")
+    synth.write_fasta(fa, z["bases"], z["offsets"])
+    env = dict(os.environ, **({"OGB_MATES_ON_HOST": "1"} if where == "host" else {}))
+    subprocess.run([exe, "-l", str(int(z["min_overlap"])), "-pe", "1", fa, "--dump", dump, "--mates", mates], check=True, timeout=120, env=env)
+    d = read_dump(dump)
+    assert np.array_equal(d["reads"]["sup"], z["sup"]) and np.array_equal(d["edges"], z["edges"])
+    start, lists = read_mates(mates)
+    assert np.array_equal(start, z["mate_start"]) and np.array_equal(lists, z["mate_lists"])
+    assert len(lists) > 1000
+
+
+def test_mate_lookup_entry_point(ctx):
+    """ogb_mate_lookup directly: bad sequences (N, low complexity, too short) give 0; a sequence and its reverse complement find
+    the same read with opposite orientation bits."""
+    import ctypes as C
+    from metagenomics_b200._lib import check, lib
+    cfg = datasets.small_configs()[1]
+    ds, ht, og = build_gpu(ctx, cfg, keep_pre=False)
+    first = ds.getReadFromID(7)
+    seqs = [first, datasets.rc(first), "N" + first[1:], "A" * len(first), first[:cfg["min_overlap"]]]
+    flat = np.frombuffer("".join(seqs).encode(), dtype=np.uint8)
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(s) for s in seqs])
+    ids, ori = np.zeros(len(seqs), np.uint32), np.zeros(len(seqs), np.uint8)
+    check(lib().ogb_mate_lookup(ctx._h, flat.ctypes.data, offs.ctypes.data, len(seqs), cfg["min_overlap"], ids.ctypes.data, ori.ctypes.data))
+    assert ids.tolist() == [7, 7, 0, 0, 0]
+    assert ori[0] == 1 and (ori[1] == 0 or first == datasets.rc(first))
