@@ -56,7 +56,7 @@ static void dumpGraph(const char *path, Dataset *dataSet, OverlapGraph *overlapG
 	fclose(f);
 }
 
-// the format of oracle/ref_harness.cpp --mates: every read's mate-pair list, in list order
+// every read's mate-pair list, in list order: u64 magic, u64 n, per read u32 count + count x (u32 matePairID, u32 orientation, u32 dataset) -- the format the parity tests read
 static void dumpMates(const char *path, Dataset *dataSet)
 {
 	FILE *f = fopen(path, "wb");
