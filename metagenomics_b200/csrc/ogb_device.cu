@@ -154,6 +154,11 @@ struct ogb_context {
 	Pool<u32> rows, more, more_own, ebits, hrows;   // more_own: this rank's overflow entries (one rank: the whole of `more`); hrows: heavy-row records
 	u64 more_stride = 0, more_cap = 0;
 	cudaStream_t xs = nullptr;       // several ranks: the rows of a finished chunk travel here while the next chunk is probed
+	// ... as copy-engine pushes into the peers' row arrays (mapped with CUDA IPC): no SM of either side is involved, unlike NCCL
+	// send / receive kernels, which would compete with the probe for the SMs during the whole of K3
+	u32 *peer_rows[64] = {};
+	const void *rows_shared = nullptr;   // the allocation the peers currently have mapped
+	bool rows_dma = false;
 	cudaEvent_t ev_rows[2] = {}, ev_xs = nullptr;
 	// scan staging: candidate queue of one chunk, spill list of heavy nodes
 	Pool<u32> cand_q, fill, ov_q;    // cand_q / cand_v hold two ping-pong queues of cand_cap entries
@@ -327,6 +332,14 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	cudaStreamSynchronize(c->stream);
 	if (c->stream2) cudaStreamSynchronize(c->stream2);
 	if (c->xs) cudaStreamSynchronize(c->xs);
+	{
+		bool mapped = false;
+		for (int p = 0; p < 64; p++) if (c->peer_rows[p]) { cudaIpcCloseMemHandle(c->peer_rows[p]); c->peer_rows[p] = nullptr; mapped = true; }
+		if (mapped && c->comm) {                                                // nobody frees an array a peer still has mapped
+			g_nccl.AllReduce(c->d_xchg + XCHG_SCRATCH + 6, c->d_xchg + XCHG_SCRATCH + 6, 1, NCCL_UINT64, 2 /*ncclMax*/, c->comm, c->stream);
+			cudaStreamSynchronize(c->stream);
+		}
+	}
 	if (c->comm) g_nccl.CommDestroy(c->comm);
 	c->words.release(); c->meta.release(); c->stage_bytes.release(); c->stage_offs.release(); c->stage_lens.release();
 	c->slots.release(); c->summary.release(); c->sup.release(); c->contained.release(); c->pos.release();
@@ -711,7 +724,7 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 	// One hash partition per rank: every rank inserts only the keys of its own partition (a slice of
 	// nb/G buckets that stays L2- and TLB-friendly), then the slices are allgathered. A replicated build
 	// of the whole table cost 3.8 ms at 8 ranks (TLB-bound inserts into 664 MB).
-	// Partitions per rank: 1 while a rank's slice fits L2; beyond that the slice is cut into pieces of <= 48 MB, the
+	// Partitions per rank: 1 up to 192 MB of slice; beyond that the slice is cut into pieces of <= 160 MB, the
 	// unit the partitioned probe (k_window_part / k_probe_parts) works through at a time.
 	// A partition is chosen by the key's first 16 bases alone and linear probing wraps inside it, so a skewed read set can
 	// fill one up (K1 raises CTR_TABLE_FULL after a whole lap; a key queue that overflows raises it to 2): the build is then repeated with half as many partitions per
@@ -723,7 +736,9 @@ extern "C" int ogb_hash_build(ogb_context *c, uint32_t min_overlap)
 		nb = std::max<u64>((u64)(buckets_per_read * c->n) + 1, 512);
 		{
 			const u64 slice_bytes = nb * OGB_BWORDS * sizeof(u32) / c->nranks;
-			u64 sub = slice_bytes > (96ull << 20) ? (slice_bytes + (48ull << 20) - 1) / (48ull << 20) : 1;
+			// measured (profiles/r2/exp_partitions.txt): the optimum is ~140-180 MB per partition at 0.55, 0.6 and 1.1 GB of index --
+			// what a partition buys is translation reach and full queue tiles, not L2 residency (46 MB partitions: +7 %)
+			u64 sub = slice_bytes > (192ull << 20) ? (slice_bytes + (160ull << 20) - 1) / (160ull << 20) : 1;
 			const char *e = getenv("OGB_SUB_PARTITIONS");                        // experiment knob
 			if (e && atoi(e) >= 1) sub = (u64)atoi(e);
 			sub = std::max<u64>(1, std::min<u64>(sub, sub_limit));
@@ -877,6 +892,55 @@ static ScanArgs scan_args(ogb_context *c, u32 lo, u32 hi)
 
 static GraphView graph_view(const ogb_context *c, u32 lo);
 
+// (Re)maps every rank's row array into the others (collective; the array is (re)allocated at the same moment on all ranks
+// because its size depends on the read count and the rank count only). On any failure the exchange falls back to NCCL.
+static int share_rows(ogb_context *c)
+{
+	const int G = c->nranks;
+	if (G == 1 || c->rows_shared == (const void *)c->rows.p) return OGB_OK;
+	for (int p = 0; p < G; p++) if (c->peer_rows[p]) { cudaIpcCloseMemHandle(c->peer_rows[p]); c->peer_rows[p] = nullptr; }
+	c->rows_dma = false;
+	c->rows_shared = c->rows.p;
+	const char *e = getenv("OGB_ROWS_NCCL");
+	u64 ok = !(e && atoi(e) != 0);
+	cudaIpcMemHandle_t mine;
+	memset(&mine, 0, sizeof mine);
+	if (ok && cudaIpcGetMemHandle(&mine, c->rows.p) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+	// handles (64 bytes) + an "I can" flag travel through a small device buffer
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	const size_t rec = 72;
+	Pool<unsigned char> buf;
+	OGB_TRY(buf.ensure(rec * G));
+	std::vector<unsigned char> host(rec * G, 0);
+	memcpy(host.data() + rec * c->rank, &mine, 64);
+	memcpy(host.data() + rec * c->rank + 64, &ok, 8);
+	CUDA_TRY(cudaMemcpyAsync(buf.p + rec * c->rank, host.data() + rec * c->rank, rec, cudaMemcpyHostToDevice, c->stream));
+	NCCL_TRY(g_nccl.AllGather(buf.p + rec * c->rank, buf.p, rec, NCCL_UINT8, c->comm, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(host.data(), buf.p, rec * G, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	buf.release();
+	bool all = true;
+	for (int p = 0; p < G; p++) { u64 f; memcpy(&f, host.data() + rec * p + 64, 8); all = all && f != 0; }
+	u64 opened = all;
+	if (all)
+		for (int p = 0; p < G && opened; p++) {
+			if (p == c->rank) continue;
+			cudaIpcMemHandle_t h;
+			memcpy(&h, host.data() + rec * p, 64);
+			void *ptr = nullptr;
+			if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; break; }
+			c->peer_rows[p] = (u32 *)ptr;
+		}
+	// everybody must have every mapping, or nobody pushes (a rank that pushes while its peer expects an NCCL receive would hang it)
+	CUDA_TRY(cudaMemcpyAsync(c->d_xchg + XCHG_SCRATCH + 6, &opened, sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+	NCCL_TRY(g_nccl.AllReduce(c->d_xchg + XCHG_SCRATCH + 6, c->d_xchg + XCHG_SCRATCH + 6, 1, NCCL_UINT64, 3 /*ncclMin*/, c->comm, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(&opened, c->d_xchg + XCHG_SCRATCH + 6, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->rows_dma = opened != 0;
+	if (!c->rows_dma) for (int p = 0; p < G; p++) if (c->peer_rows[p]) { cudaIpcCloseMemHandle(c->peer_rows[p]); c->peer_rows[p] = nullptr; }
+	return OGB_OK;
+}
+
 // Several ranks: chunk `ci` of every rank's rows (reads [lo_r + ci*chunk, lo_r + (ci+1)*chunk) of rank r) goes to every other
 // rank, as one group of point-to-point sends / receives on the exchange stream. Every rank calls this for the same chunk
 // grid; a rank whose chunk is empty only receives.
@@ -890,6 +954,16 @@ static int exchange_chunk_rows(ogb_context *c, u32 ci, cudaStream_t st)
 	};
 	u64 ma, mb;
 	range(c->rank, ma, mb);
+	if (c->rows_dma) {
+		// push: one device-to-device copy per peer into its mapped row array (copy engines over NVLink). The peers learn that the
+		// rows have landed from the next collective on the main stream (the verdict allgather of ogb_build_graph), which every rank
+		// enqueues behind its own pushes.
+		for (int k = 1; k < G && mb > ma; k++) {
+			const int p = (c->rank + k) % G;
+			CUDA_TRY(cudaMemcpyAsync(c->peer_rows[p] + ma * OGB_ROW_W, c->rows.p + ma * OGB_ROW_W, (mb - ma) * OGB_ROW_W * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+		}
+		return OGB_OK;
+	}
 	NCCL_TRY(g_nccl.GroupStart());
 	for (int p = 0; p < G; p++) {
 		if (p == c->rank) continue;
@@ -1138,7 +1212,15 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	OGB_TRY(c->fill.ensure(per + 1));
 	OGB_TRY(c->surv.ensure((per + 1) * OGB_SURV));
 	OGB_TRY(c->cand.ensure((per + 1) * OGB_SURV * 2));
+	if (G > 1 && per * G * OGB_ROW_W + 64 > c->rows.cap && c->rows_shared) {
+		// the array is about to be reallocated (on every rank: same size rule): the peers' mappings of the old one go first
+		for (int p = 0; p < G; p++) if (c->peer_rows[p]) { cudaIpcCloseMemHandle(c->peer_rows[p]); c->peer_rows[p] = nullptr; }
+		c->rows_dma = false; c->rows_shared = nullptr;
+		NCCL_TRY(g_nccl.AllReduce(c->d_xchg + XCHG_SCRATCH + 6, c->d_xchg + XCHG_SCRATCH + 6, 1, NCCL_UINT64, 2 /*ncclMax*/, c->comm, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+	}
 	OGB_TRY(c->rows.ensure(per * G * OGB_ROW_W + 64));
+	OGB_TRY(share_rows(c));
 	if (c->ov_q.cap == 0) { OGB_TRY(c->ov_q.ensure(1 << 20)); OGB_TRY(c->ov_e.ensure(1 << 20)); }
 
 	// ---- K3 (probe + verify in chunks) into the slot regions and the adjacency rows; retried with larger pools when a
