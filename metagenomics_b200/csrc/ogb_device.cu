@@ -11,8 +11,6 @@
 #include "ogb_internal.h"
 #include "ogb_kernels.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -126,6 +124,8 @@ struct ogb_context {
 	cudaEvent_t ev[EV_COUNT] = {};
 	// packed reads
 	Pool<u64> words, meta;
+	Pool<u64> ds_words;              // tight packed words of the data set last finalized on this device (downloaded on demand)
+	ogb_dataset *pending_ds = nullptr;   // ... whose host copy of them is still outstanding
 	Pool<char> stage_bytes;          // upload staging (ASCII bases / tight words)
 	Pool<u64> stage_offs;
 	Pool<unsigned short> stage_lens;
@@ -227,6 +227,8 @@ static void kev_collect(ogb_context *c)
 	c->n_kev = 0;
 }
 #define KEV(cls, stream, launch) do { const int kev_i_ = kev_begin(c, cls, stream); launch; kev_end(c, kev_i_, stream); } while (0)
+
+static int fetch_words_cb(ogb_dataset *ds);
 
 static int ctr_zero(ogb_context *c) { CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, CTR_COUNT * sizeof(u64), c->stream)); return OGB_OK; }
 static int ctr_fetch(ogb_context *c)
@@ -330,6 +332,7 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
+	if (c->pending_ds) fetch_words_cb(c->pending_ds);                        // a data set still expects its packed words from this device
 	if (c->stream2) cudaStreamSynchronize(c->stream2);
 	if (c->xs) cudaStreamSynchronize(c->xs);
 	{
@@ -341,7 +344,7 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 		}
 	}
 	if (c->comm) g_nccl.CommDestroy(c->comm);
-	c->words.release(); c->meta.release(); c->stage_bytes.release(); c->stage_offs.release(); c->stage_lens.release();
+	c->words.release(); c->meta.release(); c->ds_words.release(); c->stage_bytes.release(); c->stage_offs.release(); c->stage_lens.release();
 	c->slots.release(); c->summary.release(); c->sup.release(); c->contained.release(); c->pos.release();
 	c->sums.release(); c->surv.release(); c->cand.release(); c->big.release(); c->cntc.release(); c->cnt.release();
 	c->scratch_keys.release(); c->fin.release(); c->pre.release(); c->flush.release(); c->fin_stage.release();
@@ -564,9 +567,45 @@ static int exclusive_scan(ogb_context *c, const u32 *cnt, u32 n, u64 *out, u64 *
 // ------------------------------------------------------------------------------------------------
 // Dataset stage on the device
 // ------------------------------------------------------------------------------------------------
+// the packed words a device finalize left in c->ds_words reach the host vectors now (ogb_dataset::fetch)
+static int fetch_words_cb(ogb_dataset *ds)
+{
+	ogb_context *c = (ogb_context *)ds->fetch_ctx;
+	ds->fetch = nullptr; ds->fetch_ctx = nullptr;
+	if (!c) return OGB_OK;
+	if (c->pending_ds == ds) c->pending_ds = nullptr;
+	CUDA_TRY(cudaSetDevice(c->device));
+	ds->words.resize(ds->pending_words);
+	if (ds->pending_words) {
+		CUDA_TRY(cudaMemcpyAsync(ds->words.data(), c->ds_words.p, ds->pending_words * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+	}
+	ds->pending_words = 0;
+	return OGB_OK;
+}
+void ogb_dataset_forget_context(ogb_dataset *ds)
+{
+	ogb_context *c = (ogb_context *)ds->fetch_ctx;
+	if (c && c->pending_ds == ds) c->pending_ds = nullptr;
+	ds->fetch = nullptr; ds->fetch_ctx = nullptr;
+}
+
+// One 8-bit pass of the radix sort over n (key, value) pairs: histogram, scan, stable scatter (ogb_kernels.cuh).
+static int radix_pass(ogb_context *c, const u64 *key, const u32 *val, u64 *key_out, u32 *val_out, u32 n, u32 shift, u32 *d_hist, u64 *d_offs)
+{
+	const u32 nblk = (n + OGB_RS_TILE - 1) / OGB_RS_TILE;
+	k_rs_hist<<<nblk, 256, 0, c->stream>>>(key, n, shift, d_hist, nblk);
+	OGB_TRY(exclusive_scan(c, d_hist, 256 * nblk, d_offs, c->d_tot));
+	k_rs_scatter<<<nblk, 256, 0, c->stream>>>(key, val, key_out, val_out, n, shift, d_offs, nblk);
+	CUDA_TRY(cudaGetLastError());
+	return OGB_OK;
+}
+
 extern "C" int ogb_dataset_finalize_device(ogb_dataset *ds, ogb_context *c, uint32_t min_overlap)
 {
-	if (!c) { ogb_set_error("ogb_dataset_finalize_device: NULL context"); return OGB_E_ARG; }
+	if (!c || !ds) { ogb_set_error("ogb_dataset_finalize_device: NULL argument"); return OGB_E_ARG; }
+	if (ds->finalized) { ogb_set_error("ogb_dataset_finalize: already finalized"); return OGB_E_STATE; }
+	if (min_overlap < 2) { ogb_set_error("ogb_dataset_finalize: minOverlap must be >= 2"); return OGB_E_ARG; }
 	const bool dbg = getenv("OGB_DBG_TIMING") != nullptr;
 	auto t_last = std::chrono::steady_clock::now();
 	auto lap = [&](const char *what) {
@@ -576,53 +615,80 @@ extern "C" int ogb_dataset_finalize_device(ogb_dataset *ds, ogb_context *c, uint
 		fprintf(stderr, "[finalize_device] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
 		t_last = now;
 	};
-	std::vector<uint64_t> idx;
-	OGB_TRY(ogb_dataset_filter(ds, min_overlap, idx));
-	lap("host filter");
-	const u64 n64 = idx.size();
-	if (n64 == 0) return OGB_OK;
-	if (n64 >= (1ull << 30)) { ogb_set_error("ogb_dataset_finalize_device: at most 2^30-1 reads per context"); return OGB_E_CAPACITY; }
+	const u64 n_raw64 = ds->raw_offs.size() - 1;
+	if (n_raw64 >= (1ull << 31)) { ogb_set_error("ogb_dataset_finalize_device: at most 2^31-1 raw reads per call"); return OGB_E_CAPACITY; }
 	CUDA_TRY(cudaSetDevice(c->device));
-	const u32 n = (u32)n64, W = (u32)((ds->longest + 31) / 32);
-	const uint64_t *ro = ds->raw_offs.data();
-	std::vector<u64> gstart(n);
-	std::vector<unsigned short> glen(n);
-	for (u32 g = 0; g < n; g++) { gstart[g] = ro[idx[g]]; glen[g] = (unsigned short)(ro[idx[g] + 1] - ro[idx[g]]); }
-	lap("host start/len arrays");
+	if (c->pending_ds) OGB_TRY(fetch_words_cb(c->pending_ds));               // the previous data set's words are about to be overwritten
+	const u32 n_raw = (u32)n_raw64;
+	ds->min_overlap = min_overlap;
 
-	Tmp<char> d_raw, d_tmp;
-	Tmp<u64> d_start, d_rows, d_key, d_key2, d_pos, d_woff, d_words;
+	Tmp<char> d_raw;
+	Tmp<u64> d_roffs, d_start, d_rows, d_key, d_key2, d_pos, d_woff, d_offs;
 	Tmp<unsigned short> d_len, d_ulen;
-	Tmp<u32> d_perm, d_perm2, d_head, d_usrc, d_unw, d_ustart, d_freq;
+	Tmp<u32> d_good, d_perm, d_perm2, d_head, d_usrc, d_unw, d_ustart, d_freq, d_hist;
 	auto release = [&]() {
-		d_raw.release(); d_tmp.release(); d_start.release(); d_rows.release(); d_key.release(); d_key2.release(); d_pos.release(); d_woff.release();
-		d_words.release(); d_len.release(); d_ulen.release(); d_perm.release(); d_perm2.release(); d_head.release(); d_usrc.release(); d_unw.release();
-		d_ustart.release(); d_freq.release();
+		d_raw.release(); d_roffs.release(); d_start.release(); d_rows.release(); d_key.release(); d_key2.release(); d_pos.release(); d_woff.release(); d_offs.release();
+		d_len.release(); d_ulen.release(); d_good.release(); d_perm.release(); d_perm2.release(); d_head.release(); d_usrc.release(); d_unw.release();
+		d_ustart.release(); d_freq.release(); d_hist.release();
 	};
+	// (pinning the raw bases with cudaHostRegister for the one upload was measured: 58 ms against 16 ms for the pageable copy of 150 MB)
 	auto run = [&]() -> int {
-		OGB_TRY(d_raw.ensure(ds->raw.size() + 1, c->stream)); OGB_TRY(d_start.ensure(n, c->stream)); OGB_TRY(d_len.ensure(n, c->stream)); OGB_TRY(d_rows.ensure((u64)n * W, c->stream));
-		OGB_TRY(d_key.ensure(n, c->stream)); OGB_TRY(d_key2.ensure(n, c->stream)); OGB_TRY(d_perm.ensure(n, c->stream)); OGB_TRY(d_perm2.ensure(n, c->stream)); OGB_TRY(d_head.ensure(n, c->stream)); OGB_TRY(d_pos.ensure((u64)n + 1, c->stream));
-		CUDA_TRY(cudaMemcpyAsync(d_raw.p, ds->raw.data(), ds->raw.size(), cudaMemcpyHostToDevice, c->stream));
-		CUDA_TRY(cudaMemcpyAsync(d_start.p, gstart.data(), n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-		CUDA_TRY(cudaMemcpyAsync(d_len.p, glen.data(), n * sizeof(unsigned short), cudaMemcpyHostToDevice, c->stream));
-		lap("alloc + H2D");
+		// ---- filter on the device (Dataset.cpp:155-158, :398-413): every raw read is uploaded, the good ones are compacted
+		OGB_TRY(d_raw.ensure(ds->raw.size() + 1, c->stream)); OGB_TRY(d_roffs.ensure((u64)n_raw + 1, c->stream));
+		OGB_TRY(d_good.ensure((u64)n_raw + 1, c->stream)); OGB_TRY(d_pos.ensure((u64)n_raw + 1, c->stream));
+		if (!ds->raw.empty()) CUDA_TRY(cudaMemcpyAsync(d_raw.p, ds->raw.data(), ds->raw.size(), cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(d_roffs.p, ds->raw_offs.data(), ((size_t)n_raw + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+		lap("alloc + H2D of the raw reads");
+		u64 stat[2] = {~0ull, 0};
+		CUDA_TRY(cudaMemcpyAsync(c->d_xchg + XCHG_SCRATCH, stat, sizeof stat, cudaMemcpyHostToDevice, c->stream));
+		if (n_raw) k_ds_filter<<<(n_raw + 127) / 128, 128, 0, c->stream>>>(d_raw.p, d_roffs.p, n_raw, min_overlap, d_good.p, c->d_xchg + XCHG_SCRATCH);
+		CUDA_TRY(cudaGetLastError());
+		OGB_TRY(exclusive_scan(c, d_good.p, n_raw, d_pos.p, c->d_tot));
+		u64 n64 = 0;
+		CUDA_TRY(cudaMemcpyAsync(&n64, c->d_tot, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(stat, c->d_xchg + XCHG_SCRATCH, sizeof stat, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		lap("filter kernel + scan");
+		ds->n_good = n64; ds->shortest = n64 ? stat[0] : ~0ULL; ds->longest = n64 ? stat[1] : 0;
+		ds->finalized = true;
+		ds->word_offs.assign(1, 0); ds->words.clear(); ds->lens.clear(); ds->freq.clear();
+		if (n64 == 0) return OGB_OK;
+		if (n64 >= (1ull << 30)) { ogb_set_error("ogb_dataset_finalize_device: at most 2^30-1 reads per context"); return OGB_E_CAPACITY; }
+		const u32 n = (u32)n64, W = (u32)((ds->longest + 31) / 32);
+		OGB_TRY(d_start.ensure(n, c->stream)); OGB_TRY(d_len.ensure(n, c->stream)); OGB_TRY(d_rows.ensure((u64)n * W, c->stream));
+		OGB_TRY(d_key.ensure(n, c->stream)); OGB_TRY(d_key2.ensure(n, c->stream)); OGB_TRY(d_perm.ensure(n, c->stream)); OGB_TRY(d_perm2.ensure(n, c->stream)); OGB_TRY(d_head.ensure(n, c->stream));
+		const u32 nblk = (n + OGB_RS_TILE - 1) / OGB_RS_TILE;
+		OGB_TRY(d_hist.ensure(256ull * nblk, c->stream)); OGB_TRY(d_offs.ensure(256ull * nblk + 1, c->stream));
+		k_ds_compact<<<(n_raw + 255) / 256, 256, 0, c->stream>>>(d_good.p, d_pos.p, d_roffs.p, n_raw, d_start.p, d_len.p);
 		const unsigned g256 = (n + 255) / 256;
 		k_ds_canon<<<(n + 127) / 128, 128, 0, c->stream>>>(d_raw.p, d_start.p, d_len.p, d_rows.p, n, W);
 		k_ds_iota<<<g256, 256, 0, c->stream>>>(d_perm.p, n);
 		CUDA_TRY(cudaGetLastError());
-		lap("canonical strand kernel");
-		// LSD radix sort: length first (least significant), then the words from last to first; every pass is stable
-		size_t tmp_bytes = 0;
-		CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key.p, d_key2.p, d_perm.p, d_perm2.p, (int)n, 0, 64, c->stream));
-		OGB_TRY(d_tmp.ensure(tmp_bytes + 16, c->stream));
+		lap("compact + canonical strand");
+		// ---- LSD radix sort: length first (least significant), then the words from last to first; every pass is stable.
+		// Bytes in which no two keys differ (zero padding, equal lengths, shared high bits) need no pass.
 		u32 *pa = d_perm.p, *pb = d_perm2.p;
+		u64 *ka = d_key.p, *kb = d_key2.p;
+		u32 passes = 0;
 		for (int word = (int)W; word >= 0; word--) {
-			k_ds_key<<<g256, 256, 0, c->stream>>>(d_rows.p, d_len.p, pa, d_key.p, n, W, (u32)word);
-			CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_key.p, d_key2.p, pa, pb, (int)n, 0, word == (int)W ? 16 : 64, c->stream));
-			std::swap(pa, pb);
+			k_ds_key<<<g256, 256, 0, c->stream>>>(d_rows.p, d_len.p, pa, ka, n, W, (u32)word);
+			u64 oa[2] = {0, ~0ull};
+			CUDA_TRY(cudaMemcpyAsync(c->d_xchg + XCHG_SCRATCH, oa, sizeof oa, cudaMemcpyHostToDevice, c->stream));
+			k_rs_orand<<<c->sm_count * 4, 256, 0, c->stream>>>(ka, n, c->d_xchg + XCHG_SCRATCH);
+			CUDA_TRY(cudaMemcpyAsync(oa, c->d_xchg + XCHG_SCRATCH, sizeof oa, cudaMemcpyDeviceToHost, c->stream));
+			CUDA_TRY(cudaStreamSynchronize(c->stream));
+			const u64 varying = oa[0] ^ oa[1];
+			for (u32 shift = 0; shift < 64; shift += 8) {
+				if (!((varying >> shift) & 255u)) continue;
+				OGB_TRY(radix_pass(c, ka, pa, kb, pb, n, shift, d_hist.p, d_offs.p));
+				std::swap(ka, kb); std::swap(pa, pb);
+				passes++;
+			}
 		}
+		if (dbg) fprintf(stderr, "[finalize_device] %u radix passes\n", passes);
 		lap("radix sort passes");
-		// dedupe: heads -> unique index, run lengths = frequencies
+		// ---- dedupe: heads -> unique index, run lengths = frequencies
+		OGB_TRY(d_pos.ensure((u64)n + 1, c->stream));
 		k_ds_heads<<<g256, 256, 0, c->stream>>>(d_rows.p, d_len.p, pa, d_head.p, n, W);
 		CUDA_TRY(cudaGetLastError());
 		OGB_TRY(exclusive_scan(c, d_head.p, n, d_pos.p, c->d_tot));
@@ -638,18 +704,19 @@ extern "C" int ogb_dataset_finalize_device(ogb_dataset *ds, ogb_context *c, uint
 		CUDA_TRY(cudaMemcpyAsync(&total_in, c->d_tot, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
 		CUDA_TRY(cudaMemcpyAsync(d_woff.p + nu, c->d_tot, sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
-		OGB_TRY(d_words.ensure(total_in + 4, c->stream));
-		k_ds_emit<<<(nu + 255) / 256, 256, 0, c->stream>>>(d_rows.p, d_usrc.p, d_unw.p, d_ustart.p, d_woff.p, d_freq.p, d_words.p, nu, n, W);
+		OGB_TRY(c->ds_words.ensure(total_in + 4));
+		k_ds_emit<<<(nu + 255) / 256, 256, 0, c->stream>>>(d_rows.p, d_usrc.p, d_unw.p, d_ustart.p, d_woff.p, d_freq.p, c->ds_words.p, nu, n, W);
 		CUDA_TRY(cudaGetLastError());
 		lap("dedupe + emit");
-		// the host keeps the same views as after ogb_dataset_finalize
-		ds->lens.resize(nu); ds->freq.resize(nu); ds->word_offs.resize((size_t)nu + 1); ds->words.resize(total_in);
+		// ---- host views: lengths, frequencies and word offsets now (small); the packed words stay on the device until somebody
+		// asks for them (ogb_dataset::fetch) -- they are two thirds of the bytes and the reads are already where the build needs them
+		ds->lens.resize(nu); ds->freq.resize(nu); ds->word_offs.resize((size_t)nu + 1);
 		CUDA_TRY(cudaMemcpyAsync(ds->lens.data(), d_ulen.p, nu * sizeof(unsigned short), cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaMemcpyAsync(ds->freq.data(), d_freq.p, nu * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaMemcpyAsync(ds->word_offs.data(), d_woff.p, ((size_t)nu + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-		CUDA_TRY(cudaMemcpyAsync(ds->words.data(), d_words.p, total_in * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		lap("D2H of the host views");
+		ds->pending_words = total_in; ds->fetch = fetch_words_cb; ds->fetch_ctx = c; c->pending_ds = ds;
+		lap("D2H of the small host views");
 		// ... and the read store of the context is filled straight from the device copy (K0), no second upload
 		u64 total_words = 0;
 		std::vector<u64> meta_host;
@@ -659,7 +726,7 @@ extern "C" int ogb_dataset_finalize_device(ogb_dataset *ds, ogb_context *c, uint
 		const u32 max_pw = ((c->max_len + 63) >> 6) << 1;
 		const u64 threads = (u64)nu * max_pw;
 		CUDA_TRY(cudaEventRecord(c->ev[EV_PACK0], c->stream));
-		k_pack_words<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(d_words.p, d_woff.p, d_ulen.p, c->words.p, c->uniform_len ? nullptr : c->meta.p,
+		k_pack_words<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->ds_words.p, d_woff.p, d_ulen.p, c->words.p, c->uniform_len ? nullptr : c->meta.p,
 		                                                                      nu, c->uniform_len, c->uniform_pw, max_pw);
 		CUDA_TRY(cudaGetLastError());
 		CUDA_TRY(cudaEventRecord(c->ev[EV_PACK1], c->stream));
@@ -671,6 +738,7 @@ extern "C" int ogb_dataset_finalize_device(ogb_dataset *ds, ogb_context *c, uint
 		return OGB_OK;
 	};
 	const int rc = run();
+	cudaStreamSynchronize(c->stream);
 	release();
 	lap("cudaFree");
 	if (rc != OGB_OK) {
@@ -678,6 +746,8 @@ extern "C" int ogb_dataset_finalize_device(ogb_dataset *ds, ogb_context *c, uint
 		ds->finalized = false;
 		ds->lens.clear(); ds->freq.clear(); ds->word_offs.clear(); ds->words.clear();
 		ds->resident_ctx = nullptr;
+		if (c->pending_ds == ds) c->pending_ds = nullptr;
+		ds->fetch = nullptr; ds->fetch_ctx = nullptr; ds->pending_words = 0;
 		return rc;
 	}
 	ds->raw.clear(); ds->raw.shrink_to_fit();

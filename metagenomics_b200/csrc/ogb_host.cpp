@@ -100,7 +100,7 @@ extern "C" int ogb_dataset_create(ogb_dataset **out)
 	return OGB_OK;
 }
 
-extern "C" void ogb_dataset_destroy(ogb_dataset *ds) { delete ds; }
+extern "C" void ogb_dataset_destroy(ogb_dataset *ds) { if (ds && ds->fetch) ogb_dataset_forget_context(ds); delete ds; }
 
 extern "C" int ogb_dataset_add_reads(ogb_dataset *ds, const char *bases, const uint64_t *offsets, uint64_t n)
 {
@@ -310,6 +310,7 @@ extern "C" uint32_t ogb_dataset_min_overlap(const ogb_dataset *ds) { return ds ?
 extern "C" const uint64_t *ogb_dataset_words(const ogb_dataset *ds, uint64_t *n_words)
 {
 	if (!ds) return nullptr;
+	if (ogb_dataset_ensure_words(ds) != OGB_OK) return nullptr;
 	if (n_words) *n_words = ds->words.size();
 	return ds->words.data();
 }
@@ -324,6 +325,7 @@ extern "C" int ogb_dataset_get_read(const ogb_dataset *ds, uint64_t id, int stra
 	uint32_t L = ds->lens[id - 1];
 	if (len) *len = L;
 	if (cap < L) { ogb_set_error("ogb_dataset_get_read: buffer too small"); return OGB_E_CAPACITY; }
+	if (int rc = ogb_dataset_ensure_words(ds)) return rc;
 	const uint64_t *w = &ds->words[ds->word_offs[id - 1]];
 	static const char B[4] = {'A', 'C', 'G', 'T'};
 	for (uint32_t i = 0; i < L; i++) {
@@ -338,6 +340,7 @@ extern "C" int ogb_dataset_find_read(const ogb_dataset *ds, const char *bases, u
 	if (!ds || !bases || !id) { ogb_set_error("ogb_dataset_find_read: NULL argument"); return OGB_E_ARG; }
 	*id = 0;
 	if (len == 0 || len > 65535 || ds->n_unique() == 0) return OGB_OK;
+	if (int rc = ogb_dataset_ensure_words(ds)) return rc;
 	uint32_t nw = (len + 31) / 32;
 	std::vector<uint64_t> fw(nw), rc(nw);
 	std::string up(bases, bases + len);

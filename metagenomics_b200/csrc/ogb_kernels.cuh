@@ -403,6 +403,101 @@ __global__ void __launch_bounds__(256) k_ds_iota(u32 *__restrict__ perm, u32 n)
 	if (i < n) perm[i] = i;
 }
 
+// Filter of Dataset::readDataset (Dataset.cpp:155-158, testRead :398-413) on the device: one thread per raw read. A read stays
+// iff its length is > minOverlap (and < 65536), it consists of ACGT only (either case) and no base reaches (UINT64)(len * .8)
+// occurrences. good[i] = 1/0; shortest / longest length of the good reads in stat[0] / stat[1].
+__global__ void __launch_bounds__(128) k_ds_filter(const char *__restrict__ raw, const u64 *__restrict__ offs, u32 n_raw, u32 min_overlap, u32 *__restrict__ good, u64 *stat)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_raw) return;
+	const u64 len = offs[i + 1] - offs[i];
+	const char *s = raw + offs[i];
+	bool ok = len > min_overlap && len < 65536;
+	u32 cnt[4] = {0, 0, 0, 0};
+	for (u32 k = 0; ok && k < (u32)len; k++) {
+		const u32 ch = (u32)(unsigned char)s[k] & ~0x20u;                       // toupper for letters (:155-156)
+		if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') ok = false;
+		else cnt[(ch >> 1) & 3]++;
+	}
+	if (ok) {
+		const u32 thr = (u32)((u32)len * .8);                                  // same double arithmetic as :409
+		if (cnt[0] >= thr || cnt[1] >= thr || cnt[2] >= thr || cnt[3] >= thr) ok = false;
+	}
+	good[i] = ok;
+	if (ok) { atomicMin(stat, len); atomicMax(stat + 1, len); }
+}
+// start / length of the good reads, in input order (pos = exclusive scan of good)
+__global__ void __launch_bounds__(256) k_ds_compact(const u32 *__restrict__ good, const u64 *__restrict__ pos, const u64 *__restrict__ offs, u32 n_raw,
+                                                    u64 *__restrict__ start, unsigned short *__restrict__ len)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_raw || !good[i]) return;
+	start[pos[i]] = offs[i];
+	len[pos[i]] = (unsigned short)(offs[i + 1] - offs[i]);
+}
+
+// ---- LSD radix sort of (64-bit key, 32-bit value) pairs, 8 bits per pass, stable; hand-written (round 1 used cub::DeviceRadixSort).
+// A pass = k_rs_hist (per-block digit histograms, laid out digit-major so that one exclusive scan over the whole array yields
+// every block's output offset per digit), the scan, k_rs_scatter. A block owns a tile of 2048 consecutive pairs and walks it
+// in 8 rounds of 256; inside a round a warp ranks its 32 pairs with __match_any_sync, and a 64 x 256 table of (round, warp)
+// counts in shared memory, prefix-summed per digit, orders the warps and rounds -- which keeps equal digits in input order.
+// k_rs_orand finds the bits in which the keys differ at all, so that passes over constant bytes (zero padding, equal lengths) are skipped.
+#define OGB_RS_TILE 2048
+__global__ void __launch_bounds__(256) k_rs_orand(const u64 *__restrict__ key, u32 n, u64 *out)   // out[0] |= keys, out[1] &= keys
+{
+	u64 o = 0, a = ~0ull;
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { const u64 k = key[i]; o |= k; a &= k; }
+	for (int d = 16; d > 0; d >>= 1) { o |= __shfl_down_sync(0xFFFFFFFFu, o, d); a &= __shfl_down_sync(0xFFFFFFFFu, a, d); }
+	if ((threadIdx.x & 31) == 0) { atomicOr(out, o); atomicAnd(out + 1, a); }
+}
+__global__ void __launch_bounds__(256) k_rs_hist(const u64 *__restrict__ key, u32 n, u32 shift, u32 *__restrict__ hist, u32 nblk)
+{
+	__shared__ u32 h[256];
+	h[threadIdx.x] = 0;
+	__syncthreads();
+	const u32 base = blockIdx.x * OGB_RS_TILE;
+	#pragma unroll
+	for (int r = 0; r < 8; r++) { const u32 i = base + r * 256 + threadIdx.x; if (i < n) atomicAdd(&h[(u32)(key[i] >> shift) & 255u], 1u); }
+	__syncthreads();
+	hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+}
+__global__ void __launch_bounds__(256) k_rs_scatter(const u64 *__restrict__ key, const u32 *__restrict__ val, u64 *__restrict__ key_out, u32 *__restrict__ val_out,
+                                                    u32 n, u32 shift, const u64 *__restrict__ offs, u32 nblk)
+{
+	__shared__ unsigned short cnt[64][256];                                  // pairs of digit d in (round, warp) p; then their exclusive prefix
+	__shared__ u32 s_base[256];
+	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lt = (1u << lane) - 1;
+	for (u32 i = threadIdx.x; i < 64 * 256 / 2; i += 256) ((u32 *)cnt)[i] = 0;
+	s_base[threadIdx.x] = (u32)offs[threadIdx.x * nblk + blockIdx.x];
+	__syncthreads();
+	const u32 base = blockIdx.x * OGB_RS_TILE;
+	u64 k[8]; u32 v[8]; unsigned char dg[8], rk[8];
+	#pragma unroll
+	for (int r = 0; r < 8; r++) {
+		const u32 i = base + r * 256 + threadIdx.x;
+		const bool valid = i < n;
+		k[r] = valid ? key[i] : 0; v[r] = valid ? val[i] : 0;
+		dg[r] = (unsigned char)((k[r] >> shift) & 255u); rk[r] = 0;
+		const u32 act = __ballot_sync(0xFFFFFFFFu, valid);
+		if (valid) {
+			const u32 m = __match_any_sync(act, (u32)dg[r]);
+			rk[r] = (unsigned char)__popc(m & lt);
+			if ((m & lt) == 0) cnt[r * 8 + wib][dg[r]] = (unsigned short)__popc(m);   // the first lane of the group
+		}
+	}
+	__syncthreads();
+	{
+		u32 run = 0;                                                          // thread d: exclusive prefix of digit d over the 64 (round, warp) pairs
+		for (int p = 0; p < 64; p++) { const u32 c = cnt[p][threadIdx.x]; cnt[p][threadIdx.x] = (unsigned short)run; run += c; }
+	}
+	__syncthreads();
+	#pragma unroll
+	for (int r = 0; r < 8; r++) {
+		const u32 i = base + r * 256 + threadIdx.x;
+		if (i < n) { const u32 at = s_base[dg[r]] + cnt[r * 8 + wib][dg[r]] + rk[r]; key_out[at] = k[r]; val_out[at] = v[r]; }
+	}
+}
+
 // head[i] = 1 when the read at sorted position i differs from its predecessor (:316-345).
 __global__ void __launch_bounds__(256) k_ds_heads(const u64 *__restrict__ rows, const unsigned short *__restrict__ len, const u32 *__restrict__ perm,
                                                   u32 *__restrict__ head, u32 n, u32 W)
@@ -520,11 +615,12 @@ __global__ void __launch_bounds__(256, 6) k_key_part(ReadStore R, Table T, KeyQu
 			read_geom(R, idx, off, L);
 			const u64 *w = R.words + off + (o >> 1) * padded_words(L);
 			const u32 p = (o & 1) ? L - T.h : 0;
+			// several ranks: 1 - 1/G of the keys belong to partitions another rank builds -- they leave after one funnel shift
+			if (T.nparts > T.sub && partition_of(key_lead<LdGlobal>(w, p, T.h), T) / T.sub != T.my_rank) continue;
 			u32 lead;
 			const u64 hash = key_hash<LdGlobal>(w, p, T.h, lead);
 			u32 part;
 			eb[r] = bucket_of(hash, lead, T, part);
-			if (T.nparts > T.sub && part / T.sub != T.my_rank) continue;          // another rank builds that partition
 			ef[r] = hash_fp(hash); ev[r] = ((idx + 1) << 2) | o;
 			ep[r] = (part << 16) | atomicAdd(&s_cnt[part], 1u);
 		}
