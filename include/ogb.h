@@ -143,10 +143,11 @@ int ogb_dataset_add_file(ogb_dataset *ds, const char *path);
  * counting frequency and assign ID = rank+1 (removeDupicateReads :316-345). */
 int ogb_dataset_finalize(ogb_dataset *ds, uint32_t min_overlap);
 
-/* The same on the GPU of `ctx`: the filter stays on the host threads; canonical strand, an LSD
- * radix sort over the packed words (cub::DeviceRadixSort per 64-bit word), dedupe and frequencies run on the device.
- * Same post-conditions and host views as ogb_dataset_finalize; in addition the packed reads stay in the context's HBM,
- * so the ogb_reads_upload_dataset that follows (HashTable::insertDataset) has nothing left to copy. */
+/* The same on the GPU of `ctx`, every step of it: the filter (k_ds_filter), canonical strand, a
+ * hand-written stable LSD radix sort over the packed words (8-bit passes, bytes in which no two reads differ skipped), dedupe and
+ * frequencies. Same post-conditions and host views as ogb_dataset_finalize (the packed words are downloaded when the host first asks
+ * for them); in addition the packed reads stay in the context's HBM, so the ogb_reads_upload_dataset that follows
+ * (HashTable::insertDataset) has nothing left to copy. On failure the raw reads are kept and ogb_dataset_finalize can still run. */
 int ogb_dataset_finalize_device(ogb_dataset *ds, ogb_context *ctx, uint32_t min_overlap);
 
 uint64_t ogb_dataset_n_reads(const ogb_dataset *ds);   /* Dataset::getNumberOfReads (:352): good reads */
