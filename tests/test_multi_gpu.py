@@ -1,6 +1,8 @@
-"""GPU, N > 1: the sharded path (query-read shards, index built partition-wise and replicated, NCCL allgather of
-the packed pre-reduction adjacency, verdict bits and final edges) gives every rank the oracle's graph. Needs >= 2 GPUs
-(`gpurun --gpus 2`); skipped otherwise."""
+"""GPU, N > 1: the sharded path (query-read shards; index built partition-wise and replicated; adjacency rows pushed to the peers
+chunk by chunk behind the verification; NCCL allgather of the overflow entries, verdict bits and final edges) gives every rank the
+oracle's graph -- on the small adversarial sets, edge for edge, and at scale (config 2 / config 3 x world, config 4 at full size on 8
+ranks) through counters and the order-independent checksum of the lean oracle's goldens. Needs >= 2 GPUs (`gpurun --gpus N`); the cases a
+box cannot run are skipped. Logs of the round's runs: profiles/r2/tests_2gpu_mid.log, profiles/r2/tests_8gpu.log."""
 import os
 import subprocess
 import sys
