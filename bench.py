@@ -510,6 +510,15 @@ def main():
             "emit": Fo * 12 + nloc * 8,
         }
         k = st["kernels"]
+        # fused schedule: chunk i's probe and chunk i-1's verification are one launch (k_probe_verify); only the first probe and the
+        # last verify run alone -- the probe / verify bytes are apportioned by launches
+        nf = k.get("probe_verify", {}).get("launches", 0)
+        npb, nvf = k.get("probe_parts", {}).get("launches", 0), k.get("verify", {}).get("launches", 0)
+        if nf:
+            probe_b, verify_b = alg["probe_parts"], alg["verify"]
+            alg["probe_parts"] = probe_b * npb / (npb + nf)
+            alg["verify"] = verify_b * nvf / (nvf + nf)
+            alg["probe_verify"] = probe_b * nf / (npb + nf) + verify_b * nf / (nvf + nf)
         mark_ms = sum(k[c]["ms"] for c in ("mark_fast1", "mark_fast2", "mark_any") if c in k)
         mark_alg = E * EDGE_BYTES + T * 4                    # own lists (8-byte words) + pivot rows (4-byte entries)
         ktable = {}
@@ -529,7 +538,8 @@ def main():
             v = C.c_double()
             check(L.ogb_gather_ceiling(ctx._h, min(next_pow2(size), 8 << 30), gb, C.byref(v)))
             ceil[label] = {"buffer_bytes": min(next_pow2(size), 8 << 30), "gather_bytes": gb, "useful_gbs": v.value}
-        gather_of = {"verify": ("read_store_32B", E * W), "probe_parts": ("index_64B", st["probe_sectors"] * 64), "mark_fast1": ("rows_128B", None),
+        gather_of = {"verify": ("read_store_32B", E * W), "probe_parts": ("index_64B", st["probe_sectors"] * 64),
+                     "probe_verify": ("read_store_32B", (E * W + st["probe_sectors"] * 64) * (nf / max(1, nvf + nf))), "mark_fast1": ("rows_128B", None),
                      "mark_fast2": ("rows_128B", None), "mark_any": ("rows_128B", None)}
         traffic = None
         tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")

@@ -74,6 +74,7 @@ enum {
 	OGB_KC_EXCH_ROWS,       /* C1: allgather of the adjacency rows */
 	OGB_KC_EXCH_BITS,       /* C2: allgather of the ELIM bits */
 	OGB_KC_EXCH_FINAL,      /* C3: allgather of the final edges */
+	OGB_KC_PROBE_VERIFY,    /* K3b+c k_probe_verify: probe of chunk i and verification of chunk i-1 in one warp-specialised launch */
 	OGB_KC_COUNT = 20
 };
 

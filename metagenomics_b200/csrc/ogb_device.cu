@@ -1095,11 +1095,71 @@ template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 	const u32 n_chunks = (u32)(((xchg ? per_rank : (u64)(hi - lo)) + c->chunk_reads - 1) / c->chunk_reads);
 	const GraphView gv_rows = graph_view(c, lo);
 	const int g_rows = grid_for(c, (const void *)k_rows_finish<false>, 256);
+	// Fused schedule (experiment knob OGB_FUSED=1; the default is the two-stream schedule below): one stream, and from the second
+	// chunk on the probe of chunk i and the verification of chunk i-1 are ONE warp-specialised launch (k_probe_verify), so that the
+	// two share every SM instead of taking turns. Measured SLOWER (config 3: K3 21.8 ms against 17.2 ms; a fused launch 0.70 ms against
+	// 0.30 + 0.30 ms apart): both kernels wait for the same thing -- random accesses beyond the translation reach -- and co-residency
+	// only makes their working sets compete (profiles/r2/exp_fused.txt).
+	const bool fused = part_mode && getenv("OGB_FUSED") && atoi(getenv("OGB_FUSED")) == 1;
+	bool have_prev = false;
+	ScanArgs a_prev = a;
+	u32 prev_i = 0;
+	// rows of a verified chunk on the third stream (+ their exchange on several ranks)
+	auto finish_chunk = [&](const ScanArgs &av, u32 ci, cudaStream_t after) -> int {
+		if (MODE != MODE_OVERLAP) return OGB_OK;
+		CUDA_TRY(cudaEventRecord(c->ev_rows[ci & 1], after));
+		CUDA_TRY(cudaStreamWaitEvent(c->xs, c->ev_rows[ci & 1], 0));
+		KEV(OGB_KC_ROWS, c->xs, (k_rows_finish<false><<<std::min<int>(g_rows, (int)((av.hi - av.lo + 255) / 256)), 256, 0, c->xs>>>(gv_rows, av.lo, av.hi, c->more_own.p, c->more_cap, c->d_ctr, nullptr, 0)));
+		c->launches++;
+		if (xchg) {
+			const int ke = kev_begin(c, OGB_KC_EXCH_ROWS, c->xs);
+			OGB_TRY(exchange_chunk_rows(c, ci, c->xs));
+			kev_end(c, ke, c->xs);
+		}
+		return OGB_OK;
+	};
+	auto flush_prev = [&]() -> int {                                          // the last verified-later chunk: its verify runs alone
+		if (!have_prev) return OGB_OK;
+		KEV(MODE == MODE_OVERLAP ? OGB_KC_VERIFY : OGB_KC_CONTAIN_VERIFY, c->stream, (k_verify<MODE><<<gv, 256, 0, c->stream>>>(a_prev)));
+		c->launches++;
+		have_prev = false;
+		return finish_chunk(a_prev, prev_i, c->stream);
+	};
 	for (; i < n_chunks; i++) {
 		const u64 b0 = (u64)lo + (u64)i * c->chunk_reads;
 		const int q = i & 1;
 		if (b0 >= hi) {                                                        // no reads of this rank in the chunk: only its part of the exchange
+			if (fused) OGB_TRY(flush_prev());
 			if (xchg) { const int ke = kev_begin(c, OGB_KC_EXCH_ROWS, c->xs); OGB_TRY(exchange_chunk_rows(c, i, c->xs)); kev_end(c, ke, c->xs); }
+			continue;
+		}
+		if (fused) {
+			a.lo = (u32)b0; a.hi = (u32)std::min<u64>(hi, b0 + c->chunk_reads);
+			a.cand_q = c->cand_q.p + q * c->cand_cap; a.cand_v = c->cand_v.p + q * c->cand_cap; a.cand_cursor = c->d_cursor + q;
+			a.prefetch = 0;
+			CUDA_TRY(cudaMemsetAsync(a.cand_cursor, 0, sizeof(u64), c->stream));
+			CUDA_TRY(cudaMemsetAsync(c->d_pq_cursor, 0, OGB_MAXPART * sizeof(u64), c->stream));
+			PartQueue pq;
+			pq.b = c->pq_b.p; pq.f = c->pq_f.p; pq.q = c->pq_q.p; pq.cursor = c->d_pq_cursor; pq.cap = c->pq_cap; pq.nparts = c->nparts;
+			const u32 nreads = a.hi - a.lo;
+			const u64 tiles = ((u64)nreads * nwin_u + 256 * OGB_WPT - 1) / (256 * OGB_WPT);
+			const bool uni = c->uniform_len && !a.contained;
+			const int gw = grid_for(c, uni ? (const void *)k_window_part<MODE, true> : (const void *)k_window_part<MODE, false>, 256);
+			const int kc = MODE == MODE_OVERLAP ? 0 : OGB_KC_CONTAIN_WINDOW - OGB_KC_WINDOW;
+			const bool timed = MODE == MODE_OVERLAP && i < 64;
+			if (timed) CUDA_TRY(cudaEventRecord(c->ev_pk[2 * i], c->stream));
+			if (uni) KEV(OGB_KC_WINDOW + kc, c->stream, (k_window_part<MODE, true><<<(unsigned)std::min<u64>(gw, tiles), 256, 0, c->stream>>>(a, nwin_u, ~0ull / nwin_u + 1, pq)));
+			else KEV(OGB_KC_WINDOW + kc, c->stream, (k_window_part<MODE, false><<<(unsigned)std::min<u64>(gw, tiles), 256, 0, c->stream>>>(a, nwin_u, ~0ull / nwin_u + 1, pq)));
+			if (timed) CUDA_TRY(cudaEventRecord(c->ev_pm[i], c->stream));
+			if (have_prev) {
+				KEV(MODE == MODE_OVERLAP ? OGB_KC_PROBE_VERIFY : OGB_KC_CONTAIN_PROBE, c->stream,
+				    (k_probe_verify<MODE><<<grid_for(c, (const void *)k_probe_verify<MODE>, 256), 256, 0, c->stream>>>(a, pq, a_prev)));
+				OGB_TRY(finish_chunk(a_prev, prev_i, c->stream));
+			} else
+				KEV(OGB_KC_PROBE + kc, c->stream, (k_probe_parts<MODE><<<grid_for(c, (const void *)k_probe_parts<MODE>, 256), 256, 0, c->stream>>>(a, pq)));
+			if (timed) { CUDA_TRY(cudaEventRecord(c->ev_pk[2 * i + 1], c->stream)); c->n_pk = i + 1; }
+			c->launches += 2;
+			have_prev = true; a_prev = a; prev_i = i;
 			continue;
 		}
 		a.lo = (u32)b0; a.hi = (u32)std::min<u64>(hi, b0 + c->chunk_reads);
@@ -1136,13 +1196,14 @@ template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 		}
 		KEV(MODE == MODE_OVERLAP ? OGB_KC_VERIFY : OGB_KC_CONTAIN_VERIFY, sv, (k_verify<MODE><<<gv, 256, 0, sv>>>(a)));
 		if (MODE == MODE_OVERLAP) {
-			// rows of the chunk's nodes right behind their verification (slot regions still in L2); nodes with more edges than
-			// slots wait for the heavy pass after K3. Several ranks: the finished rows leave on the exchange stream.
-			KEV(OGB_KC_ROWS, sv, (k_rows_finish<false><<<std::min<int>(g_rows, (int)((a.hi - a.lo + 255) / 256)), 256, 0, sv>>>(gv_rows, a.lo, a.hi, c->more_own.p, c->more_cap, c->d_ctr, nullptr, 0)));
+			// rows of the chunk's nodes right behind their verification (slot regions still in L2), on the third stream so that the
+			// next verify does not queue behind them; nodes with more edges than slots wait for the heavy pass after K3. Several
+			// ranks: the finished rows leave on the same stream.
+			CUDA_TRY(cudaEventRecord(c->ev_rows[q], sv));
+			CUDA_TRY(cudaStreamWaitEvent(c->xs, c->ev_rows[q], 0));
+			KEV(OGB_KC_ROWS, c->xs, (k_rows_finish<false><<<std::min<int>(g_rows, (int)((a.hi - a.lo + 255) / 256)), 256, 0, c->xs>>>(gv_rows, a.lo, a.hi, c->more_own.p, c->more_cap, c->d_ctr, nullptr, 0)));
 			c->launches++;
 			if (xchg) {
-				CUDA_TRY(cudaEventRecord(c->ev_rows[q], sv));
-				CUDA_TRY(cudaStreamWaitEvent(c->xs, c->ev_rows[q], 0));
 				const int ke = kev_begin(c, OGB_KC_EXCH_ROWS, c->xs);
 				OGB_TRY(exchange_chunk_rows(c, i, c->xs));
 				kev_end(c, ke, c->xs);
@@ -1151,9 +1212,10 @@ template <int MODE> static int scan_chunks(ogb_context *c, u32 lo, u32 hi)
 		if (overlap_streams) CUDA_TRY(cudaEventRecord(c->ev_verify[q], sv));
 		c->launches += 2;
 	}
-	if (overlap_streams)                                                     // the main stream continues after every verify
+	if (fused) OGB_TRY(flush_prev());
+	if (overlap_streams && !fused)                                           // the main stream continues after every verify
 		for (int q = 0; q < 2 && q < (int)i; q++) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_verify[q], 0));
-	if (xchg) { CUDA_TRY(cudaEventRecord(c->ev_xs, c->xs)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_xs, 0)); }
+	if (MODE == MODE_OVERLAP) { CUDA_TRY(cudaEventRecord(c->ev_xs, c->xs)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_xs, 0)); }
 	CUDA_TRY(cudaGetLastError());
 	return OGB_OK;
 }

@@ -1009,11 +1009,10 @@ __global__ void __launch_bounds__(256, 6) k_window_part(ScanArgs A, u32 nwin, u6
 	}
 }
 
+// Body of the partition probe for the warp `gw` of `nwarps` warps that share the work.
 template <int MODE>
-__global__ void __launch_bounds__(256, OGB_PROBE_MINBLOCKS) k_probe_parts(ScanArgs A, PartQueue PQ)
+__device__ __forceinline__ void probe_parts_body(const ScanArgs &A, const PartQueue &PQ, u64 gw, u64 nwarps, u32 lane)
 {
-	const u32 lane = threadIdx.x & 31;
-	const u64 gw = (blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * (u64)blockDim.x) >> 5;
 	u64 c_sectors = 0;
 	QueueCursor Q = {0, 0, 0};
 	for (u32 part = 0; part < PQ.nparts; part++) {
@@ -1031,19 +1030,25 @@ __global__ void __launch_bounds__(256, OGB_PROBE_MINBLOCKS) k_probe_parts(ScanAr
 	for (int d = 16; d > 0; d >>= 1) c_sectors += __shfl_down_sync(0xFFFFFFFFu, c_sectors, d);
 	if (lane == 0) atomicAdd(A.ctr + CTR_SECTORS, c_sectors);
 }
+template <int MODE>
+__global__ void __launch_bounds__(256, OGB_PROBE_MINBLOCKS) k_probe_parts(ScanArgs A, PartQueue PQ)
+{
+	probe_parts_body<MODE>(A, PQ, (blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5, (gridDim.x * (u64)blockDim.x) >> 5, threadIdx.x & 31);
+}
 
 // One thread per candidate. The loop is warp-uniform (32 consecutive candidates per warp and
 // iteration): a read's candidates are adjacent in the queue, so the lanes of a warp mostly append to
 // the same one or two nodes -- their deg[] increments are aggregated with __match_any_sync into one
 // atomic per distinct node instead of ~26 serialised same-address atomics.
+// Body of the verification for the threads `first + lane` of a warp, `stride` threads sharing the work (warp-uniform loop).
 template <int MODE>
-__global__ void __launch_bounds__(256, OGB_VERIFY_MINBLOCKS) k_verify(ScanArgs A)
+__device__ __forceinline__ void verify_body(const ScanArgs &A, u64 first, u64 stride, bool announce)
 {
 	const u64 total = min(*A.cand_cursor, A.cand_cap);
-	if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(A.ctr + CTR_CAND_MAX, *A.cand_cursor);
+	if (announce) atomicMax(A.ctr + CTR_CAND_MAX, *A.cand_cursor);
 	const u32 h = A.T.h, lane = threadIdx.x & 31, lt = (1u << lane) - 1;
 	u32 c_cand = 0, c_hits = 0;
-	for (u64 c0 = (u64)blockIdx.x * blockDim.x + (threadIdx.x - lane); c0 < total; c0 += (u64)gridDim.x * blockDim.x) {
+	for (u64 c0 = first; c0 < total; c0 += stride) {
 		const u64 c = c0 + lane;
 		bool ok = false;
 		u32 qi = c < total ? A.cand_q[c] : OGB_NOCAND, ri = 0, o = 0, L1 = 0, L2 = 0, orient = 0, offset = 0;
@@ -1122,6 +1127,21 @@ __global__ void __launch_bounds__(256, OGB_VERIFY_MINBLOCKS) k_verify(ScanArgs A
 		if (c_cand) atomicAdd(A.ctr + CTR_CANDIDATES, (u64)c_cand);
 		if (MODE == MODE_CONTAIN && c_hits) atomicAdd(A.ctr + CTR_CONTAIN_HITS, (u64)c_hits);
 	}
+}
+template <int MODE>
+__global__ void __launch_bounds__(256, OGB_VERIFY_MINBLOCKS) k_verify(ScanArgs A)
+{
+	verify_body<MODE>(A, (u64)blockIdx.x * blockDim.x + (threadIdx.x - (threadIdx.x & 31)), (u64)gridDim.x * blockDim.x, blockIdx.x == 0 && threadIdx.x == 0);
+}
+// Probe of one chunk and verification of the previous one in ONE launch, warp-specialised: warps 0-3 of every block probe,
+// warps 4-7 verify. Launched one after the other each kernel fills the SMs with its own blocks, so the issue-bound probe and the
+// gather-latency-bound verify never actually share an SM (two streams only overlap their tails); inside one block they do.
+template <int MODE>
+__global__ void __launch_bounds__(256, OGB_PROBE_MINBLOCKS) k_probe_verify(ScanArgs AP, PartQueue PQ, ScanArgs AV)
+{
+	const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	if (wib < 4) probe_parts_body<MODE>(AP, PQ, (u64)blockIdx.x * 4 + wib, (u64)gridDim.x * 4, lane);
+	else verify_body<MODE>(AV, (u64)blockIdx.x * 128 + (wib - 4) * 32, (u64)gridDim.x * 128, blockIdx.x == 0 && threadIdx.x == 128);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1375,10 +1395,13 @@ __device__ __forceinline__ int pick_min(bool cand, u64 w)
 // with indexed shuffles and compares: stale or foreign table bytes can never produce a hit, so the tables are never
 // cleared. The states are bit masks in registers (bit k = the destination REPRESENTED by entry k was eliminated; every
 // entry knows its representative = the entry the tables return for its destination, which also covers multi-edges).
-#define OGB_T1 1024
+#ifndef OGB_T1_BITS
+#define OGB_T1_BITS 10
+#endif
+#define OGB_T1 (1 << OGB_T1_BITS)
 #define OGB_T2 256
 #define OGB_FALLBACK 0xFFFFFFFFu   // cntc value: the fast kernel hands the node to k_mark_any
-template <int S> __device__ __forceinline__ u32 rs_h1(u32 key) { return (key * 2654435761u) >> (S == 1 ? 22 : 21); }
+template <int S> __device__ __forceinline__ u32 rs_h1(u32 key) { return (key * 2654435761u) >> (32 - OGB_T1_BITS - (S - 1)); }
 __device__ __forceinline__ u32 rs_h2(u32 key) { return (key * 0x85EBCA6Bu) >> 24; }
 // destination held by entry j (every lane of the warp must call this)
 template <int S> __device__ __forceinline__ u32 rs_fetch(const u32 (&dst)[S], u32 j)
