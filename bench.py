@@ -508,6 +508,10 @@ def main():
             "mark_fast1": None, "mark_fast2": None, "mark_any": None,   # split below
             "keep": 2 * st["active_pivots"] * 8 + st["active_pivots"] * 4,
             "emit": Fo * 12 + nloc * 8,
+            # K2 (mixed read lengths only): the same scan over every window of every read, candidates = containment hits + fingerprint collisions
+            "contain_window": W * nloc + 4 * st["contain_probes"],
+            "contain_probe": SECTOR * st["contain_probes"],
+            "contain_verify": st["contain_hits"] * (W + 12),
         }
         k = st["kernels"]
         # fused schedule: chunk i's probe and chunk i-1's verification are one launch (k_probe_verify); only the first probe and the
