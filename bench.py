@@ -493,6 +493,22 @@ def main():
         dist.all_reduce(xfer)
     h2d_all, d2h_all = (int(x) for x in xfer.cpu())
 
+    # ---- the stage after the timed path (OverlapGraph.cpp:211-215: contraction + dead-end removal to the fix-point), on the graph
+    # the last step left on the device. Not part of the metric (BASELINE's path ends at :210); reported beside it. One rank only.
+    simplify = None
+    if world == 1:
+        from metagenomics_b200._lib import SimplifyStats
+        try:
+            ss = SimplifyStats()
+            times = []
+            for _ in range(3):
+                check(L.ogb_graph_simplify(ctx._h, C.byref(ss)))
+                times.append(ss.ms)
+            simplify = dict(ss.as_dict(), ms=min(times[1:]), ms_runs=[round(float(x), 3) for x in times],
+                            what="ogb_graph_simplify on the final graph of the last step, device time (CUDA events), result left on the device")
+        except Exception as e:                                   # auxiliary stage: reported, never fatal for the bench line
+            simplify = {"error": str(e)}
+
     peak, peak_src = measured_peaks()
     if rank == 0:
         # ---- per-kernel-class roofline (rank 0; event pairs around every launch, recorded during the last timed step)
@@ -596,6 +612,7 @@ def main():
             "roofline_step": {"bound": "hbm", "algorithmic_bytes": bytes_alg, "formula": "SURVEY.md 8(d): S = 32 B, B_e = 16 B, W = padded strand; counters of this run",
                               "achieved": bytes_alg / (ms_step * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s", "frac": bytes_alg / (ms_step * 1e-3) / 1e9 / (peak * world)},
             "kernels": ktable,
+            "simplify": simplify,
             "gather_ceilings": ceil,
             "phases_ms": {k_: st[k_] for k_ in ("ms_hash_build", "ms_contain", "ms_overlap", "ms_scan_kernel", "ms_exchange_pre", "ms_mark", "ms_reduce", "ms_total")},
             "stats": {k_: st[k_] for k_ in ("table_bytes", "hash_partitions", "overlap_probes", "probe_sectors", "candidates", "pivot_entries", "active_pivots",

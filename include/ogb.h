@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OGB_VERSION 200
+#define OGB_VERSION 210
 
 enum {
 	OGB_OK = 0,
@@ -249,6 +249,53 @@ int ogb_graph_edges_shard(ogb_context *ctx, ogb_edge *out, uint64_t cap, uint64_
  * mix(src*K1 ^ dst*K2 ^ offset*K3 ^ orient*K4), mix(x) = (x ^ x>>29) * K5, then ^ >>32 -- the figure the oracle's
  * full-size goldens carry (tests/golden/full_size.json), so a result of GBs can be checked without leaving HBM. */
 int ogb_graph_checksum(ogb_context *ctx, int which, uint64_t *xor_out, uint64_t *sum_out);
+
+/* ----------------------------------------------------------------------------------------------
+ * Graph simplification: the fix-point that ends OverlapGraph::buildOverlapGraphFromHashTable,
+ *     do { counter = contractCompositePaths(); counter += removeDeadEndNodes(); } while (counter > 0);
+ * (OverlapGraph.cpp:211-215; contractCompositePaths :669-694, mergeEdges :702-752, mergeList :760-785,
+ * removeDeadEndNodes :931-988), on the device, on the post-reduction edge list of this context.
+ * -------------------------------------------------------------------------------------------- */
+
+/* One directed edge of the simplified graph: an Edge record (Edge.h:17-44) whose listOfReads / listOfOverlapOffsets /
+ * listOfOrientations are items[list_start .. list_start + count). twin = index of the reverse edge in the same array. */
+typedef struct ogb_cedge {
+	uint32_t src;
+	uint32_t dst;
+	uint64_t offset;     /* overlapOffset: UINT64 once edges are merged (Edge.h:25) */
+	uint64_t list_start;
+	uint32_t count;
+	uint32_t twin;
+	uint8_t orient;
+	uint8_t reserved[3];
+	uint32_t reserved2;
+} ogb_cedge; /* 40 bytes */
+
+/* One read inside a composite edge: read ID, its overlap offset from the previous read (UINT16) and its orientation
+ * (1 forward, 0 reverse) -- the three parallel vectors of Edge.h:30-32. */
+typedef struct ogb_clist_item {
+	uint32_t read;
+	uint16_t offset;
+	uint8_t orient;
+	uint8_t reserved;
+} ogb_clist_item; /* 8 bytes */
+
+typedef struct ogb_simplify_stats {
+	uint64_t n_edges_in, n_edges_out, n_items;
+	uint64_t merges, dead_ends;   /* sums of the reference's two counters over all iterations */
+	uint32_t iterations;          /* of the do-while */
+	uint32_t rounds;              /* launches pairs of the contraction sweeps (see csrc/ogb_contract.cuh) */
+	uint32_t jumps;               /* pointer-jumping launches that ranked the read lists */
+	uint32_t launches;
+	float ms;                     /* device time of the whole stage */
+} ogb_simplify_stats;
+
+/* Runs the fix-point on the graph ogb_build_graph left on the device (every rank holds the whole post-reduction list, so this
+ * is rank-local: no collective) and keeps the result on the device. The edge list of ogb_graph_edges stays as it was. */
+int ogb_graph_simplify(ogb_context *ctx, ogb_simplify_stats *stats);
+/* Copies the simplified graph to host memory: edges in (src, position in the source's original row) order, items as indexed
+ * by list_start. Capacities in elements (ogb_simplify_stats.n_edges_out / n_items). */
+int ogb_graph_composite_edges(ogb_context *ctx, ogb_cedge *edges, uint64_t edge_cap, ogb_clist_item *items, uint64_t item_cap);
 
 int ogb_get_stats(ogb_context *ctx, ogb_stats *out);
 

@@ -39,6 +39,15 @@ class Stats(C.Structure):
         return d
 
 
+class SimplifyStats(C.Structure):
+    """ogb_simplify_stats (include/ogb.h)."""
+    _fields_ = [(n, C.c_uint64) for n in ("n_edges_in", "n_edges_out", "n_items", "merges", "dead_ends")] + [
+        (n, C.c_uint32) for n in ("iterations", "rounds", "jumps", "launches")] + [("ms", C.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 # every symbol include/ogb.h declares: name -> (restype, argtypes)
 _u64p = C.POINTER(C.c_uint64)
 _vp = C.c_void_p
@@ -83,6 +92,8 @@ PROTOTYPES = {
     "ogb_graph_edges": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
     "ogb_graph_edges_shard": (C.c_int, [_vp, _vp, C.c_uint64, _u64p]),
     "ogb_graph_checksum": (C.c_int, [_vp, C.c_int, _u64p, _u64p]),
+    "ogb_graph_simplify": (C.c_int, [_vp, C.POINTER(SimplifyStats)]),
+    "ogb_graph_composite_edges": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_uint64]),
     "ogb_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "ogb_timer_begin": (C.c_int, [_vp]),
     "ogb_timer_end": (C.c_int, [_vp, C.POINTER(C.c_float)]),

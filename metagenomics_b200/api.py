@@ -13,6 +13,11 @@ import numpy as np
 from ._lib import Edge, OgbError, Stats, check, lib  # noqa: F401
 
 EDGE_DTYPE = np.dtype([("src", "<u4"), ("dst", "<u4"), ("offset", "<u2"), ("orient", "u1"), ("reserved", "u1")])
+# ogb_cedge / ogb_clist_item (include/ogb.h): the simplified graph
+CEDGE_DTYPE = np.dtype([("src", "<u4"), ("dst", "<u4"), ("offset", "<u8"), ("list_start", "<u8"), ("count", "<u4"), ("twin", "<u4"), ("orient", "u1"),
+                        ("reserved", "u1", (3,)), ("reserved2", "<u4")])
+CITEM_DTYPE = np.dtype([("read", "<u4"), ("offset", "<u2"), ("orient", "u1"), ("reserved", "u1")])
+assert CEDGE_DTYPE.itemsize == 40 and CITEM_DTYPE.itemsize == 8
 assert EDGE_DTYPE.itemsize == C.sizeof(Edge) == 12
 
 
@@ -230,6 +235,18 @@ class OverlapGraph:
         out = np.zeros(cap, dtype=EDGE_DTYPE)
         check(lib().ogb_graph_edges_shard(self.ctx._h, out.ctypes.data, cap, C.byref(n)))
         return out[:n.value]
+
+    def simplify(self):
+        """The fix-point that ends buildOverlapGraphFromHashTable (OverlapGraph.cpp:211-215: contractCompositePaths +
+        removeDeadEndNodes until neither changes anything), on the device. Returns (edges, items, stats): edges as CEDGE_DTYPE
+        records in source order, the reads inside edge i = items[list_start : list_start + count] (CITEM_DTYPE)."""
+        from ._lib import SimplifyStats
+        st = SimplifyStats()
+        check(lib().ogb_graph_simplify(self.ctx._h, C.byref(st)))
+        edges = np.zeros(st.n_edges_out, dtype=CEDGE_DTYPE)
+        items = np.zeros(st.n_items, dtype=CITEM_DTYPE)
+        check(lib().ogb_graph_composite_edges(self.ctx._h, edges.ctypes.data, len(edges), items.ctypes.data, len(items)))
+        return edges, items, st.as_dict()
 
     def checksum(self, pre=False):
         """[xor, sum] of the 64-bit mix of every edge tuple, computed on the device (the figure of tests/golden/full_size.json)."""

@@ -10,6 +10,7 @@
 
 #include "ogb_internal.h"
 #include "ogb_kernels.cuh"
+#include "ogb_contract.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -181,6 +182,16 @@ struct ogb_context {
 	bool have_graph = false, have_pre = false;
 	u64 *d_ctr = nullptr, *h_ctr = nullptr;
 	u64 *d_tot = nullptr;            // [0] scan total of pre-reduction degrees, [1] of surviving edges
+	// simplification (ogb_contract.cuh): CSR of entries, rope records, per-sweep work lists, the result
+	Pool<CEntry> sE;
+	Pool<CRec> s_rec;
+	Pool<u32> s_rowptr, s_cp, s_info, s_list, s_keep, s_items;
+	Pool<uint8_t> s_state, s_ready, s_flag;
+	Pool<u64> s_epos, s_lpos, s_ctr;
+	Pool<ogb_cedge> s_out;
+	Pool<ogb_clist_item> s_out_items;
+	bool have_simplified = false;
+	ogb_simplify_stats sst = {};
 	ogb_stats st = {};
 	u32 launches = 0;
 
@@ -348,6 +359,8 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	c->slots.release(); c->summary.release(); c->sup.release(); c->contained.release(); c->pos.release();
 	c->sums.release(); c->surv.release(); c->cand.release(); c->big.release(); c->cntc.release(); c->cnt.release();
 	c->scratch_keys.release(); c->fin.release(); c->pre.release(); c->flush.release(); c->fin_stage.release();
+	c->sE.release(); c->s_rec.release(); c->s_rowptr.release(); c->s_cp.release(); c->s_info.release(); c->s_list.release(); c->s_keep.release(); c->s_items.release();
+	c->s_state.release(); c->s_ready.release(); c->s_flag.release(); c->s_epos.release(); c->s_lpos.release(); c->s_ctr.release(); c->s_out.release(); c->s_out_items.release();
 	if (c->d_ctr) cudaFree(c->d_ctr);
 	if (c->d_tot) cudaFree(c->d_tot);
 	if (c->d_cursor) cudaFree(c->d_cursor);
@@ -1326,7 +1339,7 @@ extern "C" int ogb_build_graph(ogb_context *c, int keep_pre)
 	CUDA_TRY(cudaSetDevice(c->device));
 	// buildOverlapGraphFromHashTable always marks contained reads first (OverlapGraph.cpp:140)
 	if (!c->contain_done) OGB_TRY(ogb_mark_contained(c));
-	c->have_graph = false; c->have_pre = false; c->n_final = 0; c->n_pre = 0;
+	c->have_graph = false; c->have_pre = false; c->have_simplified = false; c->n_final = 0; c->n_pre = 0;
 	const u32 n = c->n;
 	if (n == 0) { c->have_graph = true; c->have_pre = keep_pre != 0; c->st.edges_pre = c->st.edges_pre_local = c->st.edges_final = c->st.nodes_final = 0; return OGB_OK; }
 	u32 lo, hi;
@@ -1645,6 +1658,140 @@ extern "C" int ogb_graph_checksum(ogb_context *c, int which, uint64_t *xor_out, 
 	CUDA_TRY(cudaMemcpyAsync(h, c->d_xchg + XCHG_SCRATCH + 4, sizeof h, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	*xor_out = h[0]; *sum_out = h[1];
+	return OGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Simplification (OverlapGraph.cpp:211-215): see ogb_contract.cuh for the formulation.
+// ------------------------------------------------------------------------------------------------
+static int read_u64(ogb_context *c, const u64 *d, u64 *h, u32 n)
+{
+	CUDA_TRY(cudaMemcpyAsync(h, d, n * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return OGB_OK;
+}
+
+extern "C" int ogb_graph_simplify(ogb_context *c, ogb_simplify_stats *stats)
+{
+	if (!c) { ogb_set_error("ogb_graph_simplify: NULL context"); return OGB_E_ARG; }
+	if (!c->have_graph) { ogb_set_error("ogb_graph_simplify: build the graph first"); return OGB_E_STATE; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	const u64 ne = c->n_final;
+	const u32 n = c->n;
+	if (ne >= (1ull << 31) || n >= (1u << 30)) { ogb_set_error("ogb_graph_simplify: %llu edges / %u reads exceed the 31-bit entry and record indices", (unsigned long long)ne, n); return OGB_E_CAPACITY; }
+	c->have_simplified = false;
+	ogb_simplify_stats st = {};
+	st.n_edges_in = ne;
+	const u64 nrec = 2 * ((u64)n + 1);
+	OGB_TRY(c->sE.ensure(std::max<u64>(ne, 1))); OGB_TRY(c->s_rec.ensure(nrec)); OGB_TRY(c->s_info.ensure(nrec)); OGB_TRY(c->s_cp.ensure(nrec));
+	OGB_TRY(c->s_rowptr.ensure((u64)n + 2)); OGB_TRY(c->s_list.ensure(2 * ((u64)n + 1))); OGB_TRY(c->s_keep.ensure(std::max<u64>(ne, 1))); OGB_TRY(c->s_items.ensure(std::max<u64>(ne, 1)));
+	OGB_TRY(c->s_state.ensure((u64)n + 1)); OGB_TRY(c->s_ready.ensure((u64)n + 1)); OGB_TRY(c->s_flag.ensure((u64)n + 2));
+	OGB_TRY(c->s_epos.ensure(ne + 1)); OGB_TRY(c->s_lpos.ensure(ne + 1)); OGB_TRY(c->s_ctr.ensure(16));
+	CGraph G;
+	G.E = c->sE.p; G.rowptr = c->s_rowptr.p; G.n = n; G.n_entries = ne; G.rec = c->s_rec.p; G.rec_info = c->s_info.p; G.state = c->s_state.p; G.cp = c->s_cp.p;
+	G.meta = c->uniform_len ? nullptr : c->meta.p; G.uniform_len = c->uniform_len;
+	// counters (u64): [0] merges, [1] dead ends, [2] twin / ranking errors, [3] largest list, [4] unfinished ropes, [5] total edges, [6] total items; [8], [9]: the two list cursors (u32)
+	u64 *ctr = c->s_ctr.p;
+	u32 *cursor = reinterpret_cast<u32 *>(ctr + 8);
+	const int grid_max = c->sm_count * 8;
+	auto grid = [&](u64 items) { return (unsigned)std::max<u64>(1, std::min<u64>((items + 255) / 256, (u64)grid_max)); };
+	CUDA_TRY(cudaEventRecord(c->ev[EV_T0], c->stream));
+	CUDA_TRY(cudaMemsetAsync(ctr, 0, 16 * sizeof(u64), c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->s_rowptr.p, 0, ((u64)n + 2) * sizeof(u32), c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->s_state.p, 0, (u64)n + 1, c->stream));
+	k_c_records<<<grid(nrec), 256, 0, c->stream>>>(G);
+	st.launches++;
+	if (ne) {
+		k_c_rowptr<<<grid(ne), 256, 0, c->stream>>>(c->fin.p, ne, n, c->s_rowptr.p);
+		k_c_entries<<<grid(ne), 256, 0, c->stream>>>(c->fin.p, G);
+		k_c_twins<<<grid(ne), 256, 0, c->stream>>>(c->fin.p, G, ctr + 2);
+		st.launches += 3;
+	}
+	CUDA_TRY(cudaGetLastError());
+	u64 h[8];
+	OGB_TRY(read_u64(c, ctr, h, 8));
+	if (h[2]) { ogb_set_error("ogb_graph_simplify: %llu edges without a twin", (unsigned long long)h[2]); return OGB_E_STATE; }
+	u32 *list[2] = {c->s_list.p, c->s_list.p + ((u64)n + 1)};
+	for (;;) {
+		if (ne == 0) break;
+		st.iterations++;
+		CUDA_TRY(cudaMemsetAsync(ctr, 0, 2 * sizeof(u64), c->stream));
+		CUDA_TRY(cudaMemsetAsync(cursor, 0, 2 * sizeof(u32), c->stream));
+		k_c_candidates<<<grid(n), 256, 0, c->stream>>>(G, list[0], cursor);
+		st.launches++;
+		u32 hc[2] = {0, 0};
+		CUDA_TRY(cudaMemcpyAsync(hc, cursor, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		u32 n_list = hc[0];
+		int cur = 0;
+		while (n_list) {
+			k_c_ready<<<grid(n_list), 256, 0, c->stream>>>(G, list[cur], n_list, c->s_ready.p);
+			CUDA_TRY(cudaMemsetAsync(cursor + (cur ^ 1), 0, sizeof(u32), c->stream));
+			k_c_turns<<<grid(n_list), 256, 0, c->stream>>>(G, list[cur], n_list, c->s_ready.p, list[cur ^ 1], cursor + (cur ^ 1), ctr);
+			CUDA_TRY(cudaGetLastError());
+			st.launches += 2; st.rounds++;
+			CUDA_TRY(cudaMemcpyAsync(hc, cursor, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
+			CUDA_TRY(cudaStreamSynchronize(c->stream));
+			const u32 n_next = hc[cur ^ 1];
+			if (n_next >= n_list) { ogb_set_error("ogb_graph_simplify: a contraction round made no progress (%u nodes pending)", n_list); return OGB_E_STATE; }
+			n_list = n_next; cur ^= 1;
+		}
+		k_c_dead_ends<<<grid(n), 256, 0, c->stream>>>(G, c->s_flag.p, ctr);
+		k_c_dead_remove<<<grid(n), 256, 0, c->stream>>>(G, c->s_flag.p);
+		CUDA_TRY(cudaGetLastError());
+		st.launches += 2;
+		OGB_TRY(read_u64(c, ctr, h, 2));
+		st.merges += h[0]; st.dead_ends += h[1];
+		if (h[0] + h[1] == 0) break;                                             // while (counter > 0)  (:215)
+	}
+	// result: surviving entries in row order, list positions, ropes ranked and written
+	u64 n_out = 0, n_items = 0;
+	if (ne) {
+		k_c_survivors<<<grid(ne), 256, 0, c->stream>>>(G, c->s_keep.p, c->s_items.p, ctr + 3);
+		st.launches++;
+		OGB_TRY(exclusive_scan(c, c->s_keep.p, (u32)ne, c->s_epos.p, ctr + 5, nullptr, nullptr));
+		OGB_TRY(exclusive_scan(c, c->s_items.p, (u32)ne, c->s_lpos.p, ctr + 6, nullptr, nullptr));
+		st.launches += 6;
+		OGB_TRY(read_u64(c, ctr, h, 8));
+		n_out = h[5]; n_items = h[6];
+		for (u64 unfinished = n_items ? 1 : 0; unfinished;) {
+			if (st.jumps > 40) { ogb_set_error("ogb_graph_simplify: list ranking did not finish"); return OGB_E_STATE; }
+			CUDA_TRY(cudaMemsetAsync(ctr + 4, 0, sizeof(u64), c->stream));
+			k_c_jump<<<grid(nrec), 256, 0, c->stream>>>(G, ctr + 4);
+			CUDA_TRY(cudaGetLastError());
+			st.launches++; st.jumps++;
+			OGB_TRY(read_u64(c, ctr + 4, &unfinished, 1));
+		}
+		OGB_TRY(c->s_out.ensure(std::max<u64>(n_out, 1))); OGB_TRY(c->s_out_items.ensure(std::max<u64>(n_items, 1)));
+		k_c_emit_edges<<<grid(n), 256, 0, c->stream>>>(G, c->s_keep.p, c->s_epos.p, c->s_lpos.p, c->s_out.p);
+		if (n_items) k_c_emit_items<<<grid(nrec), 256, 0, c->stream>>>(G, c->s_lpos.p, c->s_out_items.p, ctr + 2);      // no items: no rope was ranked
+		CUDA_TRY(cudaGetLastError());
+		st.launches += 2;
+		OGB_TRY(read_u64(c, ctr, h, 8));
+		if (h[2]) { ogb_set_error("ogb_graph_simplify: %llu list records left unranked", (unsigned long long)h[2]); return OGB_E_STATE; }
+	}
+	CUDA_TRY(cudaEventRecord(c->ev[EV_T1], c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	CUDA_TRY(cudaEventElapsedTime(&st.ms, c->ev[EV_T0], c->ev[EV_T1]));
+	st.n_edges_out = n_out; st.n_items = n_items;
+	c->sst = st; c->have_simplified = true;
+	if (stats) *stats = st;
+	return OGB_OK;
+}
+
+extern "C" int ogb_graph_composite_edges(ogb_context *c, ogb_cedge *edges, uint64_t edge_cap, ogb_clist_item *items, uint64_t item_cap)
+{
+	if (!c) { ogb_set_error("ogb_graph_composite_edges: NULL context"); return OGB_E_ARG; }
+	if (!c->have_simplified) { ogb_set_error("ogb_graph_composite_edges: run ogb_graph_simplify first"); return OGB_E_STATE; }
+	const u64 ne = c->sst.n_edges_out, ni = c->sst.n_items;
+	if ((ne && (!edges || edge_cap < ne)) || (ni && (!items || item_cap < ni))) {
+		ogb_set_error("ogb_graph_composite_edges: need room for %llu edges and %llu list items", (unsigned long long)ne, (unsigned long long)ni);
+		return OGB_E_CAPACITY;
+	}
+	CUDA_TRY(cudaSetDevice(c->device));
+	if (ne) CUDA_TRY(cudaMemcpyAsync(edges, c->s_out.p, ne * sizeof(ogb_cedge), cudaMemcpyDeviceToHost, c->stream));
+	if (ni) CUDA_TRY(cudaMemcpyAsync(items, c->s_out_items.p, ni * sizeof(ogb_clist_item), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	return OGB_OK;
 }
 

@@ -7,26 +7,38 @@
 static bool byDestination(Edge *a, Edge *b) { return a->getDestinationRead()->getReadNumber() < b->getDestinationRead()->getReadNumber(); }
 static bool byOffset(Edge *a, Edge *b) { return a->getOverlapOffset() < b->getOverlapOffset(); }
 
+bool OverlapGraph::simplifyInBuild = true;
+
 OverlapGraph::OverlapGraph(void)
 	: dataSet(NULL), hashTable(NULL), graph(new vector<vector<Edge *> *>), numberOfNodes(0), numberOfEdges(0), hashStringLength(0), flowComputed(false)
 {
 	memset(&lastStats, 0, sizeof lastStats);
+	memset(&lastSimplifyStats, 0, sizeof lastSimplifyStats);
 }
 
 OverlapGraph::OverlapGraph(HashTable *ht)
 	: dataSet(NULL), hashTable(NULL), graph(new vector<vector<Edge *> *>), numberOfNodes(0), numberOfEdges(0), hashStringLength(0), flowComputed(false)
 {
 	memset(&lastStats, 0, sizeof lastStats);
+	memset(&lastSimplifyStats, 0, sizeof lastSimplifyStats);
 	buildOverlapGraphFromHashTable(ht);
 }
 
-OverlapGraph::~OverlapGraph()
+void OverlapGraph::clearGraph(void)
 {
 	for (size_t i = 0; i < graph->size(); i++) {
 		for (size_t j = 0; j < graph->at(i)->size(); j++) delete graph->at(i)->at(j);
 		delete graph->at(i);
 	}
+	graph->clear();
+	numberOfNodes = numberOfEdges = 0;
+}
+
+OverlapGraph::~OverlapGraph()
+{
+	clearGraph();
 	delete graph;
+	delete hashTable;														// only still there after a build that stopped at :210
 }
 
 // OverlapGraph.cpp:841-855
@@ -40,17 +52,12 @@ UINT8 OverlapGraph::twinEdgeOrientation(UINT8 orientation)
 // OverlapGraph.cpp:107-210 on the device.
 bool OverlapGraph::buildOverlapGraphFromHashTable(HashTable *ht)
 {
-	numberOfNodes = 0;
-	numberOfEdges = 0;
 	flowComputed = false;
+	if (hashTable != ht) delete hashTable;									// a table left over from a build that stopped at :210
 	hashTable = ht;
 	dataSet = ht->getDataset();
 	hashStringLength = ht->getHashStringLength();
-	for (size_t i = 0; i < graph->size(); i++) {
-		for (size_t j = 0; j < graph->at(i)->size(); j++) delete graph->at(i)->at(j);
-		delete graph->at(i);
-	}
-	graph->clear();
+	clearGraph();
 	graph->reserve(dataSet->getNumberOfUniqueReads() + 1);
 	for (UINT64 i = 0; i <= dataSet->getNumberOfUniqueReads(); i++) graph->push_back(new vector<Edge *>);	// :131-138
 
@@ -61,6 +68,8 @@ bool OverlapGraph::buildOverlapGraphFromHashTable(HashTable *ht)
 
 	ogb_context *ctx = ht->getContext();
 	ogbCheck(ogb_build_graph(ctx, 0), "OverlapGraph::buildOverlapGraphFromHashTable");	// :144-204
+	ogbCheck(ogb_get_stats(ctx, &lastStats), "OverlapGraph");
+	if (simplifyInBuild) return simplifyGraph();							// :211-215; the graph at :210 never leaves the device
 	uint64_t n = 0;
 	ogbCheck(ogb_graph_edge_count(ctx, 0, &n), "OverlapGraph");
 	void *pinned = NULL;
@@ -69,7 +78,37 @@ bool OverlapGraph::buildOverlapGraphFromHashTable(HashTable *ht)
 	if (rc == OGB_OK) materialise((const ogb_edge *)pinned, n);
 	ogb_free_host(pinned);
 	ogbCheck(rc, "OverlapGraph");
-	ogbCheck(ogb_get_stats(ctx, &lastStats), "OverlapGraph");
+	return true;															// the table (and its device context) stays until simplifyGraph() or the destructor
+}
+
+// OverlapGraph.cpp:211-215 on the device: do { contractCompositePaths(); removeDeadEndNodes(); } while (counter > 0), then the
+// Edge objects of the simplified graph -- composite edges with their three lists (Edge.h:30-32), linked to their reverse edges.
+bool OverlapGraph::simplifyGraph(void)
+{
+	if (!hashTable) throw OgbFailure(OGB_E_STATE, "simplifyGraph: the hash table (and its device context) has been freed");
+	ogb_context *ctx = hashTable->getContext();
+	ogbCheck(ogb_graph_simplify(ctx, &lastSimplifyStats), "OverlapGraph::simplifyGraph");
+	const uint64_t ne = lastSimplifyStats.n_edges_out, ni = lastSimplifyStats.n_items;
+	vector<ogb_cedge> edges(ne ? ne : 1);
+	vector<ogb_clist_item> items(ni ? ni : 1);
+	ogbCheck(ogb_graph_composite_edges(ctx, edges.data(), ne, items.data(), ni), "OverlapGraph::simplifyGraph");
+	const UINT64 nodes = graph->size();
+	clearGraph();
+	for (UINT64 i = 0; i < nodes; i++) graph->push_back(new vector<Edge *>);
+	vector<Edge *> objs(ne, (Edge *)NULL);
+	for (uint64_t e = 0; e < ne; e++) {
+		const ogb_cedge &x = edges[e];
+		vector<UINT64> *listReads = new vector<UINT64>(x.count);
+		vector<UINT16> *listOverlapOffsets = new vector<UINT16>(x.count);
+		vector<UINT8> *listOrientations = new vector<UINT8>(x.count);
+		for (uint32_t k = 0; k < x.count; k++) {
+			const ogb_clist_item &it = items[x.list_start + k];
+			listReads->at(k) = it.read; listOverlapOffsets->at(k) = it.offset; listOrientations->at(k) = it.orient;
+		}
+		objs[e] = new Edge(dataSet->getReadFromID(x.src), dataSet->getReadFromID(x.dst), x.orient, x.offset, listReads, listOverlapOffsets, listOrientations);
+		insertEdge(objs[e]);
+	}
+	for (uint64_t e = 0; e < ne; e++) objs[e]->setReverseEdge(objs[edges[e].twin]);
 	delete hashTable;														// :210 -- the graph owns and frees the table
 	hashTable = NULL;
 	return true;

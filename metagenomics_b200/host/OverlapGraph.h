@@ -1,11 +1,14 @@
 // OverlapGraph.h -- drop-in for the graph-construction half of MetaGenomics/OverlapGraph.h:32-76.
 //
 // OverlapGraph(HashTable*) runs the reference's buildOverlapGraphFromHashTable (OverlapGraph.cpp:
-// 107-210) on the GPU -- contained-read marking, window scan with exact verification, transitive
-// reduction -- and leaves exactly the state the reference has when it reaches `delete hashTable`
-// (:210): graph[1..N] of linked twin Edge objects, numberOfNodes / numberOfEdges, Read::superReadID,
-// mate-pair lists filled after containment marking, hash table freed. The host stages that follow in
-// the reference (contractCompositePaths ... calculateFlow) consume that state unchanged and are not
+// 107-215) on the GPU -- contained-read marking, window scan with exact verification, transitive
+// reduction, and the closing fix-point of contractCompositePaths + removeDeadEndNodes (:211-215) --
+// and leaves the state the reference has when the function returns: graph[1..N] of linked twin Edge
+// objects with their composite read lists, numberOfNodes / numberOfEdges, Read::superReadID, mate-pair
+// lists filled after containment marking, hash table freed. With OverlapGraph::simplifyInBuild = false
+// the build stops at `delete hashTable` (:210, the graph before the fix-point) and keeps the table's
+// device context until simplifyGraph() is called. The host stages that follow in the reference
+// (calculateFlow and the simplification loops of main.cpp) consume that state unchanged and are not
 // part of this library.
 //
 // The per-read member functions of the reference build (checkOverlap, insertAllEdgesOfRead,
@@ -35,13 +38,17 @@ class OverlapGraph
 		ogb_stats lastStats;
 		UINT8 twinEdgeOrientation(UINT8 orientation);
 		void materialise(const ogb_edge *edges, UINT64 n);
+		void clearGraph(void);
+		ogb_simplify_stats lastSimplifyStats;
 
 	public:
 		bool flowComputed;
+		static bool simplifyInBuild;					// true (default): the build ends with the fix-point of :211-215, like the reference's
 		OverlapGraph(void);
 		OverlapGraph(HashTable *ht);
 		~OverlapGraph();
 		bool buildOverlapGraphFromHashTable(HashTable *ht);
+		bool simplifyGraph(void);						// :211-215 on the device (only after a build with simplifyInBuild == false); frees the hash table
 		void markContainedReads(void);
 		bool checkOverlap(Read *read1, Read *read2, UINT64 orient, UINT64 start);
 		bool checkOverlapForContainedRead(Read *read1, Read *read2, UINT64 orient, UINT64 start);
@@ -60,6 +67,7 @@ class OverlapGraph
 		bool isEdgePresent(UINT64 source, UINT64 destination);
 		vector<vector<Edge *> *> *getGraph(void) { return graph; }
 		const ogb_stats &getBuildStats(void) const { return lastStats; }
+		const ogb_simplify_stats &getSimplifyStats(void) const { return lastSimplifyStats; }
 };
 
 #endif

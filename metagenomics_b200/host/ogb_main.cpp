@@ -118,18 +118,24 @@ int main(int argc, char **argv)
 			delete overlapGraph;
 			return 0;
 		}
+		if (dumpPath) OverlapGraph::simplifyInBuild = false;											// --dump wants the graph as it is at OverlapGraph.cpp:210
 		HashTable *hashTable = new HashTable();															// main.cpp:45
 		hashTable->insertDataset(dataSet, minimumOverlapLength);										// main.cpp:46
 		overlapGraph = new OverlapGraph(hashTable); //hashTable deleted by this function after building the graph (main.cpp:47)
 		if (allFileName != "") dataSet->saveReads(allFileName + "_sortedReads.fasta");					// main.cpp:48
-		if (dumpPath) dumpGraph(dumpPath, dataSet, overlapGraph, minimumOverlapLength);
+		if (dumpPath) {
+			dumpGraph(dumpPath, dataSet, overlapGraph, minimumOverlapLength);
+			overlapGraph->simplifyGraph();																// ... and then the rest of the constructor (:211-215)
+		}
 		if (matesPath) dumpMates(matesPath, dataSet);
 		overlapGraph->sortEdges();																		// main.cpp:49
-		if (allFileName != "") overlapGraph->saveGraphToFile(allFileName + ".unitig");					// main.cpp:50 (the graph at :210; the reference contracts first)
+		if (allFileName != "") overlapGraph->saveGraphToFile(allFileName + ".unitig");					// main.cpp:50
 		const ogb_stats &st = overlapGraph->getBuildStats();
+		const ogb_simplify_stats &ss = overlapGraph->getSimplifyStats();
 		cout << "reads: " << dataSet->getNumberOfReads() << " unique: " << dataSet->getNumberOfUniqueReads()
 		     << " nodes: " << overlapGraph->getNumberOfNodes() << " edges: " << overlapGraph->getNumberOfEdges()
-		     << " device ms: " << st.ms_total << endl;
+		     << " device ms: " << st.ms_total << " + simplification " << ss.ms << " (" << ss.merges << " merges, " << ss.dead_ends << " dead ends, "
+		     << ss.iterations << " iterations, " << ss.rounds << " rounds)" << endl;
 		delete dataSet;
 		delete overlapGraph;
 	} catch (const OgbFailure &e) {

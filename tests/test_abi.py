@@ -23,12 +23,15 @@ def test_every_declared_symbol_is_exported_and_bound():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/ogb.h but not exported by libogb.so"
     assert set(names) == set(PROTOTYPES), set(names) ^ set(PROTOTYPES)
-    assert lib().ogb_version() == 200
+    assert lib().ogb_version() == 210
 
 
 def test_struct_layout():
     from metagenomics_b200._lib import Edge, Stats
     assert C.sizeof(Edge) == 12 and Edge.offset.offset == 8 and Edge.orient.offset == 10
+    from metagenomics_b200._lib import SimplifyStats
+    from metagenomics_b200.api import CEDGE_DTYPE, CITEM_DTYPE
+    assert C.sizeof(SimplifyStats) == 5 * 8 + 4 * 4 + 4 + 4 and CEDGE_DTYPE.itemsize == 40 and CITEM_DTYPE.itemsize == 8
     assert C.sizeof(Stats) == 17 * 8 + 4 * 4 + 11 * 4 + 20 * 4 + 20 * 4 + 4      # 11 + 20 floats, 20 counters, padded to the 8-byte alignment of the struct
 
 

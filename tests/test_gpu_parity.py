@@ -159,6 +159,17 @@ def test_empty_and_tiny_inputs(ctx):
     assert_same_edges(edges_as_tuples(og.edges()), orc.edges(), "pair")
 
 
+def same_unitig_records(path, z, name):
+    """The .unitig file of the drop-in against the unmodified reference's graph after its fix-point (the c_* arrays of the
+    fixture): every record with source < destination, lists included; of a self-edge's twin pair the reference writes the one
+    with the lower heap address, so there either twin is accepted."""
+    from contract_lib import fixture_records, unitig_records
+    got, want = unitig_records(path), fixture_records(z)
+    assert [r for r in got if r[0] < r[1]] == [r for r in want if r[0] < r[1]], name
+    loops_got, loops_want = [r for r in got if r[0] == r[1]], [r for r in want if r[0] == r[1]]
+    assert all(r[0] <= r[1] for r in got) and 2 * len(loops_got) == len(loops_want) and set(loops_got) <= set(loops_want), name
+
+
 def test_cpp_dropin_matches_reference_dump(ctx, tmp_path):
     """The C++ drop-in classes (metagenomics_b200/host: Dataset, HashTable, OverlapGraph, Edge) driven
     exactly like MetaGenomics/main.cpp:33,45-47 by host/ogb_overlap produce the reference's dump."""
@@ -175,11 +186,19 @@ def test_cpp_dropin_matches_reference_dump(ctx, tmp_path):
         prefix = str(tmp_path / name)
         subprocess.run([exe, "-l", str(int(z["min_overlap"])), kind, "1", fa, "-f", prefix, "--dump", dump], check=True, timeout=120)
         d = read_dump(dump)
-        # main.cpp:48-50: the sorted reads and the .unitig file of the GPU-built graph; the resume path (main.cpp:36-42) reads it back
+        # main.cpp:48-50: the sorted reads and the .unitig file -- the graph after the fix-point of OverlapGraph.cpp:211-215, run on the
+        # device (--dump above is the graph at :210, then the driver finishes the constructor with simplifyGraph())
         assert os.path.exists(prefix + "_sortedReads.fasta") and os.path.exists(prefix + ".unitig")
+        same_unitig_records(prefix + ".unitig", z, name)
+        # without --dump the constructor runs the fix-point itself: same file
+        subprocess.run([exe, "-l", str(int(z["min_overlap"])), kind, "1", fa, "-f", prefix + "_b"], check=True, timeout=120)
+        assert open(prefix + "_b.unitig", "rb").read() == open(prefix + ".unitig", "rb").read(), name
+        # the resume path (main.cpp:36-42) reads the file back: both directions of every composite edge
         subprocess.run([exe, "-l", str(int(z["min_overlap"])), kind, "1", fa, "-f", prefix, "-s", "--dump", dump + "2"], check=True, timeout=120)
         d2 = read_dump(dump + "2")
-        assert np.array_equal(d2["edges"], d["edges"]) and d2["number_of_nodes"] == d["number_of_nodes"] and d2["number_of_edges"] == d["number_of_edges"], name
+        ce = z["c_edges"].astype(np.int64)
+        assert np.array_equal(d2["edges"], sort_tuples(np.stack([ce[:, 0], ce[:, 1], ce[:, 4], ce[:, 2]], axis=1))), name
+        assert d2["number_of_edges"] == int(z["c_number_of_edges"]) and d2["number_of_nodes"] == int(z["c_number_of_nodes"]), name
         assert d["n"] == len(z["sup"]) and np.array_equal(d["reads"]["fnv"], z["fnv"]), name
         assert np.array_equal(d["reads"]["sup"], z["sup"]) and np.array_equal(d["reads"]["freq"], z["freq"]), name
         assert np.array_equal(d["edges"], z["edges"]), name
@@ -312,3 +331,70 @@ def test_mate_lookup_entry_point(ctx):
     check(lib().ogb_mate_lookup(ctx._h, flat.ctypes.data, offs.ctypes.data, len(seqs), cfg["min_overlap"], ids.ctypes.data, ori.ctypes.data))
     assert ids.tolist() == [7, 7, 0, 0, 0]
     assert ori[0] == 1 and (ori[1] == 0 or first == datasets.rc(first))
+
+
+# ---- the simplification stage (OverlapGraph.cpp:211-215) ----
+
+def test_simplify_matches_reference_fixtures(ctx):
+    """contractCompositePaths + removeDeadEndNodes to the fix-point, on the device, against the unmodified reference's graph after
+    that stage (--dump2 fixtures): end points, orientation, offset and the read / offset / orientation lists of every edge."""
+    from contract_lib import check_twins, composite_records, fixture_records
+    files = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+    seen = 0
+    for f in files:
+        z = np.load(f)
+        if "c_edges" not in z.files:
+            continue
+        cfg = dict(bases=z["bases"], offsets=z["offsets"], min_overlap=int(z["min_overlap"]))
+        ds, ht, og = build_gpu(ctx, cfg, keep_pre=False)
+        edges, items, st = og.simplify()
+        assert composite_records(edges, items) == fixture_records(z), os.path.basename(f)
+        check_twins(edges)
+        assert st["n_edges_in"] == int(z["number_of_edges"]) and st["n_edges_out"] == len(z["c_edges"]) == int(z["c_number_of_edges"]), f
+        assert len(np.unique(edges["src"])) == int(z["c_number_of_nodes"]), f
+        # the graph of ogb_graph_edges is untouched, and a second run gives the same result
+        e2, i2, st2 = og.simplify()
+        assert np.array_equal(e2, edges) and np.array_equal(i2, items) and og.getNumberOfEdges() == int(z["number_of_edges"])
+        seen += 1
+    assert seen >= 6
+
+
+def test_simplify_seeded_sets_match_sequential_restatement(ctx):
+    """Beyond the fixtures: the adversarial sets (parallel chains between the same end nodes, tandem repeats, palindromes ...)
+    and samples of configs 1-5 against the sequential restatement (pinned to the reference by the CPU suite)."""
+    from contract_lib import check_twins, composite_records, load_oracle_module
+    from metagenomics_b200 import edges_as_tuples, synth
+    co = load_oracle_module("contract_oracle")
+    sets = datasets.adversarial() + [synth.config(2, scale=0.02), synth.config(3, scale=0.004), synth.config(1, scale=1.0),
+                                     synth.containment_stress(9, genome_len=9000, n_primary=2500), synth.config(4, scale=0.001), datasets.paired_mixed()]
+    for cfg in sets:
+        ds, ht, og = build_gpu(ctx, cfg, keep_pre=False)
+        t = edges_as_tuples(og.edges())
+        want = co.Graph(t.tolist(), ds.lengths().tolist()).simplify().edge_records()
+        edges, items, st = og.simplify()
+        assert composite_records(edges, items) == want, cfg["name"]
+        check_twins(edges)
+
+
+def test_simplify_config3_quarter_equals_kernel_bodies_on_cpu(ctx):
+    """2.1 M reads / 4.2 M edges: the launches on the device (thousands of nodes per round, races would show here) against the
+    same per-thread bodies run one after the other on the CPU (tests/contract_emul.cpp; the bodies are pinned to the reference
+    by tests/test_contract.py). Same deterministic output order, so the arrays must be identical. Plus the invariants of the
+    stage: a contracted read sits in exactly one edge pair and owns no edge, offsets add up."""
+    from contract_lib import build_emul, check_twins
+    from metagenomics_b200 import synth
+    cfg = synth.config(3, scale=0.25)
+    ds, ht, og = build_gpu(ctx, cfg, keep_pre=False)
+    fin = og.edges()
+    edges, items, st = og.simplify()
+    want_e, want_i, stats = build_emul()(None, ds.lengths(), presorted=fin)
+    assert st["merges"] == int(stats[0]) and st["dead_ends"] == int(stats[1]) and st["iterations"] == int(stats[2])
+    assert np.array_equal(edges, want_e) and np.array_equal(items, want_i)
+    check_twins(edges)
+    inside = items["read"]
+    reads, counts = np.unique(inside, return_counts=True)
+    assert (counts == 2).all()                                                  # once per direction
+    assert not np.isin(reads, edges["src"]).any()
+    sums = np.add.reduceat(items["offset"].astype(np.int64), edges["list_start"][edges["count"] > 0].astype(np.int64)) if len(items) else np.array([])
+    assert (sums <= edges["offset"][edges["count"] > 0].astype(np.int64)).all()
+    print("simplify config3@0.25:", st)
