@@ -287,7 +287,12 @@ typedef struct ogb_simplify_stats {
 	uint32_t rounds;              /* launches pairs of the contraction sweeps (see csrc/ogb_contract.cuh) */
 	uint32_t jumps;               /* pointer-jumping launches that ranked the read lists */
 	uint32_t launches;
-	float ms;                     /* device time of the whole stage */
+	float ms;                     /* device time of the whole stage = the four parts below */
+	float ms_setup;               /* rows, entries, twin links */
+	float ms_sweeps;              /* contraction rounds */
+	float ms_dead_ends;
+	float ms_lists;               /* survivors, scans, list ranking, output */
+	uint32_t reserved;
 } ogb_simplify_stats;
 
 /* Runs the fix-point on the graph ogb_build_graph left on the device (every rank holds the whole post-reduction list, so this

@@ -42,10 +42,11 @@ class Stats(C.Structure):
 class SimplifyStats(C.Structure):
     """ogb_simplify_stats (include/ogb.h)."""
     _fields_ = [(n, C.c_uint64) for n in ("n_edges_in", "n_edges_out", "n_items", "merges", "dead_ends")] + [
-        (n, C.c_uint32) for n in ("iterations", "rounds", "jumps", "launches")] + [("ms", C.c_float)]
+        (n, C.c_uint32) for n in ("iterations", "rounds", "jumps", "launches")] + [
+        (n, C.c_float) for n in ("ms", "ms_setup", "ms_sweeps", "ms_dead_ends", "ms_lists")] + [("reserved", C.c_uint32)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
 
 
 # every symbol include/ogb.h declares: name -> (restype, argtypes)

@@ -70,6 +70,7 @@ struct CGraph {
 	cu32 *rec_info;       // offset | orientation << 16 | OGB_C_REC_USED
 	uint8_t *state;       // n + 1: 1 = degree 2 and turn still to come in this sweep
 	cu32 *cp;             // 2 (n + 1): the node's two entries in this sweep
+	cu32 *blocker;        // n + 1: the node that made x wait when it was last checked (0 = none yet)
 	const cu64 *meta;     // read lengths as the read store keeps them (low 16 bits of meta[id-1]); null = all uniform_len
 	cu32 uniform_len;
 };
@@ -136,25 +137,34 @@ OGB_HD bool cb_candidate(cu32 x, const CGraph &G)
 	}
 	const bool in = k == 2;
 	G.state[x] = in ? 1 : 0;
-	if (in) { G.cp[2 * (cu64)x] = p[0]; G.cp[2 * (cu64)x + 1] = p[1]; }
+	if (in) { G.cp[2 * (cu64)x] = p[0]; G.cp[2 * (cu64)x + 1] = p[1]; G.blocker[x] = 0; }
 	return in;
 }
 
-OGB_HD bool c_row_blocks(const CGraph &G, cu32 F, cu32 x)
+// the node of degree 2 with a smaller index and its turn still to come that is F or a neighbour of F (0 = none)
+OGB_HD cu32 c_row_blocker(const CGraph &G, cu32 F, cu32 x)
 {
-	if (F < x && G.state[F]) return true;
+	if (F < x && G.state[F]) return F;
 	for (cu32 q = G.rowptr[F]; q < G.rowptr[F + 1]; q++) {
 		const CEntry &e = G.E[q];
-		if (e.valid && e.dst < x && G.state[e.dst]) return true;
+		if (e.valid && e.dst < x && G.state[e.dst]) return e.dst;
 	}
-	return false;
+	return 0;
 }
 
-// thread k = pending node list[k]: is it ready in this round? (reads only; the graph is not modified by this launch)
+// thread k = pending node list[k]: is it ready in this round? (reads the graph only; the launch does not modify it)
+// A node that had to wait remembers for whom: while that node's turn has not come it stays a far end or a neighbour of a far end of
+// x (neither x's far ends nor their rows can change without a contraction of a node that x waits for anyway), so x is still
+// blocked and the two rows need not be read again.
 OGB_HD bool cb_ready(cu32 x, const CGraph &G)
 {
+	const cu32 last = G.blocker[x];
+	if (last && G.state[last]) return false;
 	const cu32 A = G.E[G.cp[2 * (cu64)x]].dst, B = G.E[G.cp[2 * (cu64)x + 1]].dst;
-	return !(c_row_blocks(G, A, x) || c_row_blocks(G, B, x));
+	cu32 b = c_row_blocker(G, A, x);
+	if (!b) b = c_row_blocker(G, B, x);
+	if (b) G.blocker[x] = b;
+	return b == 0;
 }
 
 OGB_HD void c_rope_append(const CGraph &G, cu32 &h, cu32 &t, cu32 bh, cu32 bt)
@@ -321,13 +331,16 @@ __global__ void __launch_bounds__(256) k_c_candidates(CGraph G, cu32 *list, cu32
 		c_append(in, x, list, cursor);
 	}
 }
-__global__ void __launch_bounds__(256) k_c_ready(CGraph G, const cu32 *__restrict__ list, cu32 n_list, uint8_t *ready)
+// the length of the work list stays on the device (*n_list_p), so that several rounds can be queued without a host round trip
+__global__ void __launch_bounds__(256) k_c_ready(CGraph G, const cu32 *__restrict__ list, const cu32 *__restrict__ n_list_p, uint8_t *ready)
 {
+	const cu32 n_list = *n_list_p;
 	OGB_C_LOOP(k, n_list) ready[k] = cb_ready(list[k], G) ? 1 : 0;
 }
 // counters: [0] merges of the sweep
-__global__ void __launch_bounds__(256) k_c_turns(CGraph G, const cu32 *__restrict__ list, cu32 n_list, const uint8_t *__restrict__ ready, cu32 *next_list, cu32 *cursor, cu64 *counters)
+__global__ void __launch_bounds__(256) k_c_turns(CGraph G, const cu32 *__restrict__ list, const cu32 *__restrict__ n_list_p, const uint8_t *__restrict__ ready, cu32 *next_list, cu32 *cursor, cu64 *counters)
 {
+	const cu32 n_list = *n_list_p;
 	const cu64 total = ((cu64)n_list + 255) / 256 * 256;
 	OGB_C_LOOP(k, total) {
 		const bool live = k < n_list;

@@ -185,7 +185,7 @@ struct ogb_context {
 	// simplification (ogb_contract.cuh): CSR of entries, rope records, per-sweep work lists, the result
 	Pool<CEntry> sE;
 	Pool<CRec> s_rec;
-	Pool<u32> s_rowptr, s_cp, s_info, s_list, s_keep, s_items;
+	Pool<u32> s_rowptr, s_cp, s_info, s_list, s_keep, s_items, s_blocker;
 	Pool<uint8_t> s_state, s_ready, s_flag;
 	Pool<u64> s_epos, s_lpos, s_ctr;
 	Pool<ogb_cedge> s_out;
@@ -359,7 +359,7 @@ extern "C" void ogb_context_destroy(ogb_context *c)
 	c->slots.release(); c->summary.release(); c->sup.release(); c->contained.release(); c->pos.release();
 	c->sums.release(); c->surv.release(); c->cand.release(); c->big.release(); c->cntc.release(); c->cnt.release();
 	c->scratch_keys.release(); c->fin.release(); c->pre.release(); c->flush.release(); c->fin_stage.release();
-	c->sE.release(); c->s_rec.release(); c->s_rowptr.release(); c->s_cp.release(); c->s_info.release(); c->s_list.release(); c->s_keep.release(); c->s_items.release();
+	c->sE.release(); c->s_rec.release(); c->s_rowptr.release(); c->s_cp.release(); c->s_info.release(); c->s_list.release(); c->s_keep.release(); c->s_items.release(); c->s_blocker.release();
 	c->s_state.release(); c->s_ready.release(); c->s_flag.release(); c->s_epos.release(); c->s_lpos.release(); c->s_ctr.release(); c->s_out.release(); c->s_out_items.release();
 	if (c->d_ctr) cudaFree(c->d_ctr);
 	if (c->d_tot) cudaFree(c->d_tot);
@@ -1685,11 +1685,11 @@ extern "C" int ogb_graph_simplify(ogb_context *c, ogb_simplify_stats *stats)
 	const u64 nrec = 2 * ((u64)n + 1);
 	OGB_TRY(c->sE.ensure(std::max<u64>(ne, 1))); OGB_TRY(c->s_rec.ensure(nrec)); OGB_TRY(c->s_info.ensure(nrec)); OGB_TRY(c->s_cp.ensure(nrec));
 	OGB_TRY(c->s_rowptr.ensure((u64)n + 2)); OGB_TRY(c->s_list.ensure(2 * ((u64)n + 1))); OGB_TRY(c->s_keep.ensure(std::max<u64>(ne, 1))); OGB_TRY(c->s_items.ensure(std::max<u64>(ne, 1)));
-	OGB_TRY(c->s_state.ensure((u64)n + 1)); OGB_TRY(c->s_ready.ensure((u64)n + 1)); OGB_TRY(c->s_flag.ensure((u64)n + 2));
+	OGB_TRY(c->s_state.ensure((u64)n + 1)); OGB_TRY(c->s_ready.ensure((u64)n + 1)); OGB_TRY(c->s_flag.ensure((u64)n + 2)); OGB_TRY(c->s_blocker.ensure((u64)n + 1));
 	OGB_TRY(c->s_epos.ensure(ne + 1)); OGB_TRY(c->s_lpos.ensure(ne + 1)); OGB_TRY(c->s_ctr.ensure(16));
 	CGraph G;
 	G.E = c->sE.p; G.rowptr = c->s_rowptr.p; G.n = n; G.n_entries = ne; G.rec = c->s_rec.p; G.rec_info = c->s_info.p; G.state = c->s_state.p; G.cp = c->s_cp.p;
-	G.meta = c->uniform_len ? nullptr : c->meta.p; G.uniform_len = c->uniform_len;
+	G.meta = c->uniform_len ? nullptr : c->meta.p; G.uniform_len = c->uniform_len; G.blocker = c->s_blocker.p;
 	// counters (u64): [0] merges, [1] dead ends, [2] twin / ranking errors, [3] largest list, [4] unfinished ropes, [5] total edges, [6] total items; [8], [9]: the two list cursors (u32)
 	u64 *ctr = c->s_ctr.p;
 	u32 *cursor = reinterpret_cast<u32 *>(ctr + 8);
@@ -1712,9 +1712,13 @@ extern "C" int ogb_graph_simplify(ogb_context *c, ogb_simplify_stats *stats)
 	OGB_TRY(read_u64(c, ctr, h, 8));
 	if (h[2]) { ogb_set_error("ogb_graph_simplify: %llu edges without a twin", (unsigned long long)h[2]); return OGB_E_STATE; }
 	u32 *list[2] = {c->s_list.p, c->s_list.p + ((u64)n + 1)};
+	cudaEvent_t *tev = c->ev_pk;                                                 // free outside a build: [0] set-up done, then 3 per iteration
+	const u32 timed_iterations = 40;
+	CUDA_TRY(cudaEventRecord(tev[0], c->stream));
 	for (;;) {
 		if (ne == 0) break;
-		st.iterations++;
+		const u32 it = st.iterations++;
+		if (it < timed_iterations) CUDA_TRY(cudaEventRecord(tev[1 + 3 * it], c->stream));
 		CUDA_TRY(cudaMemsetAsync(ctr, 0, 2 * sizeof(u64), c->stream));
 		CUDA_TRY(cudaMemsetAsync(cursor, 0, 2 * sizeof(u32), c->stream));
 		k_c_candidates<<<grid(n), 256, 0, c->stream>>>(G, list[0], cursor);
@@ -1722,24 +1726,31 @@ extern "C" int ogb_graph_simplify(ogb_context *c, ogb_simplify_stats *stats)
 		u32 hc[2] = {0, 0};
 		CUDA_TRY(cudaMemcpyAsync(hc, cursor, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		u32 n_list = hc[0];
+		u32 bound = hc[0];                                                       // what the host knows: an upper bound of the work list's length
 		int cur = 0;
-		while (n_list) {
-			k_c_ready<<<grid(n_list), 256, 0, c->stream>>>(G, list[cur], n_list, c->s_ready.p);
-			CUDA_TRY(cudaMemsetAsync(cursor + (cur ^ 1), 0, sizeof(u32), c->stream));
-			k_c_turns<<<grid(n_list), 256, 0, c->stream>>>(G, list[cur], n_list, c->s_ready.p, list[cur ^ 1], cursor + (cur ^ 1), ctr);
+		while (bound) {
+			// the list's length lives on the device, so a few rounds are queued per host round trip (the list shrinks by ~20 % per round:
+			// the grids stay sized for `bound`); a round with an empty list is two empty launches
+			const int batch = bound > (1u << 20) ? 2 : (bound > (1u << 16) ? 4 : 8);
+			for (int r = 0; r < batch; r++) {
+				CUDA_TRY(cudaMemsetAsync(cursor + (cur ^ 1), 0, sizeof(u32), c->stream));
+				k_c_ready<<<grid(bound), 256, 0, c->stream>>>(G, list[cur], cursor + cur, c->s_ready.p);
+				k_c_turns<<<grid(bound), 256, 0, c->stream>>>(G, list[cur], cursor + cur, c->s_ready.p, list[cur ^ 1], cursor + (cur ^ 1), ctr);
+				st.launches += 2; st.rounds++;
+				cur ^= 1;
+			}
 			CUDA_TRY(cudaGetLastError());
-			st.launches += 2; st.rounds++;
 			CUDA_TRY(cudaMemcpyAsync(hc, cursor, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
 			CUDA_TRY(cudaStreamSynchronize(c->stream));
-			const u32 n_next = hc[cur ^ 1];
-			if (n_next >= n_list) { ogb_set_error("ogb_graph_simplify: a contraction round made no progress (%u nodes pending)", n_list); return OGB_E_STATE; }
-			n_list = n_next; cur ^= 1;
+			if (hc[cur] >= bound) { ogb_set_error("ogb_graph_simplify: contraction rounds made no progress (%u nodes pending)", bound); return OGB_E_STATE; }
+			bound = hc[cur];
 		}
+		if (it < timed_iterations) CUDA_TRY(cudaEventRecord(tev[2 + 3 * it], c->stream));
 		k_c_dead_ends<<<grid(n), 256, 0, c->stream>>>(G, c->s_flag.p, ctr);
 		k_c_dead_remove<<<grid(n), 256, 0, c->stream>>>(G, c->s_flag.p);
 		CUDA_TRY(cudaGetLastError());
 		st.launches += 2;
+		if (it < timed_iterations) CUDA_TRY(cudaEventRecord(tev[3 + 3 * it], c->stream));
 		OGB_TRY(read_u64(c, ctr, h, 2));
 		st.merges += h[0]; st.dead_ends += h[1];
 		if (h[0] + h[1] == 0) break;                                             // while (counter > 0)  (:215)
@@ -1773,6 +1784,14 @@ extern "C" int ogb_graph_simplify(ogb_context *c, ogb_simplify_stats *stats)
 	CUDA_TRY(cudaEventRecord(c->ev[EV_T1], c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	CUDA_TRY(cudaEventElapsedTime(&st.ms, c->ev[EV_T0], c->ev[EV_T1]));
+	CUDA_TRY(cudaEventElapsedTime(&st.ms_setup, c->ev[EV_T0], tev[0]));
+	for (u32 it = 0; it < std::min(st.iterations, timed_iterations); it++) {
+		float a = 0, b = 0;
+		CUDA_TRY(cudaEventElapsedTime(&a, tev[1 + 3 * it], tev[2 + 3 * it]));
+		CUDA_TRY(cudaEventElapsedTime(&b, tev[2 + 3 * it], tev[3 + 3 * it]));
+		st.ms_sweeps += a; st.ms_dead_ends += b;
+	}
+	st.ms_lists = st.ms - st.ms_setup - st.ms_sweeps - st.ms_dead_ends;
 	st.n_edges_out = n_out; st.n_items = n_items;
 	c->sst = st; c->have_simplified = true;
 	if (stats) *stats = st;

@@ -15,14 +15,14 @@ extern "C" int emul_simplify(const ogb_edge *fin, uint64_t ne, const uint16_t *l
                              ogb_clist_item **out_items, uint64_t *n_items, uint64_t *stats /* merges, dead ends, iterations, rounds, jumps */)
 {
 	std::vector<CEntry> E(ne ? ne : 1);
-	std::vector<cu32> rowptr((size_t)n + 2, 0), info(2 * ((size_t)n + 1), 0), cp(2 * ((size_t)n + 1), 0);
+	std::vector<cu32> rowptr((size_t)n + 2, 0), info(2 * ((size_t)n + 1), 0), cp(2 * ((size_t)n + 1), 0), blocker((size_t)n + 1, 0);
 	std::vector<CRec> rec(2 * ((size_t)n + 1));
 	std::vector<uint8_t> state((size_t)n + 1, 0), flag((size_t)n + 2, 0);
 	std::vector<cu64> meta(n ? n : 1);
 	for (uint32_t i = 0; i < n; i++) meta[i] = lens[i];
 	CGraph G;
 	G.E = E.data(); G.rowptr = rowptr.data(); G.n = n; G.n_entries = ne; G.rec = rec.data(); G.rec_info = info.data(); G.state = state.data(); G.cp = cp.data();
-	G.meta = meta.data(); G.uniform_len = 0;
+	G.meta = meta.data(); G.uniform_len = 0; G.blocker = blocker.data();
 	const cu64 nrec = 2 * ((cu64)n + 1);
 	for (cu64 r = 0; r < nrec; r++) { rec[r].next = OGB_C_NIL; rec[r].hops = 0; }
 	for (cu64 i = 0; i < ne; i++) cb_rowptr(i, fin, ne, n, rowptr.data());

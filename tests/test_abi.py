@@ -31,7 +31,7 @@ def test_struct_layout():
     assert C.sizeof(Edge) == 12 and Edge.offset.offset == 8 and Edge.orient.offset == 10
     from metagenomics_b200._lib import SimplifyStats
     from metagenomics_b200.api import CEDGE_DTYPE, CITEM_DTYPE
-    assert C.sizeof(SimplifyStats) == 5 * 8 + 4 * 4 + 4 + 4 and CEDGE_DTYPE.itemsize == 40 and CITEM_DTYPE.itemsize == 8
+    assert C.sizeof(SimplifyStats) == 5 * 8 + 4 * 4 + 5 * 4 + 4 and CEDGE_DTYPE.itemsize == 40 and CITEM_DTYPE.itemsize == 8
     assert C.sizeof(Stats) == 17 * 8 + 4 * 4 + 11 * 4 + 20 * 4 + 20 * 4 + 4      # 11 + 20 floats, 20 counters, padded to the 8-byte alignment of the struct
 
 
