@@ -141,15 +141,17 @@ OGB_HD bool cb_candidate(cu32 x, const CGraph &G)
 	return in;
 }
 
-// the node of degree 2 with a smaller index and its turn still to come that is F or a neighbour of F (0 = none)
+// the LARGEST node of degree 2 with an index below x and its turn still to come that is F or a neighbour of F (0 = none). Any such
+// node would do; the largest one tends to wait longest itself, so x re-reads its neighbourhood less often (2.5 instead of 3.0 full
+// checks per node at config 3)
 OGB_HD cu32 c_row_blocker(const CGraph &G, cu32 F, cu32 x)
 {
-	if (F < x && G.state[F]) return F;
+	cu32 b = (F < x && G.state[F]) ? F : 0;
 	for (cu32 q = G.rowptr[F]; q < G.rowptr[F + 1]; q++) {
 		const CEntry &e = G.E[q];
-		if (e.valid && e.dst < x && G.state[e.dst]) return e.dst;
+		if (e.valid && e.dst < x && e.dst > b && G.state[e.dst]) b = e.dst;
 	}
-	return 0;
+	return b;
 }
 
 // thread k = pending node list[k]: is it ready in this round? (reads the graph only; the launch does not modify it)
@@ -161,8 +163,7 @@ OGB_HD bool cb_ready(cu32 x, const CGraph &G)
 	const cu32 last = G.blocker[x];
 	if (last && G.state[last]) return false;
 	const cu32 A = G.E[G.cp[2 * (cu64)x]].dst, B = G.E[G.cp[2 * (cu64)x + 1]].dst;
-	cu32 b = c_row_blocker(G, A, x);
-	if (!b) b = c_row_blocker(G, B, x);
+	const cu32 ba = c_row_blocker(G, A, x), bb = c_row_blocker(G, B, x), b = ba > bb ? ba : bb;
 	if (b) G.blocker[x] = b;
 	return b == 0;
 }

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--tag", default="")
     ap.add_argument("--device-dataset", action="store_true")
+    ap.add_argument("--simplify", action="store_true", help="also run the simplification stage (OverlapGraph.cpp:211-215) on the last graph")
     a = ap.parse_args()
     import ctypes as C
     from metagenomics_b200 import Context, Dataset, HashTable, OverlapGraph, edges_as_tuples, synth
@@ -72,6 +73,10 @@ def main():
     print(f"[{a.tag or 'exp'}] config{a.config}@{a.scale} n={st['n_reads']} {verdict} | step {r[0]:.3f} ms | hash {r[1]:.3f} contain {r[2]:.3f} overlap {r[3]:.3f} "
           f"(scan {r[4]:.3f}, probe launch {r[5]:.4f} [window part {r[9]:.4f}] x{st['probe_launches']}) barrier {r[6]:.3f} mark {r[7]:.3f} reduce {r[8]:.3f} | "
           f"E_pre {st['edges_pre']} E_final {st['edges_final']} heavy {st['overflow_reads']} launches {st['kernel_launches']} | host setup {t_host:.1f} s", flush=True)
+    if a.simplify:
+        for _ in range(2):
+            edges, items, ss = og.simplify()
+        print(f"[{a.tag or 'exp'}] simplify: {ss}", flush=True)
     ctx.close()
 
 
