@@ -195,6 +195,7 @@ struct ogb_context {
 	// L2 persistence window on the bucket summary (l2_keep_summary)
 	const void *l2_window_ptr = nullptr;
 	size_t l2_window_bytes = 0;
+	bool l2_refused = false;
 	ogb_stats st = {};
 	u32 launches = 0;
 
@@ -779,37 +780,49 @@ extern "C" int ogb_dataset_finalize_device(ogb_dataset *ds, ogb_context *c, uint
 // The per-bucket summary is the one structure of K3 every window reads at random and that is small enough for L2 (4 bytes per
 // bucket: 34 MB at config 3), but the streams of the kernels around it (window queues, buckets, partner strands) keep evicting it:
 // k_window_part alone read 0.53 GB from DRAM per launch for a 34 MB array. An access-policy window on the scan stream makes its
-// sectors persisting in a set-aside part of L2 (hit ratio = what fits). The window is open from the end of K1 to the end of K3
-// only: K1's atomics on the summary got slower under it (1.80 -> 2.14 ms at config 3, 4.2 -> 8.7 ms with a 69 MB summary).
-// OGB_L2_PERSIST=0 turns it off.
+// sectors persisting in a set-aside part of L2 (hit ratio = what fits): 0.06 GB per launch, K3 17.1 -> 15.7 ms at config 3.
+// The window is open while K2 / K3 run only, and closing it also resets the persisting lines and takes the set-aside back: with
+// the set-aside left in place K1 of the next build went from 1.8 to 2.3 ms (4.3 -> 10.4 ms with a 69 MB summary), and neither
+// closing the window alone nor resetting the lines gives that back (profiles/r2/exp_l2_persist.txt). It is a hint: if the runtime
+// refuses any of the calls the context goes on without it. OGB_L2_PERSIST=0 turns it off.
 static int l2_keep_summary(ogb_context *c, bool enable)
 {
 	static int max_persist = -1, max_window = 0;
+	if (c->l2_refused) return OGB_OK;
 	if (max_persist < 0) {
 		cudaDeviceProp prop;
 		CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
 		max_persist = prop.persistingL2CacheMaxSize; max_window = prop.accessPolicyMaxWindowSize;
 	}
 	const char *e = getenv("OGB_L2_PERSIST");
-	const bool on = enable && c->use_summary && max_persist > 0 && !(e && atoi(e) == 0);
+	const bool on = enable && c->use_summary && max_persist > 0 && max_window > 0 && !(e && atoi(e) == 0);
 	const size_t bytes = on ? (size_t)c->nb * sizeof(u32) : 0, window = std::min<size_t>(bytes, (size_t)max_window);
 	const size_t set_aside = std::min<size_t>(window, (size_t)max_persist);
 	if (c->l2_window_ptr == (on ? (const void *)c->summary.p : nullptr) && c->l2_window_bytes == window) return OGB_OK;   // already so
-	// closing: the lines the window made persisting go back to normal and the set-aside part of L2 is handed back, or the kernels that
-	// follow run with what is left (K1 of the next build: 1.8 -> 2.3 ms at config 3, 4.3 -> 10.4 ms with a 69 MB summary)
 	cudaStreamAttrValue attr;
 	memset(&attr, 0, sizeof attr);
+	bool ok = true;
 	if (on) {
-		CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+		ok = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside) == cudaSuccess;
 		attr.accessPolicyWindow.base_ptr = c->summary.p;
 		attr.accessPolicyWindow.num_bytes = window;
-		attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)set_aside / (double)window);
+		attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)set_aside / (double)std::max<size_t>(window, 1));
 		attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
 		attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
 	}
 	else { attr.accessPolicyWindow.num_bytes = 0; attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal; attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal; }
-	CUDA_TRY(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-	if (!on && c->l2_window_ptr) { CUDA_TRY(cudaCtxResetPersistingL2Cache()); CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0)); }
+	ok = ok && cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+	if (!on && c->l2_window_ptr) ok = ok && cudaCtxResetPersistingL2Cache() == cudaSuccess && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) == cudaSuccess;
+	if (!ok) {                                                               // not an error of the build: go on with a plain L2
+		cudaGetLastError();
+		memset(&attr, 0, sizeof attr);
+		attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal; attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+		cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+		cudaGetLastError();
+		c->l2_refused = true; c->l2_window_ptr = nullptr; c->l2_window_bytes = 0;
+		return OGB_OK;
+	}
 	c->l2_window_ptr = on ? c->summary.p : nullptr; c->l2_window_bytes = window;
 	return OGB_OK;
 }
