@@ -506,6 +506,19 @@ def main():
                 times.append(ss.ms)
             simplify = dict(ss.as_dict(), ms=min(times[1:]), ms_runs=[round(float(x), 3) for x in times],
                             what="ogb_graph_simplify on the final graph of the last step, device time (CUDA events), result left on the device")
+            if gold is not None and "simplified" in gold:
+                # parity of the stage: counters of the fix-point and the checksum over every composite edge with its lists, against the
+                # golden of the sequential restatement (oracle/contract_seq.cpp via tests/golden/make_simplified_full_size.py)
+                from contract_lib import simplified_checksum
+                from metagenomics_b200.api import CEDGE_DTYPE, CITEM_DTYPE
+                ce, ci = np.zeros(ss.n_edges_out, dtype=CEDGE_DTYPE), np.zeros(ss.n_items, dtype=CITEM_DTYPE)
+                check(L.ogb_graph_composite_edges(ctx._h, ce.ctypes.data, len(ce), ci.ctypes.data, len(ci)))
+                w = gold["simplified"]
+                same = ((ss.n_edges_out, ss.n_items, ss.merges, ss.dead_ends, ss.iterations) == (w["n_edges"], w["n_items"], w["merges"], w["dead_ends"], w["iterations"])
+                        and simplified_checksum(ce, ci) == w["checksum"])
+                simplify["parity"] = "ok" if same else "MISMATCH"
+            else:
+                simplify["parity"] = "no golden"
         except Exception as e:                                   # auxiliary stage: reported, never fatal for the bench line
             simplify = {"error": str(e)}
 

@@ -99,3 +99,64 @@ def build_emul():
         lib.emul_free(pe); lib.emul_free(pi)
         return edges, items, stats
     return run
+
+
+# ---- the sequential C++ restatement (oracle/contract_seq.cpp) and the checksum of a simplified graph ----
+
+class _SeqResult(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_edges", "n_items", "merges", "dead_ends", "iterations", "ck_xor", "ck_sum")]
+
+
+def seq_simplify(edge_tuples, lens, arrays=True):
+    """oracle/libcontractseq.so: the reference's fix-point in its own sequential order. Returns (stats dict, edges, items): edges
+    (n, 6) uint64 [src, dst, orient, offset, count, list_start], items (m, 3) uint32 [read, offset, orientation] (None, None
+    without arrays); stats carries the order-independent checksum [ck_xor, ck_sum]."""
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "libcontractseq.so"))
+    lib.cseq_simplify.restype = C.c_int
+    lib.cseq_simplify.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(_SeqResult), C.c_void_p, C.c_void_p]
+    lib.cseq_free.argtypes = [C.c_void_p]
+    e = np.ascontiguousarray(np.asarray(edge_tuples).reshape(-1, 4), dtype=np.uint32)
+    lens = np.ascontiguousarray(lens, dtype=np.uint16)
+    res, pe, pi = _SeqResult(), C.c_void_p(), C.c_void_p()
+    rc = lib.cseq_simplify(e.ctypes.data, len(e), lens.ctypes.data, len(lens), C.byref(res), C.byref(pe) if arrays else None, C.byref(pi) if arrays else None)
+    assert rc == 0, rc
+    st = {n: int(getattr(res, n)) for n, _ in _SeqResult._fields_}
+    st["checksum"] = [st.pop("ck_xor"), st.pop("ck_sum")]
+    if not arrays:
+        return st, None, None
+    edges = np.frombuffer(C.string_at(pe.value, st["n_edges"] * 48), dtype=np.uint64).reshape(-1, 6).copy()
+    items = np.frombuffer(C.string_at(pi.value, st["n_items"] * 12), dtype=np.uint32).reshape(-1, 3).copy()
+    lib.cseq_free(pe); lib.cseq_free(pi)
+    return st, edges, items
+
+
+def seq_records(edges, items):
+    out = []
+    for s, d, o, off, k, a in edges.tolist():
+        out.append((s, d, o, off, tuple(items[a:a + k, 0].tolist()), tuple(items[a:a + k, 1].tolist()), tuple(items[a:a + k, 2].tolist())))
+    return sorted(out)
+
+
+def _mix(x):
+    x = x ^ (x >> np.uint64(29))
+    x = x * np.uint64(0xBF58476D1CE4E5B9)
+    return x ^ (x >> np.uint64(32))
+
+
+def simplified_checksum(edges, items):
+    """The figure of oracle/contract_seq.cpp (checksum_edge / checksum_item) for a simplified graph given as ogb_cedge /
+    ogb_clist_item arrays (metagenomics_b200.api CEDGE_DTYPE / CITEM_DTYPE): independent of the order of the edges, dependent
+    on the order inside every list. Lists must be laid out in edge order (list_start ascending), as the library returns them."""
+    K1, K2, K3, K4, K5 = (np.uint64(k) for k in (0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0x27D4EB2F165667C5, 0x94D049BB133111EB))
+    with np.errstate(over="ignore"):
+        cnt = edges["count"].astype(np.uint64)
+        start = edges["list_start"].astype(np.int64)
+        assert len(items) == int(cnt.sum()) and (len(edges) == 0 or (np.array_equal(start, np.concatenate([[0], np.cumsum(cnt.astype(np.int64))[:-1]]))))
+        pos = np.arange(len(items), dtype=np.int64) - np.repeat(start, cnt.astype(np.int64)) + 1
+        h = _mix(items["read"].astype(np.uint64) * K1 ^ items["offset"].astype(np.uint64) * K2 ^ items["orient"].astype(np.uint64) * K3 ^ pos.astype(np.uint64) * K4)
+        csum = np.concatenate([[np.uint64(0)], np.cumsum(h, dtype=np.uint64)])
+        list_sum = csum[start + cnt.astype(np.int64)] - csum[start]
+        eh = _mix(edges["src"].astype(np.uint64) * K1 ^ edges["dst"].astype(np.uint64) * K2 ^ edges["offset"].astype(np.uint64) * K3
+                  ^ edges["orient"].astype(np.uint64) * K4 ^ cnt * K5)
+        tot = _mix(eh + list_sum)
+        return [int(np.bitwise_xor.reduce(tot)) if len(tot) else 0, int(tot.sum(dtype=np.uint64))]

@@ -130,3 +130,34 @@ def test_random_graphs_all_formulations_agree(emul):
             check_twins(edges)
         merged += int(stats[0])
     assert merged > 1000
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_sequential_cpp_restatement_matches_reference(name, emul):
+    """oracle/contract_seq.cpp (the golden for BASELINE.json sizes) against the unmodified reference's fixtures, and its checksum
+    against the numpy form of the same figure computed on what the kernel bodies return."""
+    from contract_lib import seq_records, seq_simplify, simplified_checksum
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    if "c_edges" not in g.files:
+        pytest.skip("fixture predates the contracted dump")
+    st, edges, items = seq_simplify(g["edges"], g["len"])
+    assert seq_records(edges, items) == fixture_records(g)
+    ke, ki, _ = emul(g["edges"], g["len"])
+    assert simplified_checksum(ke, ki) == st["checksum"]
+    assert st["n_edges"] == len(ke) and st["n_items"] == len(ki)
+
+
+def test_kernel_bodies_match_sequential_restatement_at_scale(emul):
+    """Config 3 at a quarter (2.1 M reads, 4.25 M edges: hubs, parallel chains, thousands of ready nodes per round): the kernel bodies
+    against the sequential C++ restatement, by checksum and counters. OGB_TEST_FULL_SIZE=1: the whole of config 3."""
+    from contract_lib import edges_struct, seq_simplify, simplified_checksum
+    from oracle_lib import LeanOracle
+    from metagenomics_b200 import synth
+    cfg = synth.config(3, scale=1.0 if os.environ.get("OGB_TEST_FULL_SIZE") else 0.25)
+    o = LeanOracle(cfg["bases"], cfg["offsets"], cfg["min_overlap"]).run(keep_edges=True)
+    e, L = o.edges(), o.read_info()["len"]
+    st, _, _ = seq_simplify(e, L, arrays=False)
+    ke, ki, ks = emul(None, L, presorted=edges_struct(e))
+    assert (int(ks[0]), int(ks[1]), int(ks[2])) == (st["merges"], st["dead_ends"], st["iterations"])
+    assert (len(ke), len(ki)) == (st["n_edges"], st["n_items"])
+    assert simplified_checksum(ke, ki) == st["checksum"]

@@ -1,7 +1,8 @@
 """GPU, BASELINE.json sizes: the build at full configuration sizes, checked against golden counters
 and an order-independent checksum produced by the CPU oracle (three-phase form, 8 threads, run once in
 the build container: tests/golden/full_size.json) and through size-independent properties (twin
-symmetry, canonical order, idempotence)."""
+symmetry, canonical order, idempotence); and the simplification stage that follows (OverlapGraph.cpp:211-215) against
+the golden of its sequential restatement."""
 import json
 import os
 
@@ -50,6 +51,16 @@ def test_full_size_matches_oracle_checksum(gold):
         tw[:, 3] = np.array([3, 1, 2, 0], dtype=np.uint32)[t[:, 3]]
         tw[:, 2] = ((lens[t[:, 1] - 1] + t[:, 2].astype(np.int64) - lens[t[:, 0] - 1]) & 0xFFFF).astype(np.uint32)
         assert checksum(tw) == gold["checksum"]
+        # the simplification stage (OverlapGraph.cpp:211-215) against the sequential restatement's golden: counters of the fix-point and
+        # the checksum over every composite edge with its read / offset / orientation lists (tests/golden/make_simplified_full_size.py)
+        if "simplified" in gold:
+            from contract_lib import check_twins, simplified_checksum
+            want = gold["simplified"]
+            edges, items, sst = og.simplify()
+            assert (sst["n_edges_out"], sst["n_items"], sst["merges"], sst["dead_ends"], sst["iterations"]) == \
+                (want["n_edges"], want["n_items"], want["merges"], want["dead_ends"], want["iterations"])
+            assert simplified_checksum(edges, items) == want["checksum"]
+            check_twins(edges)
         og.buildOverlapGraphFromHashTable()                    # idempotence
         assert checksum(edges_as_tuples(og.edges())) == gold["checksum"]
     finally:
