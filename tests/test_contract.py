@@ -161,3 +161,23 @@ def test_kernel_bodies_match_sequential_restatement_at_scale(emul):
     assert (int(ks[0]), int(ks[1]), int(ks[2])) == (st["merges"], st["dead_ends"], st["iterations"])
     assert (len(ke), len(ki)) == (st["n_edges"], st["n_items"])
     assert simplified_checksum(ke, ki) == st["checksum"]
+
+
+def test_large_random_graphs_kernel_bodies_match_sequential_restatement(emul):
+    """Random multigraphs of up to 4000 nodes (long chains with random indices, hubs, parallel paths, cycles, self-loops, dead-end
+    tips): the kernel bodies, threads run forwards and backwards, against the sequential C++ restatement -- records, not checksums."""
+    from contract_lib import seq_records, seq_simplify, simplified_checksum
+    rng = np.random.default_rng(7)
+    deep = 0
+    for it in range(60):
+        n = int(rng.integers(200, 4000))
+        e, L = random_graph(rng, n, int(rng.integers(0, n // 2)), float(rng.uniform(0.9, 0.999)))
+        st, se, si = seq_simplify(e, L)
+        want = seq_records(se, si)
+        for reverse in (False, True):
+            ke, ki, ks = emul(e, L, reverse)
+            assert composite_records(ke, ki) == want, (it, reverse)
+            assert simplified_checksum(ke, ki) == st["checksum"]
+            assert (int(ks[0]), int(ks[1]), int(ks[2])) == (st["merges"], st["dead_ends"], st["iterations"])
+        deep += st["iterations"] > 3
+    assert deep > 5
